@@ -1,0 +1,188 @@
+"""Generate golden input/output fixtures by running the UNMODIFIED reference modules.
+
+Run in the build container (where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+It imports ``FNOModules`` / ``NIOModules`` read-only from the four reference
+directories (with a 3-line ``timm`` stub, which the 2-D ``NIOModules`` imports
+at module top but the hot path never uses), runs forward + backward in fp32 on
+the CPU with seeded inputs and weights, and writes ``tests/golden/*.npz``.
+Every fixture stores: inputs, the state_dict (minus the unused ``branch.*``
+encoder of NIOFP2D_FNO, 9.9 M floats the path never touches), outputs, the
+upstream gradient, and the gradient of every parameter autograd reached.
+Nothing from the reference is copied; only tensors it produced are stored.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("BLINDNO_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+_MODNAMES = ("NIOModules", "FNOModules", "DeepONetModules", "Baselines", "debug_tools", "model", "utils")
+
+
+def _timm_stub():
+    if "timm" in sys.modules:
+        return
+    timm = types.ModuleType("timm")
+    models = types.ModuleType("timm.models")
+    layers = types.ModuleType("timm.models.layers")
+    layers.trunc_normal_ = torch.nn.init.trunc_normal_
+    timm.models, models.layers = models, layers
+    sys.modules.update({"timm": timm, "timm.models": models, "timm.models.layers": layers})
+
+
+def load_reference(subdir: str, module: str):
+    """Import ``module`` from /root/reference/<subdir> with a clean module cache."""
+    _timm_stub()
+    for name in list(sys.modules):
+        if name.split(".")[0] in _MODNAMES:
+            del sys.modules[name]
+    path = os.path.join(REF, subdir)
+    sys.path.insert(0, path)
+    try:
+        return importlib.import_module(module)
+    finally:
+        sys.path.remove(path)
+
+
+def _np(t):
+    t = t.detach().cpu()
+    return t.numpy().copy()
+
+
+def _pack(prefix, named):
+    return {f"{prefix}{k}": _np(v) for k, v in named}
+
+
+def _save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(arrays)} arrays")
+
+
+def _run(module, args, gy_seed):
+    out = module(*args)
+    g = torch.Generator().manual_seed(gy_seed)
+    gy = torch.randn(out.shape, generator=g)
+    out.backward(gy)
+    return out, gy
+
+
+def _module_case(name, module, x, extra_args=(), skip=("branch.",), **meta):
+    x = x.clone().requires_grad_(True)
+    out, gy = _run(module, (x, *extra_args), 99)
+    params = [(k, v) for k, v in module.state_dict().items() if not k.startswith(skip)]
+    grads = [(k, p.grad) for k, p in module.named_parameters() if p.grad is not None and not k.startswith(skip)]
+    nograd = [k for k, p in module.named_parameters() if p.grad is None and not k.startswith(skip)]
+    _save(name, x=_np(x), y=_np(out), gy=_np(gy), gx=_np(x.grad),
+          nograd=np.array(nograd, dtype="U"),
+          **{f"meta.{k}": np.asarray(v) for k, v in meta.items()},
+          **_pack("p.", params), **_pack("g.", grads))
+
+
+def main():
+    torch.set_num_threads(1)
+    g = torch.Generator()
+
+    # ---- single spectral layers -------------------------------------------
+    F2 = load_reference("2d_FPE", "FNOModules")
+    torch.manual_seed(11)
+    _module_case("spectral2d_pair", F2.SpectralConv2d(3, 4, 3, 4),
+                 torch.randn(2, 3, 10, 12, generator=g.manual_seed(1)))
+    torch.manual_seed(12)
+    _module_case("spectral2d_pair_odd", F2.SpectralConv2d(2, 2, 4, 5),
+                 torch.randn(3, 2, 9, 11, generator=g.manual_seed(2)))
+    torch.manual_seed(13)
+    _module_case("spectral2d_pair_nyquist", F2.SpectralConv2d(2, 3, 4, 5),
+                 torch.randn(2, 2, 8, 8, generator=g.manual_seed(3)))
+
+    F1 = load_reference("1d_FPE", "FNOModules")
+    torch.manual_seed(14)
+    _module_case("spectral1d", F1.SpectralConv1d(3, 3, 5),
+                 torch.randn(2, 3, 20, generator=g.manual_seed(4)))
+    torch.manual_seed(15)
+    _module_case("spectral1d_odd", F1.SpectralConv1d(2, 4, 6),
+                 torch.randn(3, 2, 15, generator=g.manual_seed(5)))
+    torch.manual_seed(16)
+    _module_case("spectral2d_c64", F1.SpectralConv2d(3, 3, 3, 4),
+                 torch.randn(2, 3, 10, 12, generator=g.manual_seed(6)))
+
+    # ---- FNO nets ------------------------------------------------------------
+    torch.manual_seed(21)
+    _module_case("fno2d", F2.FNO2d(4, 5, 3, 3, 1),
+                 torch.randn(2, 13, 13, 3, generator=g.manual_seed(7)))
+    torch.manual_seed(22)
+    _module_case("fno2d_rect", F2.FNO2d(3, 4, 2, 2, 1),      # exercises the swapped crop (Q4)
+                 torch.randn(2, 12, 17, 2, generator=g.manual_seed(8)))
+    torch.manual_seed(23)
+    _module_case("fno1d", F1.FNO1d(5, 6, 3, 2, 2),
+                 torch.randn(3, 22, 2, generator=g.manual_seed(9)))       # round(5.5) -> 6
+    torch.manual_seed(24)
+    _module_case("fno1d_banker", F1.FNO1d(4, 3, 1, 1, 1),
+                 torch.randn(2, 10, 1, generator=g.manual_seed(10)))      # round(2.5) -> 2
+
+    # ---- whole NIO-FNO models -------------------------------------------------
+    def grid2d(n):
+        ax = np.linspace(-1, 1, n, dtype=np.float32)
+        gx, gy = np.meshgrid(ax, ax, indexing="ij")
+        return torch.tensor(np.stack([gx, gy], axis=2))
+
+    N2 = load_reference("2d_FPE", "NIOModules")
+    torch.manual_seed(31)
+    m = N2.NIOFP2D_FNO(2, 3, 100, 25, 2, 6, 5, 2).eval()
+    _module_case("niofp2d_fno_eval", m, torch.randn(2, 7, 20, 20, generator=g.manual_seed(11)),
+                 extra_args=(grid2d(20),), grid=grid2d(20).numpy())
+    m.train()
+    np.random.seed(5)
+    state = np.random.get_state()
+    n_keep = np.random.randint(50, 53)
+    idx = np.random.choice(53, n_keep)
+    np.random.set_state(state)
+    for prm in m.parameters():
+        prm.grad = None
+    _module_case("niofp2d_fno_train", m, torch.randn(1, 53, 20, 20, generator=g.manual_seed(12)),
+                 extra_args=(grid2d(20),), grid=grid2d(20).numpy(), np_seed=5, idx=idx)
+
+    NC = load_reference("2d_Non_conservative_FPE", "NIOModules")
+    torch.manual_seed(32)
+    m = NC.NIOFP2D_FNO(2, 3, 100, 25, 2, 5, 4, 2).eval()
+    _module_case("niofp2d_nc_fno_eval", m, torch.randn(2, 5, 20, 20, generator=g.manual_seed(13)),
+                 extra_args=(grid2d(20),), grid=grid2d(20).numpy())
+
+    N1 = load_reference("1d_FPE", "NIOModules")
+    torch.manual_seed(33)
+    grid1 = torch.linspace(0, 1, 40).unsqueeze(-1)
+    m = N1.NIOFP_FNO(2, 10, 7, 2, "cpu").train()
+    np.random.seed(6)
+    state = np.random.get_state()
+    n_keep = np.random.randint(50, 54)
+    idx = np.random.choice(54, n_keep)
+    np.random.set_state(state)
+    _module_case("niofp1d_fno_train", m, torch.randn(2, 54, 40, generator=g.manual_seed(14)),
+                 extra_args=(grid1,), grid=grid1.numpy(), np_seed=6, idx=idx)
+
+    NG = load_reference("1d_GPE", "NIOModules")
+    torch.manual_seed(34)
+    grid1 = torch.linspace(0, 1, 32).unsqueeze(-1)
+    m = NG.NIOFP_FNO(3, 8, 9, 1, "cpu").eval()
+    _module_case("niofp1d_gpe_fno_eval", m, torch.randn(2, 6, 32, generator=g.manual_seed(15)),
+                 extra_args=(grid1,), grid=grid1.numpy())
+
+    # ---- one default-shape spectral layer (heads: C=12, 76x76, m=32), weights from a seed
+    torch.manual_seed(41)
+    layer = F2.SpectralConv2d(12, 12, 32, 32)
+    x = torch.randn(1, 12, 76, 76, generator=g.manual_seed(16))
+    _save("spectral2d_default_head", y=_np(layer(x)), **{"meta.weight_seed": np.asarray(41),
+                                                         "meta.x_seed": np.asarray(16)})
+
+
+if __name__ == "__main__":
+    main()
