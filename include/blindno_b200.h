@@ -1,0 +1,198 @@
+/*
+ * blindno_b200.h -- C ABI of the B200 (sm_100a) NIO-FNO hot path.
+ *
+ * The reference (yl602019618/Reconstruction-of-PDE-without-Time-Label) is pure
+ * Python and has no FFI of its own: its "operator interface" for this path is
+ * the forward() of a handful of nn.Modules.  Each entry point below replaces
+ * the body of one of them (file:line relative to the reference tree) and is
+ * what a ctypes / cffi / pybind stub on the reference side binds (see
+ * INTEGRATION.md).  Plain pointers and sizes only, no torch types, no
+ * exceptions across the boundary.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - all tensors are dense fp32; "complex" means interleaved (re, im) pairs,
+ *     which is both torch.complex64 and the reference's [..., 2] float layout;
+ *   - activations inside an FNO are channels-first and zero padded:
+ *     [images, width, Hp, Wp] (1-D: Hp = 1);
+ *   - inputs are borrowed, outputs and workspaces are caller-owned;
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and
+ *     returns without synchronising;
+ *   - return value 0 = ok, negative = BdnStatus; bdn_last_error() gives text.
+ *   - re-entrant: the only shared state is the per-device plan cache (DFT
+ *     tables), guarded by a mutex.
+ */
+#ifndef BLINDNO_B200_H
+#define BLINDNO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDN_MAX_LAYERS 8
+#define BDN_ABI_VERSION 1
+
+typedef enum BdnStatus {
+  BDN_OK = 0,
+  BDN_ERR_INVALID = -1,     /* bad shape / null pointer / unsupported size      */
+  BDN_ERR_CUDA = -2,        /* a CUDA runtime call failed                         */
+  BDN_ERR_WORKSPACE = -3,   /* workspace too small                                */
+  BDN_ERR_UNSUPPORTED = -4  /* valid request this build cannot serve              */
+} BdnStatus;
+
+/* Arithmetic of the DFT GEMMs.  FP32 = CUDA-core FFMA (the 1e-5 parity mode);
+ * TF32 = tcgen05 tensor cores with TF32 operands, fp32 accumulation in TMEM
+ * (bound stated in DESIGN.md).  */
+typedef enum BdnPrecision { BDN_PREC_FP32 = 0, BDN_PREC_TF32 = 1 } BdnPrecision;
+
+/* ---------------------------------------------------------------------------
+ * Shape of one spectral convolution.
+ *   2-D: SpectralConv2d.forward  2d_FPE/FNOModules.py:156-178 (+ compl_mul2d :141-154)
+ *   1-D: SpectralConv1d.forward  1d_FPE/FNOModules.py:47-59   (hp = 1, m1 = 0, DC bin * 0.5)
+ * ------------------------------------------------------------------------- */
+typedef struct BdnSpectralShape {
+  int32_t ndim;      /* 1 or 2                                                    */
+  int32_t images;    /* B' = batch (x bag size when snapshots are folded in)      */
+  int32_t c_in;      /* input channels                                            */
+  int32_t c_out;     /* output channels                                           */
+  int32_t hp, wp;    /* transformed (already padded) extents; hp = 1 in 1-D       */
+  int32_t m1, m2;    /* kept modes: rows {0..m1-1} u {hp-m1..hp-1}, cols 0..m2-1;
+                        1-D: m1 = 0 and m2 = modes1                               */
+  int32_t prec;      /* BdnPrecision                                              */
+} BdnSpectralShape;
+
+/* y = spectral(x).  w1/w2: [c_in, c_out, m1, m2] complex (w2 NULL in 1-D, where
+ * w1 is [c_in, c_out, m2]).  xs_saved (optional, may be NULL): receives the kept
+ * spectrum of x, [images, c_in, K, m2] complex with K = 2*m1 (1-D: 1), which
+ * bdn_spectral_backward needs.  ws: bdn_spectral_workspace_bytes() bytes. */
+size_t bdn_spectral_workspace_bytes(const BdnSpectralShape* s);
+int bdn_spectral_forward(const BdnSpectralShape* s, const float* x, const float* w1, const float* w2,
+                         float* y, float* xs_saved, void* ws, size_t ws_bytes, void* stream);
+/* gx (may be NULL), gw1, gw2 are OVERWRITTEN (not accumulated). */
+int bdn_spectral_backward(const BdnSpectralShape* s, const float* gy, const float* xs_saved,
+                          const float* w1, const float* w2, float* gx, float* gw1, float* gw2,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * A whole FNO net: FNO1d.forward 1d_FPE/FNOModules.py:99-122,
+ *                  FNO2d.forward 2d_FPE/FNOModules.py:218-240.
+ * lift fc0 -> zero pad -> n_layers x [spectral + 1x1 conv (+ exact GELU except
+ * last)] -> crop -> fc1 -> GELU -> fc2.
+ * ------------------------------------------------------------------------- */
+typedef struct BdnFnoShape {
+  int32_t ndim;            /* 1 or 2                                              */
+  int32_t images;          /* B'                                                  */
+  int32_t c_in;            /* fc0 input features                                  */
+  int32_t width;           /* channel width C                                     */
+  int32_t c_out;           /* fc2 output features (FNO2d: always 1, Q3)           */
+  int32_t hidden;          /* fc1 output features (128 in the reference)          */
+  int32_t n_layers;        /* <= BDN_MAX_LAYERS                                   */
+  int32_t h, w;            /* unpadded grid (1-D: h = 1, w = N)                   */
+  int32_t hp, wp;          /* padded grid: h + round(h/4), w + round(w/4)         */
+  int32_t out_h, out_w;    /* cropped grid the projection runs on (Q4: the
+                              reference crops H by the W pad and W by the H pad)  */
+  int32_t m1, m2;          /* kept modes (1-D: m1 = 0)                            */
+  int32_t prec;            /* BdnPrecision                                        */
+} BdnFnoShape;
+
+typedef struct BdnFnoParams {      /* names = the reference state_dict keys       */
+  const float* fc0_w;              /* fc0.weight [width, c_in]                    */
+  const float* fc0_b;              /* fc0.bias   [width]                          */
+  const float* conv_w[BDN_MAX_LAYERS];   /* conv_list.k.weight [width, width(,1,1)] */
+  const float* conv_b[BDN_MAX_LAYERS];   /* conv_list.k.bias   [width]              */
+  const float* spec_w1[BDN_MAX_LAYERS];  /* spectral_list.k.weights1 (complex)      */
+  const float* spec_w2[BDN_MAX_LAYERS];  /* spectral_list.k.weights2 (2-D only)     */
+  const float* fc1_w;              /* fc1.weight [hidden, width]                  */
+  const float* fc1_b;              /* fc1.bias   [hidden]                         */
+  const float* fc2_w;              /* fc2.weight [c_out, hidden]                  */
+  const float* fc2_b;              /* fc2.bias   [c_out]                          */
+} BdnFnoParams;
+
+typedef struct BdnFnoGrads {       /* same shapes as BdnFnoParams; ACCUMULATED into
+                                      (+=), so the caller zeroes them (this is what
+                                      lets weight-grad kernels write straight into a
+                                      flat all-reduce buffer)                        */
+  float* fc0_w; float* fc0_b;
+  float* conv_w[BDN_MAX_LAYERS]; float* conv_b[BDN_MAX_LAYERS];
+  float* spec_w1[BDN_MAX_LAYERS]; float* spec_w2[BDN_MAX_LAYERS];
+  float* fc1_w; float* fc1_b; float* fc2_w; float* fc2_b;
+} BdnFnoGrads;
+
+/* Where the lift reads its input from.
+ *   x_cl != NULL : channels-last [images, h, w, c_in]               (FNO heads)
+ *   x_cl == NULL : the NIO-FNO per-snapshot input, never materialised:
+ *                  image (b, l) = concat(bags[b, idx[l]], grid), c_in = 1 + grid_dim
+ *                  (NIOFP2D_FNO.forward 2d_FPE/NIOModules.py:548-560,
+ *                   NIOFP_FNO.forward   1d_FPE/NIOModules.py:124-135)            */
+typedef struct BdnLiftInput {
+  const float* x_cl;
+  const float* bags;       /* [n_bags, bag_len, h, w]                             */
+  const int32_t* idx;      /* [n_keep] snapshot indices, NULL = identity          */
+  const float* grid;       /* [h, w, grid_dim]                                    */
+  int32_t n_bags, bag_len, n_keep, grid_dim;   /* images == n_bags * n_keep       */
+} BdnLiftInput;
+
+/* Buffers kept from forward to backward (caller-owned, sizes below). */
+size_t bdn_fno_act_floats(const BdnFnoShape* s);    /* z: (n_layers+1) x [images,width,hp,wp] */
+size_t bdn_fno_spec_floats(const BdnFnoShape* s);   /* xs: n_layers x [images,width,K,m2,2]   */
+size_t bdn_fno_workspace_bytes(const BdnFnoShape* s);
+
+/* out: [images, out_h, out_w, c_out] channels-last.  z_saved / xs_saved may be
+ * NULL for inference (then ws must be bdn_fno_workspace_bytes() + room for two
+ * activations, which bdn_fno_workspace_bytes already includes). */
+int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftInput* in,
+                    float* out, float* z_saved, float* xs_saved,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* g_out: [images, out_h, out_w, c_out]; or, when pooled_g != 0, the gradient of
+ * the bag mean [n_bags, out_h, out_w, c_out] which every snapshot of the bag
+ * receives scaled by 1/n_keep (backward of the mean in bag_pool_lift).
+ * gx_cl: [images, h, w, c_in] or NULL (the raw bags need no gradient). */
+int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftInput* in,
+                     const float* g_out, int32_t pooled_g, int32_t n_keep,
+                     const float* z_saved, const float* xs_saved,
+                     const BdnFnoGrads* grads, float* gx_cl,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Bag mean + lift: fc0([grid, mean_l s_l]) with fc0 detached
+ *   2d_FPE/NIOModules.py:564-575, 1d_FPE/NIOModules.py:139-149,
+ *   1d_GPE/NIOModules.py:209-219.
+ * s: [n_bags, n_keep, npix] per-snapshot scalars; grid: [npix, grid_dim];
+ * w0: [width, grid_dim + 1]; b0: [width]; out: [n_bags, npix, width].
+ * backward: gs[b, l, p] = (1/n_keep) * sum_j w0[j, grid_dim] * g[b, p, j]
+ * is produced in POOLED form gpool [n_bags, npix] (feed it to
+ * bdn_fno_backward with pooled_g = 1).
+ * ------------------------------------------------------------------------- */
+int bdn_bag_pool_lift_forward(const float* s, const float* grid, const float* w0, const float* b0,
+                              float* out, int32_t n_bags, int32_t n_keep, int32_t npix,
+                              int32_t grid_dim, int32_t width, void* stream);
+int bdn_bag_pool_lift_backward(const float* g, const float* w0, float* gpool,
+                               int32_t n_bags, int32_t npix, int32_t grid_dim, int32_t width,
+                               void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Optimiser step fused over a flat fp32 buffer (torch.optim.Adam semantics,
+ * 2d_FPE/train_fno.py:117; eps added after the bias-corrected sqrt, no
+ * weight decay / amsgrad).  step = 1-based step count.
+ * ------------------------------------------------------------------------- */
+int bdn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                  float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------
+ * misc
+ * ------------------------------------------------------------------------- */
+int bdn_abi_version(void);
+const char* bdn_last_error(void);          /* thread-local, valid until the next failing call */
+int bdn_pad_amount(int n);                 /* int(round(n / 4)) with Python's banker's rounding */
+int64_t bdn_kernel_launches(void);         /* kernels launched by this library so far (process-wide) */
+int bdn_device_sm_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLINDNO_B200_H */

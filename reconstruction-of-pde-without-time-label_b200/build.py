@@ -1,0 +1,69 @@
+"""Build libblindno_b200.so (hand-written sm_100a CUDA + the C ABI of include/blindno_b200.h).
+
+nvcc cross-compiles without a GPU; the .so is written in-tree (``lib/``) so that it travels
+to the GPU box with the repo snapshot.  ``python -m blindno_b200.build`` or
+``__graft_entry__.build()``.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIBPATH = os.path.join(LIBDIR, "libblindno_b200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+SOURCES = ["spectral.cu", "pointwise.cu", "tc_gemm.cu", "api.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libblindno_b200.so cannot be built")
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    files = sorted(os.listdir(CSRC)) + [os.path.join(INCLUDE, "blindno_b200.h")]
+    for f in files:
+        path = f if os.path.isabs(f) else os.path.join(CSRC, f)
+        with open(path, "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile if the sources changed since the last build.  Returns the .so path."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    stamp = os.path.join(LIBDIR, "build.stamp")
+    fp = _fingerprint()
+    if not force and os.path.exists(LIBPATH) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
+        return LIBPATH
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-o", LIBPATH, *srcs]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr, file=sys.stderr)
+    with open(stamp, "w") as fh:
+        fh.write(fp)
+    return LIBPATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

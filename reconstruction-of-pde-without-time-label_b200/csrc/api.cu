@@ -1,0 +1,442 @@
+// C ABI of libblindno_b200 (include/blindno_b200.h): plan cache, argument checking and the
+// host-side sequencing of the kernels of one FNO net / one spectral convolution.
+#include "../../include/blindno_b200.h"
+#include "bdn_internal.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+namespace bdn {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int check_cuda(const char* where) {
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(BDN_ERR_CUDA, "%s: %s", where, cudaGetErrorString(e));
+  }
+  return BDN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// plan cache
+// ---------------------------------------------------------------------------
+static std::mutex g_plan_mu;
+static std::map<std::tuple<int, int, int, int, int, int>, Plan*> g_plans;
+
+template <typename T>
+static T* upload(const std::vector<T>& v) {
+  if (v.empty()) return nullptr;
+  T* d = nullptr;
+  if (cudaMalloc(&d, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  return d;
+}
+
+static int round_up(int a, int m) { return (a + m - 1) / m * m; }
+
+const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  const auto key = std::make_tuple(dev, ndim, hp, wp, m1, m2);
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) return it->second;
+
+  Plan* pl = new Plan();
+  pl->ndim = ndim; pl->hp = hp; pl->wp = wp; pl->m1 = m1; pl->m2 = m2;
+  pl->K = ndim == 2 ? 2 * m1 : 1;
+  pl->Kp = round_up(pl->K, 8);
+  pl->hp8 = round_up(hp, 8);
+  pl->wp4 = round_up(wp, 4);
+  const double two_pi = 6.283185307179586476925286766559;
+
+  std::vector<float2> t_wl((size_t)wp * m2);
+  std::vector<float> t_cos((size_t)m2 * pl->wp4, 0.f), t_sin((size_t)m2 * pl->wp4, 0.f);
+  for (int w = 0; w < wp; ++w)
+    for (int l = 0; l < m2; ++l) {
+      const double th = two_pi * (double)(((long long)l * w) % wp) / (double)wp;
+      const float c = (float)std::cos(th), s = (float)std::sin(th);
+      t_wl[(size_t)w * m2 + l] = make_float2(c, s);
+      t_cos[(size_t)l * pl->wp4 + w] = c;
+      t_sin[(size_t)l * pl->wp4 + w] = s;
+    }
+  pl->t_wl = upload(t_wl);
+  pl->t_lw_cos = upload(t_cos);
+  pl->t_lw_sin = upload(t_sin);
+
+  pl->t_hk = nullptr; pl->t_kh = nullptr;
+  if (ndim == 2) {
+    std::vector<float2> t_hk((size_t)hp * pl->Kp, make_float2(0.f, 0.f));
+    std::vector<float2> t_kh((size_t)pl->K * pl->hp8, make_float2(0.f, 0.f));
+    for (int k = 0; k < pl->K; ++k) {
+      const int kk = k < m1 ? k : hp - 2 * m1 + k;
+      for (int h = 0; h < hp; ++h) {
+        const double ph = two_pi * (double)(((long long)kk * h) % hp) / (double)hp;
+        const float2 v = make_float2((float)std::cos(ph), (float)std::sin(ph));
+        t_hk[(size_t)h * pl->Kp + k] = v;
+        t_kh[(size_t)k * pl->hp8 + h] = v;
+      }
+    }
+    pl->t_hk = upload(t_hk);
+    pl->t_kh = upload(t_kh);
+  }
+  std::vector<float> col_fwd(m2), col_dc(m2, 1.f);
+  for (int l = 0; l < m2; ++l) {
+    const bool self_conj = l == 0 || (wp % 2 == 0 && l == wp / 2);
+    col_fwd[l] = (float)((self_conj ? 1.0 : 2.0) / ((double)hp * (double)wp));
+  }
+  if (ndim == 1) col_dc[0] = 0.5f;
+  pl->col_fwd = upload(col_fwd);
+  pl->col_dc = upload(col_dc);
+  pl->tc_fwd_b = nullptr; pl->tc_inv_b = nullptr;
+
+  if (!pl->t_wl || !pl->t_lw_cos || !pl->t_lw_sin || !pl->col_fwd || !pl->col_dc ||
+      (ndim == 2 && (!pl->t_hk || !pl->t_kh))) {
+    set_error(BDN_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete pl;
+    return nullptr;
+  }
+  g_plans[key] = pl;
+  return pl;
+}
+
+// ---------------------------------------------------------------------------
+// shape helpers
+// ---------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+static int check_modes(int ndim, int hp, int wp, int m1, int m2) {
+  if (ndim != 1 && ndim != 2) return set_error(BDN_ERR_INVALID, "ndim must be 1 or 2 (got %d)", ndim);
+  if (wp < 1 || hp < 1 || m2 < 1) return set_error(BDN_ERR_INVALID, "empty transform %dx%d modes %d", hp, wp, m2);
+  if (m2 > wp / 2 + 1) return set_error(BDN_ERR_INVALID, "modes2=%d exceeds wp/2+1=%d", m2, wp / 2 + 1);
+  if (ndim == 2 && (m1 < 1 || 2 * m1 > hp))
+    return set_error(BDN_ERR_INVALID, "2*modes1=%d exceeds hp=%d (row blocks would overlap)", 2 * m1, hp);
+  if (ndim == 1 && (hp != 1 || m1 != 0)) return set_error(BDN_ERR_INVALID, "1-D needs hp=1, m1=0");
+  if (m2 > 64) return set_error(BDN_ERR_UNSUPPORTED, "modes2=%d > 64 not built", m2);
+  return BDN_OK;
+}
+
+struct Carver {
+  char* p; size_t left;
+  void* take(size_t bytes) {
+    bytes = align_up(bytes);
+    if (bytes > left) return nullptr;
+    void* r = p; p += bytes; left -= bytes;
+    return r;
+  }
+};
+
+static size_t spec1_bytes(int images, int c, int hp, int m2) { return (size_t)images * c * hp * m2 * sizeof(float2); }
+static size_t kspec_bytes(int images, int c, int K, int m2) { return (size_t)images * c * K * m2 * sizeof(float2); }
+
+}  // namespace bdn
+
+using namespace bdn;
+
+extern "C" {
+
+int bdn_abi_version(void) { return BDN_ABI_VERSION; }
+const char* bdn_last_error(void) { return g_err; }
+int64_t bdn_kernel_launches(void) { return (int64_t)g_launches.load(); }
+
+int bdn_pad_amount(int n) {
+  // int(round(n * 0.25)) with round-half-to-even: n = 4q + r
+  const int q = n / 4, r = n % 4;
+  if (r < 2) return q;
+  if (r > 2) return q + 1;
+  return (q % 2 == 0) ? q : q + 1;   // exactly .5 -> nearest even
+}
+
+int bdn_device_sm_count(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return sms;
+}
+
+// ---------------------------------------------------------------------------
+// one spectral convolution
+// ---------------------------------------------------------------------------
+static int check_spectral(const BdnSpectralShape* s) {
+  if (!s) return set_error(BDN_ERR_INVALID, "null shape");
+  if (s->images < 0 || s->c_in < 1 || s->c_out < 1) return set_error(BDN_ERR_INVALID, "bad channel/batch counts");
+  return check_modes(s->ndim, s->hp, s->wp, s->m1, s->m2);
+}
+
+size_t bdn_spectral_workspace_bytes(const BdnSpectralShape* s) {
+  if (check_spectral(s) != BDN_OK) return 0;
+  const int K = s->ndim == 2 ? 2 * s->m1 : 1;
+  return align_up(spec1_bytes(s->images, s->c_in, s->hp, s->m2)) +
+         align_up(spec1_bytes(s->images, s->c_out, s->hp, s->m2)) +
+         align_up(kspec_bytes(s->images, s->c_out, K, s->m2)) + 256;
+}
+
+int bdn_spectral_forward(const BdnSpectralShape* s, const float* x, const float* w1, const float* w2, float* y,
+                         float* xs_saved, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_spectral(s);
+  if (rc != BDN_OK) return rc;
+  if (s->images == 0) return BDN_OK;
+  if (!x || !w1 || !y || !ws || (s->ndim == 2 && !w2)) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  if (s->prec != BDN_PREC_FP32) return set_error(BDN_ERR_UNSUPPORTED, "standalone spectral op is fp32 only");
+  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  if (!pl) return BDN_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv{(char*)ws, ws_bytes};
+  float2* X1 = (float2*)cv.take(spec1_bytes(s->images, s->c_in, s->hp, s->m2));
+  float2* Z = (float2*)cv.take(spec1_bytes(s->images, s->c_out, s->hp, s->m2));
+  if (!X1 || !Z) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+  launch_wfwd(pl, x, X1, s->images * s->c_in * s->hp, 0, st);
+  if (s->ndim == 2)
+    launch_core2d(pl, X1, Z, (float2*)xs_saved, (const float2*)w1, (const float2*)w2, s->images, s->c_in, s->c_out,
+                  false, st);
+  else
+    launch_mix1d(pl, X1, Z, (float2*)xs_saved, (const float2*)w1, s->images, s->c_in, s->c_out, false, st);
+  WinvArgs wa{};
+  wa.z = Z; wa.y = y; wa.images = s->images; wa.c = s->c_out;
+  launch_winv(pl, WINV_PLAIN, wa, st);
+  return check_cuda("bdn_spectral_forward");
+}
+
+int bdn_spectral_backward(const BdnSpectralShape* s, const float* gy, const float* xs_saved, const float* w1,
+                          const float* w2, float* gx, float* gw1, float* gw2, void* ws, size_t ws_bytes,
+                          void* stream) {
+  int rc = check_spectral(s);
+  if (rc != BDN_OK) return rc;
+  if (!gy || !xs_saved || !w1 || !gw1 || !ws || (s->ndim == 2 && (!w2 || !gw2)))
+    return set_error(BDN_ERR_INVALID, "null pointer argument");
+  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  if (!pl) return BDN_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = pl->K, m1r = s->ndim == 2 ? s->m1 : 1;
+  const size_t wbytes = (size_t)s->c_in * s->c_out * m1r * s->m2 * sizeof(float2);
+  cudaMemsetAsync(gw1, 0, wbytes, st);
+  if (s->ndim == 2) cudaMemsetAsync(gw2, 0, wbytes, st);
+  if (s->images == 0) return check_cuda("bdn_spectral_backward");
+  Carver cv{(char*)ws, ws_bytes};
+  float2* GZ = (float2*)cv.take(spec1_bytes(s->images, s->c_in, s->hp, s->m2));
+  float2* G1 = (float2*)cv.take(spec1_bytes(s->images, s->c_out, s->hp, s->m2));
+  float2* GY = (float2*)cv.take(kspec_bytes(s->images, s->c_out, K, s->m2));
+  if (!GZ || !G1 || !GY) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+  launch_wfwd(pl, gy, G1, s->images * s->c_out * s->hp, 0, st);
+  if (s->ndim == 2)
+    launch_core2d(pl, G1, GZ, GY, (const float2*)w1, (const float2*)w2, s->images, s->c_in, s->c_out, true, st);
+  else
+    launch_mix1d(pl, G1, GZ, GY, (const float2*)w1, s->images, s->c_in, s->c_out, true, st);
+  launch_gw_reduce(pl, (const float2*)xs_saved, GY, (float2*)gw1, (float2*)gw2, s->images, s->c_in, s->c_out, st);
+  if (gx) {
+    WinvArgs wa{};
+    wa.z = GZ; wa.y = gx; wa.images = s->images; wa.c = s->c_in;
+    launch_winv(pl, WINV_PLAIN, wa, st);
+  }
+  return check_cuda("bdn_spectral_backward");
+}
+
+// ---------------------------------------------------------------------------
+// a whole FNO net
+// ---------------------------------------------------------------------------
+static int check_fno(const BdnFnoShape* s) {
+  if (!s) return set_error(BDN_ERR_INVALID, "null shape");
+  if (s->images < 0 || s->c_in < 1 || s->width < 1 || s->c_out < 1 || s->hidden < 1)
+    return set_error(BDN_ERR_INVALID, "bad channel/batch counts");
+  if (s->n_layers < 1 || s->n_layers > BDN_MAX_LAYERS)
+    return set_error(BDN_ERR_INVALID, "n_layers=%d outside 1..%d", s->n_layers, BDN_MAX_LAYERS);
+  if (s->width > 32 || s->c_in > 32) return set_error(BDN_ERR_UNSUPPORTED, "width/c_in > 32 not built");
+  if (s->c_out > 4) return set_error(BDN_ERR_UNSUPPORTED, "c_out > 4 not built");
+  if (s->hidden > 512) return set_error(BDN_ERR_UNSUPPORTED, "hidden > 512 not built");
+  if (s->h < 1 || s->w < 1 || s->hp < s->h || s->wp < s->w) return set_error(BDN_ERR_INVALID, "bad grid/pad extents");
+  if (s->out_h < 1 || s->out_w < 1 || s->out_h > s->hp || s->out_w > s->wp)
+    return set_error(BDN_ERR_INVALID, "bad cropped extents %dx%d", s->out_h, s->out_w);
+  if (s->ndim == 1 && s->h != 1) return set_error(BDN_ERR_INVALID, "1-D needs h=1");
+  return check_modes(s->ndim, s->hp, s->wp, s->m1, s->m2);
+}
+
+static size_t act_floats1(const BdnFnoShape* s) { return (size_t)s->images * s->width * s->hp * s->wp; }
+static size_t kspec_floats1(const BdnFnoShape* s) {
+  const int K = s->ndim == 2 ? 2 * s->m1 : 1;
+  return (size_t)s->images * s->width * K * s->m2 * 2;
+}
+
+size_t bdn_fno_act_floats(const BdnFnoShape* s) {
+  return check_fno(s) == BDN_OK ? (size_t)(s->n_layers + 1) * act_floats1(s) : 0;
+}
+size_t bdn_fno_spec_floats(const BdnFnoShape* s) {
+  return check_fno(s) == BDN_OK ? (size_t)s->n_layers * kspec_floats1(s) : 0;
+}
+size_t bdn_fno_workspace_bytes(const BdnFnoShape* s) {
+  if (check_fno(s) != BDN_OK) return 0;
+  return 2 * align_up(spec1_bytes(s->images, s->width, s->hp, s->m2)) + 2 * align_up(act_floats1(s) * sizeof(float)) +
+         align_up(kspec_floats1(s) * sizeof(float)) + 256;
+}
+
+static LiftArgs make_lift(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftInput* in) {
+  LiftArgs a{};
+  a.x_cl = in->x_cl; a.bags = in->bags; a.idx = in->idx; a.grid = in->grid;
+  a.n_bags = in->n_bags; a.bag_len = in->bag_len; a.n_keep = in->n_keep; a.grid_dim = in->grid_dim;
+  a.w0 = p->fc0_w; a.b0 = p->fc0_b;
+  a.images = s->images; a.c_in = s->c_in; a.width = s->width;
+  a.h = s->h; a.w = s->w; a.hp = s->hp; a.wp = s->wp;
+  return a;
+}
+
+static int check_lift_input(const BdnFnoShape* s, const BdnLiftInput* in) {
+  if (!in) return set_error(BDN_ERR_INVALID, "null lift input");
+  if (in->x_cl) return BDN_OK;
+  if (!in->bags || !in->grid) return set_error(BDN_ERR_INVALID, "lift input: need x_cl or bags+grid");
+  if (in->n_bags * in->n_keep != s->images)
+    return set_error(BDN_ERR_INVALID, "n_bags*n_keep=%d != images=%d", in->n_bags * in->n_keep, s->images);
+  if (1 + in->grid_dim != s->c_in) return set_error(BDN_ERR_INVALID, "1+grid_dim=%d != c_in=%d", 1 + in->grid_dim, s->c_in);
+  if (in->idx == nullptr && in->n_keep != in->bag_len)
+    return set_error(BDN_ERR_INVALID, "idx is null but n_keep=%d != bag_len=%d", in->n_keep, in->bag_len);
+  return BDN_OK;
+}
+
+static ProjArgs make_proj(const BdnFnoShape* s, const BdnFnoParams* p, const float* z) {
+  ProjArgs a{};
+  a.z = z; a.w1 = p->fc1_w; a.b1 = p->fc1_b; a.w2 = p->fc2_w; a.b2 = p->fc2_b;
+  a.images = s->images; a.width = s->width; a.hidden = s->hidden; a.c_out = s->c_out;
+  a.hp = s->hp; a.wp = s->wp; a.out_h = s->out_h; a.out_w = s->out_w;
+  return a;
+}
+
+int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftInput* in, float* out, float* z_saved,
+                    float* xs_saved, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_fno(s);
+  if (rc != BDN_OK) return rc;
+  if (s->images == 0) return BDN_OK;
+  if (!p || !out || !ws) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  if ((rc = check_lift_input(s, in)) != BDN_OK) return rc;
+  if (s->prec != BDN_PREC_FP32 && s->prec != BDN_PREC_TF32) return set_error(BDN_ERR_INVALID, "bad precision");
+  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  if (!pl) return BDN_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t act = act_floats1(s), ksp = kspec_floats1(s);
+  Carver cv{(char*)ws, ws_bytes};
+  float2* X1 = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
+  float2* Z = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
+  float* zping[2] = {nullptr, nullptr};
+  if (!z_saved) {
+    zping[0] = (float*)cv.take(act * sizeof(float));
+    zping[1] = (float*)cv.take(act * sizeof(float));
+  }
+  if (!X1 || !Z || (!z_saved && (!zping[0] || !zping[1])))
+    return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+  auto zbuf = [&](int k) { return z_saved ? z_saved + (size_t)k * act : zping[k & 1]; };
+
+  launch_lift(make_lift(s, p, in), zbuf(0), st);
+  const int rows = s->images * s->width * s->hp;
+  for (int k = 0; k < s->n_layers; ++k) {
+    const int act_in = k > 0;
+    float2* xs_k = xs_saved ? (float2*)(xs_saved + (size_t)k * ksp) : nullptr;
+    launch_wfwd(pl, zbuf(k), X1, rows, act_in, st);
+    if (s->ndim == 2)
+      launch_core2d(pl, X1, Z, xs_k, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], s->images, s->width,
+                    s->width, false, st);
+    else
+      launch_mix1d(pl, X1, Z, xs_k, (const float2*)p->spec_w1[k], s->images, s->width, s->width, false, st);
+    WinvArgs wa{};
+    wa.z = Z; wa.y = zbuf(k + 1); wa.a = zbuf(k); wa.pw_w = p->conv_w[k]; wa.pw_b = p->conv_b[k];
+    wa.images = s->images; wa.c = s->width; wa.act_in = act_in;
+    launch_winv(pl, WINV_LAYER_FWD, wa, st);
+  }
+  launch_project(make_proj(s, p, zbuf(s->n_layers)), out, st);
+  return check_cuda("bdn_fno_forward");
+}
+
+int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftInput* in, const float* g_out,
+                     int32_t pooled_g, int32_t n_keep, const float* z_saved, const float* xs_saved,
+                     const BdnFnoGrads* g, float* gx_cl, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_fno(s);
+  if (rc != BDN_OK) return rc;
+  if (s->images == 0) return BDN_OK;
+  if (!p || !g_out || !z_saved || !xs_saved || !g || !ws) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  if ((rc = check_lift_input(s, in)) != BDN_OK) return rc;
+  if (pooled_g && (n_keep < 1 || s->images % n_keep != 0))
+    return set_error(BDN_ERR_INVALID, "pooled gradient: images=%d not a multiple of n_keep=%d", s->images, n_keep);
+  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  if (!pl) return BDN_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t act = act_floats1(s), ksp = kspec_floats1(s);
+  Carver cv{(char*)ws, ws_bytes};
+  float2* G1 = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
+  float2* GZ = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
+  float* gz[2];
+  gz[0] = (float*)cv.take(act * sizeof(float));
+  gz[1] = (float*)cv.take(act * sizeof(float));
+  float2* GY = (float2*)cv.take(ksp * sizeof(float));
+  if (!G1 || !GZ || !gz[0] || !gz[1] || !GY) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+
+  int cur = 0;
+  launch_project_bwd(make_proj(s, p, z_saved + (size_t)s->n_layers * act), g_out, pooled_g, n_keep, gz[cur], g->fc1_w,
+                     g->fc1_b, g->fc2_w, g->fc2_b, st);
+  const int rows = s->images * s->width * s->hp;
+  for (int k = s->n_layers - 1; k >= 0; --k) {
+    launch_wfwd(pl, gz[cur], G1, rows, 0, st);
+    if (s->ndim == 2)
+      launch_core2d(pl, G1, GZ, GY, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], s->images, s->width,
+                    s->width, true, st);
+    else
+      launch_mix1d(pl, G1, GZ, GY, (const float2*)p->spec_w1[k], s->images, s->width, s->width, true, st);
+    launch_gw_reduce(pl, (const float2*)(xs_saved + (size_t)k * ksp), GY, (float2*)g->spec_w1[k],
+                     (float2*)g->spec_w2[k], s->images, s->width, s->width, st);
+    WinvArgs wa{};
+    wa.z = GZ; wa.y = gz[cur ^ 1]; wa.a = gz[cur]; wa.zin = z_saved + (size_t)k * act;
+    wa.pw_w = p->conv_w[k]; wa.g_pw_w = g->conv_w[k]; wa.g_pw_b = g->conv_b[k];
+    wa.images = s->images; wa.c = s->width; wa.act_in = k > 0;
+    launch_winv(pl, WINV_LAYER_BWD, wa, st);
+    cur ^= 1;
+  }
+  launch_lift_bwd(make_lift(s, p, in), gz[cur], g->fc0_w, g->fc0_b, gx_cl, st);
+  return check_cuda("bdn_fno_backward");
+}
+
+// ---------------------------------------------------------------------------
+// bag pool, optimiser
+// ---------------------------------------------------------------------------
+int bdn_bag_pool_lift_forward(const float* s, const float* grid, const float* w0, const float* b0, float* out,
+                              int32_t n_bags, int32_t n_keep, int32_t npix, int32_t grid_dim, int32_t width,
+                              void* stream) {
+  if (!s || !grid || !w0 || !b0 || !out) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  if (n_bags < 0 || n_keep < 1 || npix < 1 || grid_dim < 1 || width < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
+  if (n_bags == 0) return BDN_OK;
+  launch_pool_lift(s, grid, w0, b0, out, n_bags, n_keep, npix, grid_dim, width, (cudaStream_t)stream);
+  return check_cuda("bdn_bag_pool_lift_forward");
+}
+
+int bdn_bag_pool_lift_backward(const float* g, const float* w0, float* gpool, int32_t n_bags, int32_t npix,
+                               int32_t grid_dim, int32_t width, void* stream) {
+  if (!g || !w0 || !gpool) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  if (n_bags < 0 || npix < 1 || grid_dim < 1 || width < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
+  if (n_bags == 0) return BDN_OK;
+  launch_pool_lift_bwd(g, w0, gpool, n_bags, npix, grid_dim, width, (cudaStream_t)stream);
+  return check_cuda("bdn_bag_pool_lift_backward");
+}
+
+int bdn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                  float beta2, float eps, int32_t step, float grad_scale, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  if (step < 1) return set_error(BDN_ERR_INVALID, "step must be >= 1");
+  if (n == 0) return BDN_OK;
+  launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
+  return check_cuda("bdn_adam_step");
+}
+
+}  // extern "C"

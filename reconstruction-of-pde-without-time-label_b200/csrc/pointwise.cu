@@ -1,0 +1,473 @@
+// Per-pixel stages of the FNO nets and the snapshot-bag pool, fp32.
+//   lift (+ zero pad)            FNO2d.forward 2d_FPE/FNOModules.py:219-224, FNO1d.forward :103-106
+//   crop + fc1 -> GELU -> fc2    FNO2d.forward :234-239, FNO1d.forward :116-121
+//   bag mean + detached fc0      NIOFP2D_FNO.forward 2d_FPE/NIOModules.py:564-575
+// The per-snapshot input concat(snapshot, grid) of NIO-FNO (2d_FPE/NIOModules.py:555-560) and the
+// bag gather x[:, idx] (:548-551) are folded into the lift's addressing; the [B*L, n, n, 128] hidden
+// tensor of the projection lives in registers only and is recomputed in backward.
+#include "bdn_internal.cuh"
+
+namespace bdn {
+
+// ===========================================================================
+// lift: z0[img, c, hp, wp] = (h < H && w < W) ? b0[c] + sum_i W0[c][i] * in_i : 0
+// ===========================================================================
+struct LiftParams {
+  const float* x_cl; const float* bags; const int32_t* idx; const float* grid;
+  int n_keep, bag_len, grid_dim;
+  const float* w0; const float* b0;
+  int images, c_in, width, h, w, hp, wp;
+};
+
+__device__ __forceinline__ void lift_fetch(const LiftParams& p, int img, int pix, float* in) {
+  if (p.x_cl != nullptr) {
+    const float* src = p.x_cl + ((size_t)img * p.h * p.w + pix) * p.c_in;
+    for (int i = 0; i < p.c_in; ++i) in[i] = __ldg(src + i);
+  } else {
+    const int b = img / p.n_keep, l = img - b * p.n_keep;
+    const int snap = p.idx != nullptr ? __ldg(p.idx + l) : l;
+    in[0] = __ldg(p.bags + ((size_t)b * p.bag_len + snap) * p.h * p.w + pix);
+    for (int d = 0; d < p.grid_dim; ++d) in[1 + d] = __ldg(p.grid + (size_t)pix * p.grid_dim + d);
+  }
+}
+
+constexpr int LIFT_MAX_CIN = 32;
+
+__global__ void __launch_bounds__(256) lift_kernel(const LiftParams p, float* __restrict__ z0) {
+  extern __shared__ float smem[];
+  float* ws = smem;                        // [width][c_in]
+  float* bs = smem + p.width * p.c_in;     // [width]
+  for (int i = threadIdx.x; i < p.width * p.c_in; i += blockDim.x) ws[i] = __ldg(p.w0 + i);
+  for (int i = threadIdx.x; i < p.width; i += blockDim.x) bs[i] = __ldg(p.b0 + i);
+  __syncthreads();
+  const int plane = p.hp * p.wp;
+  const long total = (long)p.images * plane;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int img = t / plane, q = t - (long)img * plane;
+    const int hh = q / p.wp, ww = q - hh * p.wp;
+    float* dst = z0 + (size_t)img * p.width * plane + q;
+    if (hh < p.h && ww < p.w) {
+      float in[LIFT_MAX_CIN];
+      lift_fetch(p, img, hh * p.w + ww, in);
+      for (int c = 0; c < p.width; ++c) {
+        float acc = bs[c];
+        for (int i = 0; i < p.c_in; ++i) acc = fmaf(ws[c * p.c_in + i], in[i], acc);
+        dst[(size_t)c * plane] = acc;
+      }
+    } else {
+      for (int c = 0; c < p.width; ++c) dst[(size_t)c * plane] = 0.f;
+    }
+  }
+}
+
+static LiftParams make_lift_params(const LiftArgs& a) {
+  LiftParams p;
+  p.x_cl = a.x_cl; p.bags = a.bags; p.idx = a.idx; p.grid = a.grid;
+  p.n_keep = a.n_keep; p.bag_len = a.bag_len; p.grid_dim = a.grid_dim;
+  p.w0 = a.w0; p.b0 = a.b0;
+  p.images = a.images; p.c_in = a.c_in; p.width = a.width; p.h = a.h; p.w = a.w; p.hp = a.hp; p.wp = a.wp;
+  return p;
+}
+
+void launch_lift(const LiftArgs& a, float* z0, cudaStream_t st) {
+  const LiftParams p = make_lift_params(a);
+  const long total = (long)a.images * a.hp * a.wp;
+  const int block = 256;
+  const int grid = (int)((total + block - 1) / block);
+  const size_t smem = (size_t)(a.width * a.c_in + a.width) * sizeof(float);
+  lift_kernel<<<grid, block, smem, st>>>(p, z0);
+  count_launch();
+}
+
+// lift backward: g_w0[c][i] += sum gz0[c] * in_i, g_b0[c] += sum gz0[c], gx_cl[.., i] = sum_c W0[c][i] gz0[c]
+// A block stages a tile of TP pixels (gz0 for all channels, the inputs) and reduces the outer product.
+__global__ void __launch_bounds__(256) lift_bwd_kernel(const LiftParams p, const float* __restrict__ gz0,
+                                                       float* g_w0, float* g_b0, float* __restrict__ gx_cl,
+                                                       int tiles_per_block) {
+  constexpr int TP = 256;
+  extern __shared__ float smem[];
+  const int C = p.width, CI = p.c_in;
+  float* gs = smem;                  // [C][TP]
+  float* xs = gs + C * TP;           // [CI][TP]
+  float* ws = xs + CI * TP;          // [C][CI]
+  float* acc = ws + C * CI;          // [C*CI + C]
+  const int npair = C * CI + C;
+  for (int i = threadIdx.x; i < C * CI; i += blockDim.x) ws[i] = __ldg(p.w0 + i);
+  for (int i = threadIdx.x; i < npair; i += blockDim.x) acc[i] = 0.f;
+  const int plane = p.hp * p.wp, hw = p.h * p.w;
+  const long total = (long)p.images * hw;
+  const int sub = blockDim.x / npair > 0 ? blockDim.x / npair : 1;   // pixel sub-slices per pair
+  for (int it = 0; it < tiles_per_block; ++it) {
+    const long t0 = ((long)blockIdx.x * tiles_per_block + it) * TP;
+    if (t0 >= total) break;
+    __syncthreads();
+    {
+      const int tp = threadIdx.x;      // TP == blockDim.x
+      const long t = t0 + tp;
+      float in[LIFT_MAX_CIN];
+      if (t < total) {
+        const int img = t / hw, pix = t - (long)img * hw;
+        const int hh = pix / p.w, ww = pix - hh * p.w;
+        lift_fetch(p, img, pix, in);
+        const float* g = gz0 + (size_t)img * C * plane + hh * p.wp + ww;
+        float gx[LIFT_MAX_CIN];
+        for (int i = 0; i < CI; ++i) gx[i] = 0.f;
+        for (int c = 0; c < C; ++c) {
+          const float gv = __ldg(g + (size_t)c * plane);
+          gs[c * TP + tp] = gv;
+          if (gx_cl != nullptr)
+            for (int i = 0; i < CI; ++i) gx[i] = fmaf(ws[c * CI + i], gv, gx[i]);
+        }
+        for (int i = 0; i < CI; ++i) xs[i * TP + tp] = in[i];
+        if (gx_cl != nullptr)
+          for (int i = 0; i < CI; ++i) gx_cl[(size_t)t * CI + i] = gx[i];
+      } else {
+        for (int c = 0; c < C; ++c) gs[c * TP + tp] = 0.f;
+        for (int i = 0; i < CI; ++i) xs[i * TP + tp] = 0.f;
+      }
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < npair * sub; item += blockDim.x) {
+      const int pair = item % npair, sl = item / npair;
+      const int lo = sl * TP / sub, hi = (sl + 1) * TP / sub;
+      float s = 0.f;
+      if (pair < C * CI) {
+        const float* g = gs + (pair / CI) * TP;
+        const float* x = xs + (pair % CI) * TP;
+        for (int q = lo; q < hi; ++q) s = fmaf(g[q], x[q], s);
+      } else {
+        const float* g = gs + (pair - C * CI) * TP;
+        for (int q = lo; q < hi; ++q) s += g[q];
+      }
+      atomicAdd(acc + pair, s);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npair; i += blockDim.x)
+    atomicAdd(i < C * CI ? g_w0 + i : g_b0 + (i - C * CI), acc[i]);
+}
+
+void launch_lift_bwd(const LiftArgs& a, const float* gz0, float* g_w0, float* g_b0, float* gx_cl,
+                     cudaStream_t st) {
+  const LiftParams p = make_lift_params(a);
+  const long total = (long)a.images * a.h * a.w;
+  const int tiles = (int)((total + 255) / 256);
+  int tpb = 1;
+  while (ceil_div(tiles, tpb) > 8 * 148) ++tpb;
+  const int grid = ceil_div(tiles, tpb);
+  const size_t smem = (size_t)((a.width + a.c_in) * 256 + 2 * a.width * a.c_in + a.width) * sizeof(float);
+  cudaFuncSetAttribute(lift_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  lift_bwd_kernel<<<grid, 256, smem, st>>>(p, gz0, g_w0, g_b0, gx_cl, tpb);
+  count_launch();
+}
+
+// ===========================================================================
+// projection: out[pix, o] = b2[o] + sum_j W2[o][j] * gelu(b1[j] + sum_c W1[j][c] * z[c, pix])
+// One thread per pixel of the cropped window; weights broadcast from shared memory.
+// ===========================================================================
+constexpr int PROJ_MAX_OUT = 4;
+
+template <int CP>   // width rounded up to a multiple of 4
+__global__ void __launch_bounds__(128) project_kernel(const ProjArgs a, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  float* w1s = smem;                               // [hidden][CP]
+  float* b1s = w1s + a.hidden * CP;                // [hidden]
+  float* w2s = b1s + a.hidden;                     // [c_out][hidden]
+  for (int i = threadIdx.x; i < a.hidden * CP; i += blockDim.x) {
+    const int j = i / CP, c = i - j * CP;
+    w1s[i] = c < a.width ? __ldg(a.w1 + j * a.width + c) : 0.f;
+  }
+  for (int i = threadIdx.x; i < a.hidden; i += blockDim.x) b1s[i] = __ldg(a.b1 + i);
+  for (int i = threadIdx.x; i < a.c_out * a.hidden; i += blockDim.x) w2s[i] = __ldg(a.w2 + i);
+  __syncthreads();
+  const int opix = a.out_h * a.out_w, plane = a.hp * a.wp;
+  const long total = (long)a.images * opix;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int img = t / opix, q = t - (long)img * opix;
+    const int oh = q / a.out_w, ow = q - oh * a.out_w;
+    const float* zp = a.z + (size_t)img * a.width * plane + oh * a.wp + ow;
+    float z[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) z[c] = c < a.width ? __ldg(zp + (size_t)c * plane) : 0.f;
+    float o[PROJ_MAX_OUT];
+#pragma unroll
+    for (int k = 0; k < PROJ_MAX_OUT; ++k) o[k] = k < a.c_out ? __ldg(a.b2 + k) : 0.f;
+    for (int j = 0; j < a.hidden; ++j) {
+      float hsum = b1s[j];
+#pragma unroll
+      for (int c4 = 0; c4 < CP; c4 += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(w1s + j * CP + c4);
+        hsum = fmaf(wv.x, z[c4], fmaf(wv.y, z[c4 + 1], fmaf(wv.z, z[c4 + 2], fmaf(wv.w, z[c4 + 3], hsum))));
+      }
+      const float g = gelu_exact(hsum);
+#pragma unroll
+      for (int k = 0; k < PROJ_MAX_OUT; ++k)
+        if (k < a.c_out) o[k] = fmaf(w2s[k * a.hidden + j], g, o[k]);
+    }
+    for (int k = 0; k < a.c_out; ++k) out[(size_t)t * a.c_out + k] = o[k];
+  }
+}
+
+template <typename F>
+static bool dispatch_cp(int width, F&& f) {
+  const int cp = (width + 3) & ~3;
+  switch (cp) {
+    case 4: f(std::integral_constant<int, 4>()); return true;
+    case 8: f(std::integral_constant<int, 8>()); return true;
+    case 12: f(std::integral_constant<int, 12>()); return true;
+    case 16: f(std::integral_constant<int, 16>()); return true;
+    case 20: f(std::integral_constant<int, 20>()); return true;
+    case 24: f(std::integral_constant<int, 24>()); return true;
+    case 28: f(std::integral_constant<int, 28>()); return true;
+    case 32: f(std::integral_constant<int, 32>()); return true;
+    default: return false;
+  }
+}
+
+void launch_project(const ProjArgs& a, float* out, cudaStream_t st) {
+  const long total = (long)a.images * a.out_h * a.out_w;
+  const int block = 128;
+  const int grid = (int)((total + block - 1) / block);
+  dispatch_cp(a.width, [&](auto cp) {
+    constexpr int CP = decltype(cp)::value;
+    const size_t smem = (size_t)(a.hidden * CP + a.hidden + a.c_out * a.hidden) * sizeof(float);
+    cudaFuncSetAttribute(project_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    project_kernel<CP><<<grid, block, smem, st>>>(a, out);
+  });
+  count_launch();
+}
+
+// projection backward.  Each thread owns PP pixels; for every hidden unit j it recomputes the
+// pre-activation, accumulates gz in registers and warp-reduces the weight-gradient partials into
+// per-block shared accumulators, flushed once per block with atomics.
+template <int CP, int PP>
+__global__ void __launch_bounds__(128) project_bwd_kernel(const ProjArgs a, const float* __restrict__ g_out,
+                                                          int pooled_g, int n_keep, float* __restrict__ gz,
+                                                          float* g_w1, float* g_b1, float* g_w2, float* g_b2,
+                                                          int tiles_per_block) {
+  extern __shared__ __align__(16) float smem[];
+  const int hidden = a.hidden, nout = a.c_out;
+  float* w1s = smem;                       // [hidden][CP]
+  float* b1s = w1s + hidden * CP;          // [hidden]
+  float* w2s = b1s + hidden;               // [nout][hidden]
+  float* aw1 = w2s + nout * hidden;        // [hidden][CP]  accumulators
+  float* ab1 = aw1 + hidden * CP;          // [hidden]
+  float* aw2 = ab1 + hidden;               // [nout][hidden]
+  float* ab2 = aw2 + nout * hidden;        // [PROJ_MAX_OUT]
+  for (int i = threadIdx.x; i < hidden * CP; i += blockDim.x) {
+    const int j = i / CP, c = i - j * CP;
+    w1s[i] = c < a.width ? __ldg(a.w1 + j * a.width + c) : 0.f;
+    aw1[i] = 0.f;
+  }
+  for (int i = threadIdx.x; i < hidden; i += blockDim.x) { b1s[i] = __ldg(a.b1 + i); ab1[i] = 0.f; }
+  for (int i = threadIdx.x; i < nout * hidden; i += blockDim.x) { w2s[i] = __ldg(a.w2 + i); aw2[i] = 0.f; }
+  if (threadIdx.x < PROJ_MAX_OUT) ab2[threadIdx.x] = 0.f;
+  __syncthreads();
+
+  const int opix = a.out_h * a.out_w, plane = a.hp * a.wp;
+  const long total = (long)a.images * opix;
+  const int lane = threadIdx.x & 31;
+  const float gscale = pooled_g ? 1.0f / (float)n_keep : 1.0f;
+  const int tile = blockDim.x * PP;
+
+  for (int it = 0; it < tiles_per_block; ++it) {
+    const long base = ((long)blockIdx.x * tiles_per_block + it) * tile;
+    if (base >= total) break;
+    float z[PP][CP], g[PP][PROJ_MAX_OUT], gzr[PP][CP];
+    size_t zoff[PP];
+    bool live[PP];
+#pragma unroll
+    for (int pp = 0; pp < PP; ++pp) {
+      const long t = base + (long)pp * blockDim.x + threadIdx.x;
+      live[pp] = t < total;
+      zoff[pp] = 0;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) { z[pp][c] = 0.f; gzr[pp][c] = 0.f; }
+#pragma unroll
+      for (int k = 0; k < PROJ_MAX_OUT; ++k) g[pp][k] = 0.f;
+      if (live[pp]) {
+        const int img = t / opix, q = t - (long)img * opix;
+        const int oh = q / a.out_w, ow = q - oh * a.out_w;
+        zoff[pp] = (size_t)img * a.width * plane + oh * a.wp + ow;
+#pragma unroll
+        for (int c = 0; c < CP; ++c)
+          if (c < a.width) z[pp][c] = __ldg(a.z + zoff[pp] + (size_t)c * plane);
+        const size_t goff = pooled_g ? ((size_t)(img / n_keep) * opix + q) * nout : (size_t)t * nout;
+        for (int k = 0; k < nout; ++k) g[pp][k] = __ldg(g_out + goff + k) * gscale;
+      }
+    }
+    float sb2[PROJ_MAX_OUT];
+#pragma unroll
+    for (int k = 0; k < PROJ_MAX_OUT; ++k) {
+      sb2[k] = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < PP; ++pp) sb2[k] += g[pp][k];
+    }
+    for (int j = 0; j < hidden; ++j) {
+      float w1r[CP];
+#pragma unroll
+      for (int c4 = 0; c4 < CP; c4 += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(w1s + j * CP + c4);
+        w1r[c4] = wv.x; w1r[c4 + 1] = wv.y; w1r[c4 + 2] = wv.z; w1r[c4 + 3] = wv.w;
+      }
+      const float b1j = b1s[j];
+      float w2r[PROJ_MAX_OUT];
+#pragma unroll
+      for (int k = 0; k < PROJ_MAX_OUT; ++k) w2r[k] = k < nout ? w2s[k * hidden + j] : 0.f;
+      float sw1[CP], sb1 = 0.f, sw2[PROJ_MAX_OUT];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) sw1[c] = 0.f;
+#pragma unroll
+      for (int k = 0; k < PROJ_MAX_OUT; ++k) sw2[k] = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < PP; ++pp) {
+        float hsum = b1j;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) hsum = fmaf(w1r[c], z[pp][c], hsum);
+        const float cdf = 0.5f * (1.0f + erff(hsum * 0.70710678118654752440f));
+        const float pdf = 0.39894228040143267794f * expf(-0.5f * hsum * hsum);
+        const float gel = hsum * cdf;
+        float d = 0.f;
+#pragma unroll
+        for (int k = 0; k < PROJ_MAX_OUT; ++k) { d = fmaf(g[pp][k], w2r[k], d); sw2[k] = fmaf(g[pp][k], gel, sw2[k]); }
+        const float e = d * (cdf + hsum * pdf);
+        sb1 += e;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) { gzr[pp][c] = fmaf(e, w1r[c], gzr[pp][c]); sw1[c] = fmaf(e, z[pp][c], sw1[c]); }
+      }
+#pragma unroll
+      for (int c = 0; c < CP; ++c) sw1[c] = warp_sum(sw1[c]);
+      sb1 = warp_sum(sb1);
+#pragma unroll
+      for (int k = 0; k < PROJ_MAX_OUT; ++k)
+        if (k < nout) sw2[k] = warp_sum(sw2[k]);
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) atomicAdd(aw1 + j * CP + c, sw1[c]);
+        atomicAdd(ab1 + j, sb1);
+#pragma unroll
+        for (int k = 0; k < PROJ_MAX_OUT; ++k)
+          if (k < nout) atomicAdd(aw2 + k * hidden + j, sw2[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PROJ_MAX_OUT; ++k) {
+      if (k < nout) {
+        const float s = warp_sum(sb2[k]);
+        if (lane == 0) atomicAdd(ab2 + k, s);
+      }
+    }
+#pragma unroll
+    for (int pp = 0; pp < PP; ++pp) {
+      if (!live[pp]) continue;
+#pragma unroll
+      for (int c = 0; c < CP; ++c)
+        if (c < a.width) gz[zoff[pp] + (size_t)c * plane] = gzr[pp][c];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < hidden * CP; i += blockDim.x) {
+    const int j = i / CP, c = i - j * CP;
+    if (c < a.width) atomicAdd(g_w1 + j * a.width + c, aw1[i]);
+  }
+  for (int i = threadIdx.x; i < hidden; i += blockDim.x) atomicAdd(g_b1 + i, ab1[i]);
+  for (int i = threadIdx.x; i < nout * hidden; i += blockDim.x) atomicAdd(g_w2 + i, aw2[i]);
+  if (threadIdx.x < nout) atomicAdd(g_b2 + threadIdx.x, ab2[threadIdx.x]);
+}
+
+void launch_project_bwd(const ProjArgs& a, const float* g_out, int pooled_g, int n_keep, float* gz, float* g_w1,
+                        float* g_b1, float* g_w2, float* g_b2, cudaStream_t st) {
+  const size_t act_bytes = (size_t)a.images * a.width * a.hp * a.wp * sizeof(float);
+  cudaMemsetAsync(gz, 0, act_bytes, st);
+  const long total = (long)a.images * a.out_h * a.out_w;
+  dispatch_cp(a.width, [&](auto cp) {
+    constexpr int CP = decltype(cp)::value;
+    constexpr int PP = CP <= 4 ? 4 : (CP <= 12 ? 2 : 1);
+    const int tile = 128 * PP;
+    const int tiles = (int)((total + tile - 1) / tile);
+    int tpb = 1;
+    while (ceil_div(tiles, tpb) > 6 * 148) ++tpb;
+    const int grid = ceil_div(tiles, tpb);
+    const size_t smem =
+        (size_t)(2 * (a.hidden * CP + a.hidden + a.c_out * a.hidden) + PROJ_MAX_OUT) * sizeof(float);
+    cudaFuncSetAttribute(project_bwd_kernel<CP, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    project_bwd_kernel<CP, PP><<<grid, 128, smem, st>>>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, tpb);
+  });
+  count_launch();
+}
+
+// ===========================================================================
+// bag mean + detached lift
+// ===========================================================================
+__global__ void pool_lift_kernel(const float* __restrict__ s, const float* __restrict__ grid,
+                                 const float* __restrict__ w0, const float* __restrict__ b0,
+                                 float* __restrict__ out, int n_bags, int n_keep, int npix, int gd, int width) {
+  const long total = (long)n_bags * npix;
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int b = t / npix, pix = t - (long)b * npix;
+  const float* sp = s + (size_t)b * n_keep * npix + pix;
+  float acc = 0.f;
+  for (int l = 0; l < n_keep; ++l) acc += __ldg(sp + (size_t)l * npix);
+  const float mean = acc / (float)n_keep;
+  for (int j = 0; j < width; ++j) {
+    float v = __ldg(b0 + j);
+    for (int d = 0; d < gd; ++d) v = fmaf(__ldg(w0 + j * (gd + 1) + d), __ldg(grid + (size_t)pix * gd + d), v);
+    out[(size_t)t * width + j] = fmaf(__ldg(w0 + j * (gd + 1) + gd), mean, v);
+  }
+}
+
+void launch_pool_lift(const float* s, const float* grid, const float* w0, const float* b0, float* out, int n_bags,
+                      int n_keep, int npix, int grid_dim, int width, cudaStream_t st) {
+  const long total = (long)n_bags * npix;
+  const int block = 64;
+  pool_lift_kernel<<<(int)((total + block - 1) / block), block, 0, st>>>(s, grid, w0, b0, out, n_bags, n_keep, npix,
+                                                                         grid_dim, width);
+  count_launch();
+}
+
+__global__ void pool_lift_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w0,
+                                     float* __restrict__ gpool, long total, int gd, int width) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  float acc = 0.f;
+  for (int j = 0; j < width; ++j) acc = fmaf(__ldg(w0 + j * (gd + 1) + gd), __ldg(g + (size_t)t * width + j), acc);
+  gpool[t] = acc;
+}
+
+void launch_pool_lift_bwd(const float* g, const float* w0, float* gpool, int n_bags, int npix, int grid_dim,
+                          int width, cudaStream_t st) {
+  const long total = (long)n_bags * npix;
+  const int block = 128;
+  pool_lift_bwd_kernel<<<(int)((total + block - 1) / block), block, 0, st>>>(g, w0, gpool, total, grid_dim, width);
+  count_launch();
+}
+
+// ===========================================================================
+// Adam over a flat buffer (torch.optim.Adam defaults: no weight decay, no amsgrad)
+// ===========================================================================
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float grad_scale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+void launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
+                 int step, float grad_scale, cudaStream_t st) {
+  const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+  const int block = 256;
+  size_t blocks = (n + block - 1) / block;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adam_kernel<<<(int)blocks, block, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  count_launch();
+}
+
+}  // namespace bdn

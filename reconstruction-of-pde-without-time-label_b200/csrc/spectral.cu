@@ -1,0 +1,570 @@
+// Pruned-DFT stages of the FNO spectral convolution, fp32 CUDA-core path (the 1e-5 parity
+// mode).  One spectral layer is W-forward -> [H-forward -> channel mix -> H-inverse] -> W-inverse
+// with the 1x1 conv / bias / GELU-gradient epilogue fused into the W-inverse store.  Only the kept
+// modes are ever computed; the zero-filled spectrum of the reference is never materialised.
+//
+// Replaces (reference file:line): SpectralConv2d.forward 2d_FPE/FNOModules.py:156-178,
+// compl_mul2d :141-154, SpectralConv1d.forward 1d_FPE/FNOModules.py:47-59 and the layer body
+// FNO2d.forward :226-232 / FNO1d.forward :108-114.
+#include "bdn_internal.cuh"
+
+namespace bdn {
+
+// ===========================================================================
+// W-forward: out[r, l] = sum_w act(x[r, w]) * (cos - i sin)(theta_lw),   r over (image, chan, h)
+// Block = 32*RT rows; lane <-> RT consecutive rows, warp <-> 4 consecutive modes.
+// ===========================================================================
+template <int RT>
+__global__ void __launch_bounds__(512) wfwd_kernel(const float* __restrict__ x, float2* __restrict__ out,
+                                                   const float2* __restrict__ t_wl, int rows, int wp, int m2,
+                                                   int act, int wc) {
+  constexpr int LT = 4;
+  constexpr int BR = 32 * RT;
+  constexpr int PITCH = BR + 4;
+  extern __shared__ __align__(16) float smem[];
+  const int nlg = blockDim.x >> 5;
+  const int m2p = nlg * LT;
+  float* xs = smem;                                             // [wc][PITCH]
+  float2* ts = reinterpret_cast<float2*>(smem + (size_t)wc * PITCH);  // [wc][m2p]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * BR;
+
+  float ar[RT][LT], ai[RT][LT];
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+#pragma unroll
+    for (int j = 0; j < LT; ++j) ar[r][j] = ai[r][j] = 0.f;
+
+  for (int w0 = 0; w0 < wp; w0 += wc) {
+    const int wcur = min(wc, wp - w0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < BR * wcur; idx += blockDim.x) {
+      const int r = idx / wcur, w = idx - r * wcur;
+      const int row = row0 + r;
+      float v = row < rows ? __ldg(x + (size_t)row * wp + w0 + w) : 0.f;
+      if (act) v = gelu_exact(v);
+      xs[w * PITCH + r] = v;
+    }
+    for (int idx = threadIdx.x; idx < wcur * m2p; idx += blockDim.x) {
+      const int w = idx / m2p, l = idx - w * m2p;
+      ts[idx] = l < m2 ? __ldg(t_wl + (size_t)(w0 + w) * m2 + l) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    for (int w = 0; w < wcur; ++w) {
+      float xv[RT];
+      if constexpr (RT == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xs + w * PITCH + lane * 4);
+        xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+      } else if constexpr (RT == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(xs + w * PITCH + lane * 2);
+        xv[0] = v.x; xv[1] = v.y;
+      } else {
+        xv[0] = xs[w * PITCH + lane];
+      }
+      const float4 t01 = *reinterpret_cast<const float4*>(ts + w * m2p + warp * LT);
+      const float4 t23 = *reinterpret_cast<const float4*>(ts + w * m2p + warp * LT + 2);
+      const float tc[4] = {t01.x, t01.z, t23.x, t23.z};
+      const float tsn[4] = {t01.y, t01.w, t23.y, t23.w};
+#pragma unroll
+      for (int r = 0; r < RT; ++r)
+#pragma unroll
+        for (int j = 0; j < LT; ++j) {
+          ar[r][j] = fmaf(xv[r], tc[j], ar[r][j]);
+          ai[r][j] = fmaf(-xv[r], tsn[j], ai[r][j]);
+        }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    const int row = row0 + lane * RT + r;
+    if (row >= rows) continue;
+#pragma unroll
+    for (int j = 0; j < LT; ++j) {
+      const int l = warp * LT + j;
+      if (l < m2) out[(size_t)row * m2 + l] = make_float2(ar[r][j], ai[r][j]);
+    }
+  }
+}
+
+static int pick_wchunk(int wp, int per_w_bytes, int budget) {
+  int n = 1;
+  while (ceil_div(wp, n) * per_w_bytes > budget) ++n;
+  return ceil_div(wp, n);
+}
+
+void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st) {
+  const int m2 = pl->m2, wp = pl->wp;
+  const int nlg = ceil_div(m2, 4);
+  const int sms = 148;
+  int rt = 4;
+  if (rows < 128 * 2 * sms) rt = 2;
+  if (rows < 64 * 2 * sms) rt = 1;
+  const int br = 32 * rt;
+  const int per_w = (br + 4) * 4 + nlg * 4 * 8;
+  const int wc = pick_wchunk(wp, per_w, 96 * 1024);
+  const size_t smem = (size_t)wc * per_w;
+  dim3 grid(ceil_div(rows, br)), block(32 * nlg);
+#define BDN_WFWD(RT)                                                                              \
+  {                                                                                               \
+    cudaFuncSetAttribute(wfwd_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+    wfwd_kernel<RT><<<grid, block, smem, st>>>(x, out, pl->t_wl, rows, wp, m2, act, wc);          \
+  }
+  if (rt == 4) BDN_WFWD(4) else if (rt == 2) BDN_WFWD(2) else BDN_WFWD(1)
+#undef BDN_WFWD
+  count_launch();
+}
+
+// ===========================================================================
+// 2-D middle stage: H-forward -> mix -> H-inverse for one image and TL mode columns.
+// ===========================================================================
+struct CoreParams {
+  const float2* in; float2* out; float2* spec_out;
+  const float2* w1; const float2* w2;
+  const float2* t_hk; const float2* t_kh;
+  const float* pre; const float* post;
+  int ca, cb, co_layer, hp, hp8, m1, m2, K, Kp, TL;
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) core2d_kernel(const CoreParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int TL = p.TL, Pa = p.ca * TL, Pb = p.cb * TL, K = p.K, hp = p.hp, m2 = p.m2;
+  const int nA = max(hp * Pa, K * Pb);
+  float2* bufA = reinterpret_cast<float2*>(smem);
+  float2* bufX = bufA + nA;
+  const int l0 = blockIdx.x * TL, b = blockIdx.y;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  // phase 0: stage the image's TL columns, all channels: bufA[h][a*TL + lt]
+  for (int idx = tid; idx < p.ca * hp * TL; idx += nt) {
+    const int lt = idx % TL, h = (idx / TL) % hp, a = idx / (TL * hp);
+    const int l = l0 + lt;
+    bufA[h * Pa + a * TL + lt] =
+        l < m2 ? __ldg(p.in + ((size_t)(b * p.ca + a) * hp + h) * m2 + l) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+
+  // phase 1: X[k][pa] = pre[l] * sum_h x[h][pa] * e^{-i phi_kh}, 8 kept rows per item
+  const int nkg = p.Kp >> 3;
+  for (int idx = tid; idx < Pa * nkg; idx += nt) {
+    const int pa = idx % Pa, kg = idx / Pa;
+    float re[8], im[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) re[j] = im[j] = 0.f;
+    const float4* trow = reinterpret_cast<const float4*>(p.t_hk + kg * 8);
+    const int pitch4 = p.Kp >> 1;  // float4 per table row
+    for (int h = 0; h < hp; ++h) {
+      const float2 x = bufA[h * Pa + pa];
+      const float4* t = trow + (size_t)h * pitch4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 cs = __ldg(t + q);
+        re[2 * q] = fmaf(x.x, cs.x, fmaf(x.y, cs.y, re[2 * q]));
+        im[2 * q] = fmaf(x.y, cs.x, fmaf(-x.x, cs.y, im[2 * q]));
+        re[2 * q + 1] = fmaf(x.x, cs.z, fmaf(x.y, cs.w, re[2 * q + 1]));
+        im[2 * q + 1] = fmaf(x.y, cs.z, fmaf(-x.x, cs.w, im[2 * q + 1]));
+      }
+    }
+    const int a = pa / TL, lt = pa - a * TL, l = l0 + lt;
+    const float sc = l < m2 ? __ldg(p.pre + l) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kg * 8 + j;
+      if (k < K) {
+        const float2 v = make_float2(re[j] * sc, im[j] * sc);
+        bufX[k * Pa + pa] = v;
+        if (p.spec_out != nullptr && l < m2) p.spec_out[((size_t)(b * p.ca + a) * K + k) * m2 + l] = v;
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase 2: per-mode channel mix.  fwd: y_b = sum_a x_a W[a][b]; bwd: y_b = sum_a x_a conj(W[b][a])
+  for (int idx = tid; idx < K * Pb; idx += nt) {
+    const int lt = idx % TL, k = (idx / TL) % K, bc = idx / (TL * K);
+    const int l = l0 + lt;
+    float yr = 0.f, yi = 0.f;
+    if (l < m2) {
+      const bool lo = k < p.m1;
+      const float2* wsel = lo ? p.w1 : p.w2;
+      const int kk = lo ? k : k - p.m1;
+      const size_t mode_off = (size_t)kk * m2 + l;
+      const size_t cstride = (size_t)p.m1 * m2;
+      for (int a = 0; a < p.ca; ++a) {
+        const float2 x = bufX[k * Pa + a * TL + lt];
+        if (!BWD) {
+          const float2 w = __ldg(wsel + (size_t)(a * p.co_layer + bc) * cstride + mode_off);
+          yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
+          yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
+        } else {
+          const float2 w = __ldg(wsel + (size_t)(bc * p.co_layer + a) * cstride + mode_off);
+          yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
+          yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
+        }
+      }
+    }
+    bufA[k * Pb + bc * TL + lt] = make_float2(yr, yi);
+  }
+  __syncthreads();
+
+  // phase 3: Z[h][pb] = post[l] * sum_k y[k][pb] * e^{+i phi_kh}, 8 rows per item
+  const int nhg = p.hp8 >> 3;
+  for (int idx = tid; idx < Pb * nhg; idx += nt) {
+    const int pb = idx % Pb, hg = idx / Pb;
+    float re[8], im[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) re[j] = im[j] = 0.f;
+    const float4* trow = reinterpret_cast<const float4*>(p.t_kh + hg * 8);
+    const int pitch4 = p.hp8 >> 1;
+    for (int k = 0; k < K; ++k) {
+      const float2 y = bufA[k * Pb + pb];
+      const float4* t = trow + (size_t)k * pitch4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 cs = __ldg(t + q);
+        re[2 * q] = fmaf(y.x, cs.x, fmaf(-y.y, cs.y, re[2 * q]));
+        im[2 * q] = fmaf(y.x, cs.y, fmaf(y.y, cs.x, im[2 * q]));
+        re[2 * q + 1] = fmaf(y.x, cs.z, fmaf(-y.y, cs.w, re[2 * q + 1]));
+        im[2 * q + 1] = fmaf(y.x, cs.w, fmaf(y.y, cs.z, im[2 * q + 1]));
+      }
+    }
+    const int bc = pb / TL, lt = pb - bc * TL, l = l0 + lt;
+    if (l >= m2) continue;
+    const float sc = __ldg(p.post + l);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int h = hg * 8 + j;
+      if (h < hp) p.out[((size_t)(b * p.cb + bc) * hp + h) * m2 + l] = make_float2(re[j] * sc, im[j] * sc);
+    }
+  }
+}
+
+void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_out, const float2* w1,
+                   const float2* w2, int images, int ci_layer, int co_layer, bool bwd, cudaStream_t st) {
+  CoreParams p;
+  p.in = in; p.out = out; p.spec_out = spec_out; p.w1 = w1; p.w2 = w2;
+  p.t_hk = pl->t_hk; p.t_kh = pl->t_kh;
+  p.pre = bwd ? pl->col_fwd : pl->col_dc;
+  p.post = bwd ? pl->col_dc : pl->col_fwd;
+  p.ca = bwd ? co_layer : ci_layer;
+  p.cb = bwd ? ci_layer : co_layer;
+  p.co_layer = co_layer;
+  p.hp = pl->hp; p.hp8 = pl->hp8; p.m1 = pl->m1; p.m2 = pl->m2; p.K = pl->K; p.Kp = pl->Kp;
+  // TL mode columns per block: the most that still gives ~2 waves of blocks and fits shared memory
+  auto smem_of = [&](int t) {
+    const size_t nA = (size_t)((pl->hp * p.ca > pl->K * p.cb) ? pl->hp * p.ca : pl->K * p.cb) * t;
+    return (nA + (size_t)pl->K * p.ca * t) * sizeof(float2);
+  };
+  int tl = 1;
+  for (int cand = 8; cand > 1; cand >>= 1) {
+    if (cand > pl->m2 || smem_of(cand) > 200 * 1024) continue;
+    if ((long)images * ceil_div(pl->m2, cand) >= 2 * 148) { tl = cand; break; }
+  }
+  p.TL = tl;
+  const size_t smem = smem_of(tl);
+  dim3 grid(ceil_div(pl->m2, tl), images), block(256);
+  if (bwd) {
+    cudaFuncSetAttribute(core2d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    core2d_kernel<true><<<grid, block, smem, st>>>(p);
+  } else {
+    cudaFuncSetAttribute(core2d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    core2d_kernel<false><<<grid, block, smem, st>>>(p);
+  }
+  count_launch();
+}
+
+// ===========================================================================
+// 1-D middle stage: column scale, save, per-mode mix, column scale.
+// ===========================================================================
+template <bool BWD>
+__global__ void mix1d_kernel(const float2* __restrict__ in, float2* __restrict__ out, float2* __restrict__ spec_out,
+                             const float2* __restrict__ w, const float* __restrict__ pre,
+                             const float* __restrict__ post, int images, int ca, int cb, int co_layer, int m2) {
+  const int cmax = ca > cb ? ca : cb;
+  const long total = (long)images * cmax * m2;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int l = idx % m2, c = (idx / m2) % cmax, b = idx / ((long)m2 * cmax);
+    const float ps = __ldg(pre + l);
+    if (spec_out != nullptr && c < ca) {
+      const float2 x = __ldg(in + ((size_t)b * ca + c) * m2 + l);
+      spec_out[((size_t)b * ca + c) * m2 + l] = make_float2(x.x * ps, x.y * ps);
+    }
+    if (c < cb) {
+      float yr = 0.f, yi = 0.f;
+      for (int a = 0; a < ca; ++a) {
+        float2 x = __ldg(in + ((size_t)b * ca + a) * m2 + l);
+        x.x *= ps; x.y *= ps;
+        if (!BWD) {
+          const float2 wv = __ldg(w + (size_t)(a * co_layer + c) * m2 + l);
+          yr = fmaf(x.x, wv.x, fmaf(-x.y, wv.y, yr));
+          yi = fmaf(x.x, wv.y, fmaf(x.y, wv.x, yi));
+        } else {
+          const float2 wv = __ldg(w + (size_t)(c * co_layer + a) * m2 + l);
+          yr = fmaf(x.x, wv.x, fmaf(x.y, wv.y, yr));
+          yi = fmaf(x.y, wv.x, fmaf(-x.x, wv.y, yi));
+        }
+      }
+      const float qs = __ldg(post + l);
+      out[((size_t)b * cb + c) * m2 + l] = make_float2(yr * qs, yi * qs);
+    }
+  }
+}
+
+void launch_mix1d(const Plan* pl, const float2* in, float2* out, float2* spec_out, const float2* w, int images,
+                  int ci_layer, int co_layer, bool bwd, cudaStream_t st) {
+  const int ca = bwd ? co_layer : ci_layer, cb = bwd ? ci_layer : co_layer;
+  const int cmax = ca > cb ? ca : cb;
+  const long total = (long)images * cmax * pl->m2;
+  const int block = 256;
+  const int grid = (int)((total + block - 1) / block);
+  if (bwd)
+    mix1d_kernel<true><<<grid, block, 0, st>>>(in, out, spec_out, w, pl->col_fwd, pl->col_dc, images, ca, cb,
+                                               co_layer, pl->m2);
+  else
+    mix1d_kernel<false><<<grid, block, 0, st>>>(in, out, spec_out, w, pl->col_dc, pl->col_fwd, images, ca, cb,
+                                                co_layer, pl->m2);
+  count_launch();
+}
+
+// ===========================================================================
+// spectral weight gradient: gw[i,o,k,l] += sum_b conj(xs[b,i,k,l]) * gys[b,o,k,l]
+// ===========================================================================
+__global__ void gw_reduce_kernel(const float2* __restrict__ xs, const float2* __restrict__ gys, float2* gw1,
+                                 float2* gw2, int images, int ci, int co, int K, int m1, int m2, int bchunk) {
+  const long total = (long)ci * co * K * m2;
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int l = idx % m2, k = (idx / m2) % K, o = (idx / ((long)m2 * K)) % co, i = idx / ((long)m2 * K * co);
+  const int b0 = blockIdx.y * bchunk, b1 = min(images, b0 + bchunk);
+  float re = 0.f, im = 0.f;
+  const size_t xoff = ((size_t)i * K + k) * m2 + l, goff = ((size_t)o * K + k) * m2 + l;
+  const size_t xstride = (size_t)ci * K * m2, gstride = (size_t)co * K * m2;
+#pragma unroll 4
+  for (int b = b0; b < b1; ++b) {
+    const float2 x = __ldg(xs + b * xstride + xoff);
+    const float2 g = __ldg(gys + b * gstride + goff);
+    re = fmaf(x.x, g.x, fmaf(x.y, g.y, re));
+    im = fmaf(x.x, g.y, fmaf(-x.y, g.x, im));
+  }
+  const bool lo = (m1 == 0) || k < m1;
+  const int kk = lo ? k : k - m1;
+  const int mrows = m1 == 0 ? 1 : m1;
+  float* dst = reinterpret_cast<float*>((lo ? gw1 : gw2) + ((size_t)(i * co + o) * mrows + kk) * m2 + l);
+  if (gridDim.y == 1) {
+    dst[0] += re; dst[1] += im;
+  } else {
+    atomicAdd(dst, re); atomicAdd(dst + 1, im);
+  }
+}
+
+void launch_gw_reduce(const Plan* pl, const float2* xs, const float2* gys, float2* gw1, float2* gw2, int images,
+                      int ci, int co, cudaStream_t st) {
+  const long total = (long)ci * co * pl->K * pl->m2;
+  const int block = 128;
+  const int gx = (int)((total + block - 1) / block);
+  // split the image loop when there are too few modes to fill the GPU
+  int chunks = 1;
+  while (chunks < images && (long)gx * chunks < 4 * 148 && images / (chunks * 2) >= 8) chunks *= 2;
+  const int bchunk = ceil_div(images, chunks);
+  dim3 grid(gx, ceil_div(images, bchunk));
+  gw_reduce_kernel<<<grid, block, 0, st>>>(xs, gys, gw1, gw2, images, ci, co, pl->K, pl->m1, pl->m2, bchunk);
+  count_launch();
+}
+
+// ===========================================================================
+// W-inverse with fused epilogue.
+//   PLAIN      y = winv(z)
+//   LAYER_FWD  z_out = winv(z) + W_pw * act(z_in) + b
+//   LAYER_BWD  gz_in = (winv(gz~) + W_pw^T * gz_out) * act'(z_in);  gW_pw += gz_out x act(z_in); gb += gz_out
+// A block owns HT consecutive "lines" (image, h) for all channels and one chunk of w.
+// ===========================================================================
+struct WinvParams {
+  const float2* z; float* y; const float* a; const float* zin;
+  const float* pw_w; const float* pw_b; float* g_pw_w; float* g_pw_b;
+  const float* t_cos; const float* t_sin;
+  int lines, c, hp, wp, wp4, m2, act_in, HT, WCH;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int c = p.c, cpad = (c + 3) & ~3, HT = p.HT, WCH = p.WCH, m2 = p.m2, hp = p.hp, wp = p.wp;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int line0 = blockIdx.x * HT, wc0 = blockIdx.y * WCH;
+  const int npx = HT * WCH;
+
+  float* tc = smem;                                        // [m2][WCH]
+  float* tsn = tc + m2 * WCH;                              // [m2][WCH]
+  float2* zs = reinterpret_cast<float2*>(tsn + m2 * WCH);  // [cpad][HT][m2]
+  float* as = reinterpret_cast<float*>(zs + cpad * HT * m2);  // [c][HT][WCH]       (MODE >= 1)
+  float* pws = as + (MODE >= 1 ? c * npx : 0);             // [cpad][c] + bias[cpad]
+  float* zact = pws + (MODE >= 1 ? cpad * c + cpad : 0);   // [c][HT][WCH]          (MODE == 2)
+
+  for (int idx = tid; idx < m2 * WCH; idx += nt) {
+    const int l = idx / WCH, w = idx - l * WCH;
+    const bool ok = wc0 + w < p.wp4;
+    tc[idx] = ok ? __ldg(p.t_cos + (size_t)l * p.wp4 + wc0 + w) : 0.f;
+    tsn[idx] = ok ? __ldg(p.t_sin + (size_t)l * p.wp4 + wc0 + w) : 0.f;
+  }
+  for (int idx = tid; idx < cpad * HT * m2; idx += nt) {
+    const int l = idx % m2, hh = (idx / m2) % HT, ch = idx / (m2 * HT);
+    const int line = line0 + hh;
+    float2 v = make_float2(0.f, 0.f);
+    if (ch < c && line < p.lines) {
+      const int b = line / hp, h = line - b * hp;
+      v = __ldg(p.z + ((size_t)(b * c + ch) * hp + h) * m2 + l);
+    }
+    zs[idx] = v;
+  }
+  if (MODE >= 1) {
+    for (int idx = tid; idx < c * npx; idx += nt) {
+      const int w = idx % WCH, hh = (idx / WCH) % HT, ch = idx / npx;
+      const int line = line0 + hh, wg = wc0 + w;
+      float v = 0.f, za = 0.f;
+      if (line < p.lines && wg < wp) {
+        const int b = line / hp, h = line - b * hp;
+        const size_t off = ((size_t)(b * c + ch) * hp + h) * wp + wg;
+        v = __ldg(p.a + off);
+        if (MODE == 1 && p.act_in) v = gelu_exact(v);
+        if (MODE == 2) {
+          za = __ldg(p.zin + off);
+          if (p.act_in) za = gelu_exact(za);
+        }
+      }
+      as[idx] = v;
+      if (MODE == 2) zact[idx] = za;
+    }
+    for (int idx = tid; idx < cpad * c; idx += nt) {
+      const int r = idx / c, q = idx - r * c;   // r: channel this pass produces, q: channel it consumes
+      float v = 0.f;
+      if (r < c) v = MODE == 1 ? __ldg(p.pw_w + r * c + q) : __ldg(p.pw_w + q * c + r);
+      pws[idx] = v;
+    }
+    for (int idx = tid; idx < cpad; idx += nt)
+      pws[cpad * c + idx] = (MODE == 1 && idx < c) ? __ldg(p.pw_b + idx) : 0.f;
+  }
+  __syncthreads();
+
+  const int nwg = WCH >> 2, nog = cpad >> 2;
+  for (int idx = tid; idx < nog * HT * nwg; idx += nt) {
+    const int wg = idx % nwg, hh = (idx / nwg) % HT, og = idx / (nwg * HT);
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
+    const float2* zrow = zs + ((og * 4) * HT + hh) * m2;
+    const int zpitch = HT * m2;
+    for (int l = 0; l < m2; ++l) {
+      const float4 cs = *reinterpret_cast<const float4*>(tc + l * WCH + wg * 4);
+      const float4 sn = *reinterpret_cast<const float4*>(tsn + l * WCH + wg * 4);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float2 zv = zrow[r * zpitch + l];
+        acc[r][0] = fmaf(zv.x, cs.x, fmaf(-zv.y, sn.x, acc[r][0]));
+        acc[r][1] = fmaf(zv.x, cs.y, fmaf(-zv.y, sn.y, acc[r][1]));
+        acc[r][2] = fmaf(zv.x, cs.z, fmaf(-zv.y, sn.z, acc[r][2]));
+        acc[r][3] = fmaf(zv.x, cs.w, fmaf(-zv.y, sn.w, acc[r][3]));
+      }
+    }
+    if (MODE >= 1) {
+      for (int q = 0; q < c; ++q) {
+        const float4 av = *reinterpret_cast<const float4*>(as + (q * HT + hh) * WCH + wg * 4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float wv = pws[(og * 4 + r) * c + q];
+          acc[r][0] = fmaf(wv, av.x, acc[r][0]);
+          acc[r][1] = fmaf(wv, av.y, acc[r][1]);
+          acc[r][2] = fmaf(wv, av.z, acc[r][2]);
+          acc[r][3] = fmaf(wv, av.w, acc[r][3]);
+        }
+      }
+    }
+    const int line = line0 + hh;
+    if (line >= p.lines) continue;
+    const int b = line / hp, h = line - b * hp;
+    const int w0 = wc0 + wg * 4;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ch = og * 4 + r;
+      if (ch >= c) continue;
+      const size_t off = ((size_t)(b * c + ch) * hp + h) * wp + w0;
+      float v[4] = {acc[r][0], acc[r][1], acc[r][2], acc[r][3]};
+      if (MODE == 1) {
+        const float bias = pws[cpad * c + ch];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += bias;
+      }
+      if (MODE == 2 && p.act_in) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (w0 + j < wp) v[j] *= gelu_grad(__ldg(p.zin + off + j));
+      }
+      if ((wp & 3) == 0 && w0 + 3 < wp) {
+        *reinterpret_cast<float4*>(p.y + off) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (w0 + j < wp) p.y[off + j] = v[j];
+      }
+    }
+  }
+
+  if (MODE == 2) {
+    // 1x1-conv weight / bias gradients over this tile: pair (o, i) per warp, lanes over pixels
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    for (int pair = warp; pair < c * c + c; pair += nwarps) {
+      float s = 0.f;
+      if (pair < c * c) {
+        const int o = pair / c, i = pair - o * c;
+        const float* go = as + o * npx;
+        const float* ai = zact + i * npx;
+        for (int px = lane; px < npx; px += 32) s = fmaf(go[px], ai[px], s);
+      } else {
+        const float* go = as + (pair - c * c) * npx;
+        for (int px = lane; px < npx; px += 32) s += go[px];
+      }
+      s = warp_sum(s);
+      if (lane == 0) atomicAdd(pair < c * c ? p.g_pw_w + pair : p.g_pw_b + (pair - c * c), s);
+    }
+  }
+}
+
+void launch_winv(const Plan* pl, int mode, const WinvArgs& a, cudaStream_t st) {
+  WinvParams p;
+  p.z = a.z; p.y = a.y; p.a = a.a; p.zin = a.zin; p.pw_w = a.pw_w; p.pw_b = a.pw_b;
+  p.g_pw_w = a.g_pw_w; p.g_pw_b = a.g_pw_b;
+  p.t_cos = pl->t_lw_cos; p.t_sin = pl->t_lw_sin;
+  p.lines = a.images * pl->hp; p.c = a.c; p.hp = pl->hp; p.wp = pl->wp; p.wp4 = pl->wp4; p.m2 = pl->m2;
+  p.act_in = a.act_in;
+  const int c = a.c, cpad = (c + 3) & ~3;
+  int ht = 32 / cpad;
+  if (ht < 1) ht = 1;
+  if (ht > 8) ht = 8;
+  while (ht > 1 && ceil_div(p.lines, ht) < 2 * 148) ht >>= 1;
+  int nch = 1;
+  auto smem_of = [&](int wch) {
+    size_t f = 2 * (size_t)pl->m2 * wch + 2 * (size_t)cpad * ht * pl->m2;
+    if (mode >= 1) f += (size_t)c * ht * wch + cpad * c + cpad;
+    if (mode == 2) f += (size_t)c * ht * wch;
+    return f * sizeof(float);
+  };
+  int wch = pl->wp4;
+  while (smem_of(wch) > 96 * 1024 && wch > 4) {
+    ++nch;
+    wch = (ceil_div(pl->wp4, nch) + 3) & ~3;
+  }
+  p.HT = ht; p.WCH = wch;
+  const size_t smem = smem_of(wch);
+  dim3 grid(ceil_div(p.lines, ht), ceil_div(pl->wp4, wch)), block(256);
+#define BDN_WINV(M)                                                                               \
+  {                                                                                               \
+    cudaFuncSetAttribute(winv_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  \
+    winv_kernel<M><<<grid, block, smem, st>>>(p);                                                 \
+  }
+  if (mode == WINV_PLAIN) BDN_WINV(0) else if (mode == WINV_LAYER_FWD) BDN_WINV(1) else BDN_WINV(2)
+#undef BDN_WINV
+  count_launch();
+}
+
+}  // namespace bdn

@@ -1,0 +1,73 @@
+"""CPU: the C-ABI library loads, exports every symbol the header declares, and rejects bad
+arguments without touching a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from blindno_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "blindno_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bdn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    handle = C.CDLL(_lib.LIB_PATH) if os.path.exists(_lib.LIB_PATH) else _lib.lib()
+    names = _declared_functions()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in include/blindno_b200.h but not exported"
+    assert set(names) == set(_lib.EXPORTS), "python binding table and header disagree"
+
+
+def test_abi_version_and_error_channel():
+    L = _lib.lib()
+    assert L.bdn_abi_version() == 1
+    s = _lib.FnoShape()
+    s.ndim = 3
+    assert L.bdn_fno_workspace_bytes(C.byref(s)) == 0
+    assert b"ndim" in L.bdn_last_error() or b"bad" in L.bdn_last_error()
+
+
+@pytest.mark.parametrize("n", list(range(0, 400)))
+def test_pad_amount_is_bankers_rounding(n):
+    assert _lib.lib().bdn_pad_amount(n) == int(round(n * 0.25)) == _lib.pad_amount(n)
+
+
+def _shape(**kw):
+    s = _lib.FnoShape()
+    base = dict(ndim=2, images=4, c_in=3, width=4, c_out=1, hidden=128, n_layers=2, h=61, w=61, hp=76, wp=76,
+                out_h=61, out_w=61, m1=12, m2=12, prec=0)
+    base.update(kw)
+    for k, v in base.items():
+        setattr(s, k, v)
+    return s
+
+
+def test_shape_validation_without_gpu():
+    L = _lib.lib()
+    ok = _shape()
+    assert L.bdn_fno_workspace_bytes(C.byref(ok)) > 0
+    assert L.bdn_fno_act_floats(C.byref(ok)) == 3 * 4 * 4 * 76 * 76
+    assert L.bdn_fno_spec_floats(C.byref(ok)) == 2 * 4 * 4 * 24 * 12 * 2
+    # overlapping row blocks (Q14), too many columns, too many layers, 1-D with rows
+    for bad in (_shape(m1=39), _shape(m2=40), _shape(n_layers=9), _shape(ndim=1), _shape(width=0)):
+        assert L.bdn_fno_workspace_bytes(C.byref(bad)) == 0
+        assert len(L.bdn_last_error()) > 0
+    one_d = _shape(ndim=1, h=1, hp=1, out_h=1, w=80, wp=100, out_w=80, m1=0, m2=15, width=30, c_in=30)
+    assert L.bdn_fno_workspace_bytes(C.byref(one_d)) > 0
+
+
+def test_null_pointers_are_rejected_not_dereferenced():
+    L = _lib.lib()
+    s = _shape()
+    rc = L.bdn_fno_forward(C.byref(s), None, None, None, None, None, None, 0, None)
+    assert rc == -1
+    rc = L.bdn_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None)
+    assert rc == -1

@@ -1,0 +1,276 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against (a) the golden vectors the
+reference produced, (b) the CPU oracle on the same seeded inputs, (c) size-independent
+properties at the BASELINE.json sizes.
+
+Tolerance (BASELINE.json north_star): FP32 mode, forward outputs and gradients within 1e-5
+relative, i.e. max|got - ref| <= 1e-5 * max|ref| per tensor.  Gradients that are sums of
+cancelling terms carry fp32 summation-order noise of up to 3e-5 of their own scale even
+CPU-vs-CPU (measured against an fp64 run of the oracle, see tests/test_oracle_golden.py), so
+for gradients the bound is: our error against the fp64 oracle may not exceed
+max(1e-5 * scale, 3 x the reference's own fp32 error against fp64).
+"""
+import numpy as np
+import pytest
+import torch
+
+from blindno_b200 import ops
+from blindno_b200.surface import fno, nio
+from oracle import blindno_oracle as O
+from oracle import dft64
+from tests.helpers import Fixture, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda"
+
+
+def _to64(p):
+    return {k: (v.to(torch.complex128) if v.is_complex() else v.double()) for k, v in p.items()}
+
+
+def _leaf(p):
+    return {k: v.clone().requires_grad_(True) for k, v in p.items()}
+
+
+def _grad_check(name, got, ref32, truth64, tol=TOL):
+    """|got - truth| <= max(tol * scale, 3 * |ref32 - truth|) elementwise-max."""
+    def flat(t):
+        t = torch.as_tensor(t).detach().cpu()
+        return torch.view_as_real(t.to(torch.complex128)).reshape(-1) if t.is_complex() else t.double().reshape(-1)
+    g, r, t = flat(got), flat(ref32), flat(truth64)
+    assert g.shape == t.shape, (name, g.shape, t.shape)
+    scale = t.abs().max().item()
+    ours = (g - t).abs().max().item()
+    theirs = (r - t).abs().max().item()
+    assert ours <= max(tol * scale, 3.0 * theirs) + 1e-30, \
+        f"{name}: |ours-fp64|={ours:.3e} scale={scale:.3e} ref's own fp32 error={theirs:.3e}"
+
+
+def _oracle_grads(fn, params, x, gy, extra=(), **kw):
+    """Run the oracle in fp32 and fp64 on the CPU; return (y32, grads32, gx32), (y64, grads64, gx64)."""
+    out = []
+    for cast in (lambda d: d, _to64):
+        p = _leaf(cast(dict(params)))
+        xx = (x.double() if cast is _to64 else x).clone().requires_grad_(True)
+        ex = tuple((e.double() if cast is _to64 and torch.is_tensor(e) and e.is_floating_point() else e) for e in extra)
+        y = fn(p, xx, *ex, **kw)
+        y.backward(gy.double() if cast is _to64 else gy)
+        out.append((y.detach(), {k: v.grad for k, v in p.items()}, xx.grad))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# single spectral layers vs the golden vectors
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["spectral2d_pair", "spectral2d_pair_odd", "spectral2d_pair_nyquist",
+                                  "spectral2d_c64", "spectral1d", "spectral1d_odd"])
+def test_spectral_golden(name):
+    fx = Fixture(name)
+    p = fx.params
+    x = fx.t("x").to(DEV).requires_grad_(True)
+    w1 = p["weights1"].to(DEV).requires_grad_(True)
+    w2 = p["weights2"].to(DEV).requires_grad_(True) if "weights2" in p else None
+    y = ops.spectral_conv(x, w1, w2)
+    assert y.shape == fx.t("y").shape
+    assert rel_err(y, fx.t("y")) < TOL
+    y.backward(fx.t("gy").to(DEV))
+    assert rel_err(x.grad, fx.t("gx")) < TOL
+    assert rel_err(w1.grad, fx.grads["weights1"]) < TOL
+    if w2 is not None:
+        assert rel_err(w2.grad, fx.grads["weights2"]) < TOL
+    # and against the library-independent fp64 pruned-DFT restatement
+    if w2 is not None:
+        want = dft64.spectral_conv2d(fx.t("x").numpy(), p["weights1"].numpy(), p["weights2"].numpy())
+    else:
+        want = dft64.spectral_conv1d(fx.t("x").numpy(), p["weights1"].numpy())
+    assert rel_err(y, want) < TOL
+
+
+def test_spectral_default_head_shape_golden():
+    fx = Fixture("spectral2d_default_head")
+    torch.manual_seed(int(fx.meta("weight_seed")))
+    scale = 1.0 / 144
+    w1 = (scale * torch.rand(12, 12, 32, 32, 2)).to(DEV)
+    w2 = (scale * torch.rand(12, 12, 32, 32, 2)).to(DEV)
+    x = torch.randn(1, 12, 76, 76, generator=torch.Generator().manual_seed(int(fx.meta("x_seed")))).to(DEV)
+    assert rel_err(ops.spectral_conv(x, w1, w2), fx.t("y")) < TOL
+
+
+def test_spectral_empty_batch_and_bad_modes():
+    w = torch.rand(3, 3, 2, 2, 2, device=DEV)
+    y = ops.spectral_conv(torch.zeros(0, 3, 8, 8, device=DEV), w, w)
+    assert y.shape == (0, 3, 8, 8)
+    with pytest.raises(RuntimeError, match="overlap|exceeds"):
+        ops.spectral_conv(torch.zeros(1, 3, 3, 8, device=DEV), w, w)      # 2*m1 > hp (Q14)
+    with pytest.raises(RuntimeError, match="exceeds"):
+        ops.spectral_conv(torch.zeros(1, 3, 8, 2, device=DEV), w, w)      # m2 > wp/2+1
+
+
+# ---------------------------------------------------------------------------------------------
+# FNO nets vs golden + oracle
+# ---------------------------------------------------------------------------------------------
+def _fno_from_fixture(fx, ndim):
+    p = fx.params
+    width, c_in = p["fc0.weight"].shape
+    n_layers = sum(1 for k in p if k.startswith("conv_list.") and k.endswith(".weight"))
+    modes = p["spectral_list.0.weights1"].shape[2]
+    c_out = p["fc2.weight"].shape[0]
+    net = fno.FNO2d(modes, width, n_layers, c_in, c_out) if ndim == 2 else fno.FNO1d(modes, width, n_layers, c_in, c_out)
+    net.load_state_dict(p)
+    return net.to(DEV)
+
+
+@pytest.mark.parametrize("name,ndim,fn", [("fno2d", 2, O.fno2d_forward), ("fno2d_rect", 2, O.fno2d_forward),
+                                          ("fno1d", 1, O.fno1d_forward), ("fno1d_banker", 1, O.fno1d_forward)])
+def test_fno_golden(name, ndim, fn):
+    fx = Fixture(name)
+    net = _fno_from_fixture(fx, ndim)
+    x = fx.t("x").to(DEV).requires_grad_(True)
+    y = net(x)
+    assert y.shape == fx.t("y").shape
+    assert rel_err(y, fx.t("y")) < TOL
+    y.backward(fx.t("gy").to(DEV))
+    (_, g32, gx32), (_, g64, gx64) = _oracle_grads(fn, fx.params, fx.t("x"), fx.t("gy"))
+    _grad_check("gx", x.grad, fx.t("gx"), gx64)
+    got = dict(net.named_parameters())
+    for k, g in fx.grads.items():
+        _grad_check(k, got[k].grad, g, g64[k])
+
+
+# ---------------------------------------------------------------------------------------------
+# whole NIO-FNO models vs golden + oracle
+# ---------------------------------------------------------------------------------------------
+CASES = {
+    "niofp2d_fno_eval": ("2d_FPE", "NIOFP2D_FNO", (2, 3, 100, 25, 2, 6, 5, 2), O.niofp2d_fno_forward, ("fno_drift", "fno_diffusion")),
+    "niofp2d_fno_train": ("2d_FPE", "NIOFP2D_FNO", (2, 3, 100, 25, 2, 6, 5, 2), O.niofp2d_fno_forward, ("fno_drift", "fno_diffusion")),
+    "niofp2d_nc_fno_eval": ("2d_Non_conservative_FPE", "NIOFP2D_FNO", (2, 3, 100, 25, 2, 5, 4, 2), O.niofp2d_fno_forward, ("fno_Fx", "fno_Fy")),
+    "niofp1d_fno_train": ("1d_FPE", "NIOFP_FNO", (2, 10, 7, 2, DEV), O.niofp1d_fno_forward, ("fno_drift", "fno_diffusion")),
+    "niofp1d_gpe_fno_eval": ("1d_GPE", "NIOFP_FNO", (3, 8, 9, 1, DEV), O.niofp1d_fno_forward, ("fno_V",)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_nio_fno_golden(name):
+    variant, cls, args, fn, heads = CASES[name]
+    fx = Fixture(name)
+    model = nio.make_models(variant)[cls](*args)
+    model.load_state_dict(fx.params, strict=False)
+    model = model.to(DEV)
+    training = fx.meta("np_seed") is not None
+    model.train(training)
+    if training:
+        np.random.seed(int(fx.meta("np_seed")))
+    grid = fx.t("meta.grid").to(DEV)
+    y = model(fx.t("x").to(DEV), grid)
+    assert y.shape == fx.t("y").shape
+    assert rel_err(y, fx.t("y")) < TOL
+    y.backward(fx.t("gy").to(DEV))
+    idx = fx.meta("idx") if training else None
+    (_, g32, _), (_, g64, _) = _oracle_grads(fn, fx.params, fx.t("x"), fx.t("gy"), extra=(fx.t("meta.grid"),),
+                                             heads=heads, idx=idx)
+    got = dict(model.named_parameters())
+    for k, g in fx.grads.items():
+        _grad_check(k, got[k].grad, g, g64[k])
+    for k in fx.nograd:
+        assert got[k].grad is None, f"{k} must not receive a gradient (fc0 is used through .data)"
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json shapes: oracle on one bag (seconds on CPU), properties at the full batch
+# ---------------------------------------------------------------------------------------------
+def _grid2d(n):
+    ax = np.linspace(-1, 1, n, dtype=np.float32)
+    return torch.tensor(np.stack(np.meshgrid(ax, ax, indexing="ij"), axis=2))
+
+
+@pytest.mark.parametrize("variant,n", [("2d_FPE", 61), ("2d_Non_conservative_FPE", 80)])
+def test_default_shape_train_step_vs_oracle(variant, n):
+    torch.manual_seed(1)
+    model = nio.make_models(variant)["NIOFP2D_FNO"](2, 3, 100, 25, 3, 12, 32, 2)
+    params = {k: v.clone() for k, v in model.state_dict().items() if not k.startswith("branch.")}
+    heads = model.head_names
+    model = model.to(DEV).train()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 100, n, n, generator=g)
+    gy = torch.randn(1, n, n, 2, generator=g)
+    grid = _grid2d(n)
+    np.random.seed(3)
+    idx = O.draw_bag(100, True)
+    np.random.seed(3)
+    y = model(x.to(DEV), grid.to(DEV))
+    y.backward(gy.to(DEV))
+    (y32, g32, _), (y64, g64, _) = _oracle_grads(O.niofp2d_fno_forward, params, x, gy, extra=(grid,), heads=heads, idx=idx)
+    _grad_check("y", y, y32, y64)
+    got = dict(model.named_parameters())
+    for k, v in g32.items():
+        if v is None:
+            assert got[k].grad is None, k
+        else:
+            _grad_check(k, got[k].grad, v, g64[k])
+
+
+def test_default_shape_1d_fpe_vs_oracle():
+    torch.manual_seed(2)
+    model = nio.make_models("1d_FPE")["NIOFP_FNO"](3, 30, 15, 2, "cpu")
+    params = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).train()
+    g = torch.Generator().manual_seed(0)
+    x, gy = torch.randn(4, 100, 80, generator=g), torch.randn(4, 80, 2, generator=g)
+    grid = torch.linspace(0, 1, 80).unsqueeze(-1)
+    np.random.seed(4)
+    idx = O.draw_bag(100, True)
+    np.random.seed(4)
+    y = model(x.to(DEV), grid.to(DEV))
+    y.backward(gy.to(DEV))
+    (y32, g32, _), (y64, g64, _) = _oracle_grads(O.niofp1d_fno_forward, params, x, gy, extra=(grid,), idx=idx)
+    _grad_check("y", y, y32, y64)
+    got = dict(model.named_parameters())
+    for k, v in g32.items():
+        if v is not None:
+            _grad_check(k, got[k].grad, v, g64[k])
+
+
+def test_full_batch_properties_2d_fpe():
+    """B=4, L0=100, 61x61: permutation invariance over the bag, sample independence, linearity of the
+    spectral convolution, and agreement of the batched run with per-sample runs."""
+    torch.manual_seed(5)
+    model = nio.make_models("2d_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 3, 12, 32, 2).to(DEV).eval()
+    x = torch.randn(4, 100, 61, 61, device=DEV)
+    grid = _grid2d(61).to(DEV)
+    with torch.no_grad():
+        y = model(x, grid)
+        perm = torch.randperm(100, device=DEV)
+        y_perm = model(x[:, perm], grid)
+        y_single = torch.cat([model(x[i:i + 1], grid) for i in range(4)])
+    assert y.shape == (4, 61, 61, 2)
+    assert rel_err(y_perm, y) < TOL          # unordered bag: time labels do not matter
+    assert rel_err(y_single, y) < 1e-6       # no cross-sample coupling
+    layer = model.fno_drift.spectral_list[0]
+    a, b = torch.randn(2, 4, 12, 76, 76, device=DEV)
+    with torch.no_grad():
+        lin = layer(2.0 * a - 3.0 * b)
+        assert rel_err(lin, 2.0 * layer(a) - 3.0 * layer(b)) < TOL
+
+
+def test_fc0_receives_no_gradient_and_unused_branch_is_untouched():
+    model = nio.make_models("2d_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 1, 4, 4, 2).to(DEV).train()
+    np.random.seed(0)
+    y = model(torch.randn(2, 60, 20, 20, device=DEV), _grid2d(20).to(DEV))
+    y.square().mean().backward()
+    assert model.fc0.weight.grad is None and model.fc0.bias.grad is None
+    assert all(p.grad is None for p in model.branch.parameters())
+    assert all(p.grad is not None for n, p in model.named_parameters() if n.startswith(("FNO_input", "fno_")))
+
+
+def test_adam_flat_matches_torch():
+    torch.manual_seed(0)
+    p = torch.randn(10007, device=DEV)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=5e-4)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 6):
+        g = torch.randn_like(p)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_step_flat(p, g, m, v, lr=5e-4, step=step)
+    assert rel_err(p, ref) < 1e-6

@@ -1,0 +1,98 @@
+"""CPU: the drop-in module surface -- names, shapes, dtypes, registration order, RNG consumption,
+checkpoint loading -- against the golden fixtures (and the live reference when it is mounted)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from blindno_b200.surface import fno, nio
+from tests.helpers import Fixture
+
+
+def _build(name):
+    if name == "niofp2d_fno_eval" or name == "niofp2d_fno_train":
+        return nio.make_models("2d_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 2, 6, 5, 2)
+    if name == "niofp2d_nc_fno_eval":
+        return nio.make_models("2d_Non_conservative_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 2, 5, 4, 2)
+    if name == "niofp1d_fno_train":
+        return nio.make_models("1d_FPE")["NIOFP_FNO"](2, 10, 7, 2, "cpu")
+    if name == "niofp1d_gpe_fno_eval":
+        return nio.make_models("1d_GPE")["NIOFP_FNO"](3, 8, 9, 1, "cpu")
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["niofp2d_fno_eval", "niofp2d_nc_fno_eval", "niofp1d_fno_train", "niofp1d_gpe_fno_eval"])
+def test_state_dict_matches_reference_checkpoint_layout(name):
+    fx = Fixture(name)
+    model = _build(name)
+    mine = {k: v for k, v in model.state_dict().items() if not k.startswith("branch.")}
+    ref = fx.params
+    assert list(mine.keys()) == list(ref.keys())
+    for k in ref:
+        assert mine[k].shape == ref[k].shape and mine[k].dtype == ref[k].dtype, k
+    missing, unexpected = model.load_state_dict(ref, strict=False)
+    assert not unexpected and all(k.startswith("branch.") for k in missing)
+    # DDP checkpoints carry a "module." prefix that the eval scripts strip (2d_FPE/eval_fno.py:104-122)
+    stripped = {k[len("module."):]: v for k, v in {"module." + k: v for k, v in ref.items()}.items()}
+    model.load_state_dict(stripped, strict=False)
+
+
+def test_fno_layouts():
+    m = fno.FNO2d(32, 12, 3, 12, 1)
+    sd = m.state_dict()
+    assert sd["spectral_list.0.weights1"].shape == (12, 12, 32, 32, 2) and sd["spectral_list.0.weights1"].dtype == torch.float32
+    assert sd["conv_list.2.weight"].shape == (12, 12, 1, 1) and sd["fc2.weight"].shape == (1, 128)
+    assert fno.FNO2d(4, 4, 1, 3, 7).fc2.out_features == 1          # Q3: output_dim ignored in 2-D
+    m1 = fno.FNO1d(15, 30, 3, 30, 2)
+    assert m1.state_dict()["spectral_list.1.weights1"].dtype == torch.complex64
+    assert m1.state_dict()["spectral_list.1.weights1"].shape == (30, 30, 15) and m1.fc2.out_features == 2
+    c = fno.FNO2dC64(3, 4, 1, 2, 1, device="cpu")
+    assert c.state_dict()["spectral_list.0.weights2"].dtype == torch.complex64
+
+
+def test_bag_draw_consumes_numpy_stream_like_the_reference():
+    for name in ("niofp2d_fno_train", "niofp1d_fno_train"):
+        fx = Fixture(name)
+        np.random.seed(int(fx.meta("np_seed")))
+        idx = nio.draw_bag(fx.t("x").shape[1], True)
+        assert np.array_equal(idx, fx.meta("idx"))
+        after = np.random.randint(0, 1 << 30)
+        np.random.seed(int(fx.meta("np_seed")))
+        n = np.random.randint(50, fx.t("x").shape[1]); np.random.choice(fx.t("x").shape[1], n)
+        assert after == np.random.randint(0, 1 << 30)
+    state = np.random.get_state()[1].copy()
+    assert nio.draw_bag(100, False) is None
+    assert np.array_equal(state, np.random.get_state()[1])       # eval draws nothing
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    m = fno.FNO2d(3, 4, 2, 3, 1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.randn(1, 8, 8, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fno.SpectralConv1d(2, 2, 3)(torch.randn(1, 2, 16))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/2d_FPE"), reason="reference tree not mounted")
+@pytest.mark.parametrize("variant,cls,args", [
+    ("2d_FPE", "NIOFP2D_FNO", (2, 3, 100, 25, 3, 12, 32, 2)),
+    ("2d_Non_conservative_FPE", "NIOFP2D_FNO", (2, 3, 100, 25, 3, 12, 32, 2)),
+    ("1d_FPE", "NIOFP_FNO", (3, 30, 15, 2, "cpu")),
+    ("1d_GPE", "NIOFP_FNO", (3, 20, 40, 1, "cpu")),
+    ("1d_GPE", "NIOFP_schrodinger", (1, 3, 100, 25, 3, 20, 40, 1, "cpu")),
+    ("1d_FPE", "NIOFP", (1, 3, 100, 25, 3, 30, 15, 2, "cpu")),
+    ("2d_FPE", "NIOFP2D", (2, 3, 100, 25, 3, 12, 32, 2)),
+])
+def test_live_state_dict_and_seeded_init_parity(variant, cls, args):
+    from tests.golden.make_golden import load_reference
+    R = load_reference(variant, "NIOModules")
+    torch.manual_seed(7)
+    ref = getattr(R, cls)(*args)
+    torch.manual_seed(7)
+    mine = nio.make_models(variant)[cls](*args)
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+    assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
