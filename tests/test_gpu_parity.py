@@ -103,7 +103,7 @@ def test_spectral_empty_batch_and_bad_modes():
     with pytest.raises(RuntimeError, match="overlap|exceeds"):
         ops.spectral_conv(torch.zeros(1, 3, 3, 8, device=DEV), w, w)      # 2*m1 > hp (Q14)
     with pytest.raises(RuntimeError, match="exceeds"):
-        ops.spectral_conv(torch.zeros(1, 3, 8, 2, device=DEV), w, w)      # m2 > wp/2+1
+        ops.spectral_conv(torch.zeros(1, 3, 8, 1, device=DEV), w, w)      # m2 > wp/2+1
 
 
 # ---------------------------------------------------------------------------------------------
