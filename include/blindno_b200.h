@@ -191,6 +191,12 @@ const char* bdn_last_error(void);          /* thread-local, valid until the next
 int bdn_pad_amount(int n);                 /* int(round(n / 4)) with Python's banker's rounding */
 int64_t bdn_kernel_launches(void);         /* kernels launched by this library so far (process-wide) */
 int bdn_device_sm_count(void);
+/* Per-kernel device timing for bench.py's roofline: between begin and end every kernel this
+ * library launches is bracketed by a CUDA event pair on its stream.  end synchronises those
+ * events and writes a JSON object {"kernel/tag": {"launches": n, "ms": total}, ...} into buf
+ * (truncated to cap); returns the number of bytes the full text needs. */
+int bdn_profile_begin(void);
+long bdn_profile_end(char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

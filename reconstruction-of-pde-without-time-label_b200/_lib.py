@@ -51,6 +51,8 @@ EXPORTS = {
     "bdn_pad_amount": (C.c_int, [C.c_int]),
     "bdn_kernel_launches": (C.c_int64, []),
     "bdn_device_sm_count": (C.c_int, []),
+    "bdn_profile_begin": (C.c_int, []),
+    "bdn_profile_end": (C.c_long, [C.c_char_p, C.c_size_t]),
     "bdn_spectral_workspace_bytes": (C.c_size_t, [C.POINTER(SpectralShape)]),
     "bdn_spectral_forward": (C.c_int, [C.POINTER(SpectralShape), _fp, _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "bdn_spectral_backward": (C.c_int, [C.POINTER(SpectralShape), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,

@@ -7,8 +7,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <map>
 #include <mutex>
+#include <string>
 #include <tuple>
 #include <vector>
 
@@ -25,6 +27,31 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+// ---------------------------------------------------------------------------
+// per-kernel device timing (bench.py roofline): event pairs around every launch while enabled
+// ---------------------------------------------------------------------------
+struct ProfRecord { std::string name; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static std::atomic<bool> g_prof_on{false};
+static std::vector<ProfRecord> g_prof;
+
+LaunchScope::LaunchScope(const char* n, cudaStream_t s, int t) : name(n), tag(t), st(s), e0(nullptr), on(false) {
+  if (g_prof_on.load(std::memory_order_relaxed)) {
+    on = cudaEventCreate(&e0) == cudaSuccess && cudaEventRecord(e0, st) == cudaSuccess;
+  }
+}
+
+LaunchScope::~LaunchScope() {
+  count_launch(1);
+  if (!on) return;
+  cudaEvent_t e1;
+  if (cudaEventCreate(&e1) != cudaSuccess || cudaEventRecord(e1, st) != cudaSuccess) return;
+  std::string full(name);
+  if (tag >= 0) full += "/" + std::to_string(tag);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof.push_back({full, e0, e1});
 }
 
 static int check_cuda(const char* where) {
@@ -164,6 +191,47 @@ int bdn_pad_amount(int n) {
   if (r < 2) return q;
   if (r > 2) return q + 1;
   return (q % 2 == 0) ? q : q + 1;   // exactly .5 -> nearest even
+}
+
+int bdn_profile_begin(void) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_prof_on.store(true);
+  return BDN_OK;
+}
+
+long bdn_profile_end(char* buf, size_t cap) {
+  g_prof_on.store(false);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  std::map<std::string, std::pair<long, double>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      auto& a = agg[r.name];
+      a.first += 1;
+      a.second += ms;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char tmp[256];
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(),
+             kv.second.first, kv.second.second);
+    js += tmp;
+    first = false;
+  }
+  js += "}";
+  if (buf && cap > 0) {
+    const size_t n = js.size() < cap - 1 ? js.size() : cap - 1;
+    memcpy(buf, js.data(), n);
+    buf[n] = 0;
+  }
+  return (long)js.size() + 1;
 }
 
 int bdn_device_sm_count(void) {

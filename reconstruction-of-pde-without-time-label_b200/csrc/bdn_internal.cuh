@@ -35,6 +35,18 @@ const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2);   // nullptr on 
 void count_launch(int n = 1);
 int set_error(int code, const char* fmt, ...);
 
+// Brackets one kernel launch: counts it, and when profiling is on (bdn_profile_begin) records a
+// CUDA event pair on the launch stream so bench.py can report per-kernel device time.
+struct LaunchScope {
+  LaunchScope(const char* name, cudaStream_t st, int tag = -1);   // tag (e.g. channel width) is appended to the name
+  ~LaunchScope();
+  const char* name;
+  int tag;
+  cudaStream_t st;
+  cudaEvent_t e0;
+  bool on;
+};
+
 // ---------------------------------------------------------------------------
 // kernel launchers (spectral.cu)
 // ---------------------------------------------------------------------------

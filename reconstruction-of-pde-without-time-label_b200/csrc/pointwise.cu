@@ -70,13 +70,13 @@ static LiftParams make_lift_params(const LiftArgs& a) {
 }
 
 void launch_lift(const LiftArgs& a, float* z0, cudaStream_t st) {
+  LaunchScope scope("lift", st, a.width);
   const LiftParams p = make_lift_params(a);
   const long total = (long)a.images * a.hp * a.wp;
   const int block = 256;
   const int grid = (int)((total + block - 1) / block);
   const size_t smem = (size_t)(a.width * a.c_in + a.width) * sizeof(float);
   lift_kernel<<<grid, block, smem, st>>>(p, z0);
-  count_launch();
 }
 
 // lift backward: g_w0[c][i] += sum gz0[c] * in_i, g_b0[c] += sum gz0[c], gx_cl[.., i] = sum_c W0[c][i] gz0[c]
@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256) lift_bwd_kernel(const LiftParams p, const
 
 void launch_lift_bwd(const LiftArgs& a, const float* gz0, float* g_w0, float* g_b0, float* gx_cl,
                      cudaStream_t st) {
+  LaunchScope scope("lift_bwd", st, a.width);
   const LiftParams p = make_lift_params(a);
   const long total = (long)a.images * a.h * a.w;
   const int tiles = (int)((total + 255) / 256);
@@ -158,7 +159,6 @@ void launch_lift_bwd(const LiftArgs& a, const float* gz0, float* g_w0, float* g_
   const size_t smem = (size_t)((a.width + a.c_in) * 256 + 2 * a.width * a.c_in + a.width) * sizeof(float);
   cudaFuncSetAttribute(lift_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   lift_bwd_kernel<<<grid, 256, smem, st>>>(p, gz0, g_w0, g_b0, gx_cl, tpb);
-  count_launch();
 }
 
 // ===========================================================================
@@ -225,6 +225,7 @@ static bool dispatch_cp(int width, F&& f) {
 }
 
 void launch_project(const ProjArgs& a, float* out, cudaStream_t st) {
+  LaunchScope scope("project", st, a.width);
   const long total = (long)a.images * a.out_h * a.out_w;
   const int block = 128;
   const int grid = (int)((total + block - 1) / block);
@@ -234,7 +235,6 @@ void launch_project(const ProjArgs& a, float* out, cudaStream_t st) {
     cudaFuncSetAttribute(project_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     project_kernel<CP><<<grid, block, smem, st>>>(a, out);
   });
-  count_launch();
 }
 
 // projection backward.  Each thread owns PP pixels; for every hidden unit j it recomputes the
@@ -377,6 +377,7 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(const ProjArgs a, cons
 
 void launch_project_bwd(const ProjArgs& a, const float* g_out, int pooled_g, int n_keep, float* gz, float* g_w1,
                         float* g_b1, float* g_w2, float* g_b2, cudaStream_t st) {
+  LaunchScope scope("project_bwd", st, a.width);
   const size_t act_bytes = (size_t)a.images * a.width * a.hp * a.wp * sizeof(float);
   cudaMemsetAsync(gz, 0, act_bytes, st);
   const long total = (long)a.images * a.out_h * a.out_w;
@@ -393,7 +394,6 @@ void launch_project_bwd(const ProjArgs& a, const float* g_out, int pooled_g, int
     cudaFuncSetAttribute(project_bwd_kernel<CP, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     project_bwd_kernel<CP, PP><<<grid, 128, smem, st>>>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, tpb);
   });
-  count_launch();
 }
 
 // ===========================================================================
@@ -419,11 +419,11 @@ __global__ void pool_lift_kernel(const float* __restrict__ s, const float* __res
 
 void launch_pool_lift(const float* s, const float* grid, const float* w0, const float* b0, float* out, int n_bags,
                       int n_keep, int npix, int grid_dim, int width, cudaStream_t st) {
+  LaunchScope scope("pool_lift", st);
   const long total = (long)n_bags * npix;
   const int block = 64;
   pool_lift_kernel<<<(int)((total + block - 1) / block), block, 0, st>>>(s, grid, w0, b0, out, n_bags, n_keep, npix,
                                                                          grid_dim, width);
-  count_launch();
 }
 
 __global__ void pool_lift_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w0,
@@ -437,10 +437,10 @@ __global__ void pool_lift_bwd_kernel(const float* __restrict__ g, const float* _
 
 void launch_pool_lift_bwd(const float* g, const float* w0, float* gpool, int n_bags, int npix, int grid_dim,
                           int width, cudaStream_t st) {
+  LaunchScope scope("pool_lift_bwd", st);
   const long total = (long)n_bags * npix;
   const int block = 128;
   pool_lift_bwd_kernel<<<(int)((total + block - 1) / block), block, 0, st>>>(g, w0, gpool, total, grid_dim, width);
-  count_launch();
 }
 
 // ===========================================================================
@@ -462,12 +462,12 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 void launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
                  int step, float grad_scale, cudaStream_t st) {
+  LaunchScope scope("adam", st);
   const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
   const int block = 256;
   size_t blocks = (n + block - 1) / block;
   if (blocks > 148 * 16) blocks = 148 * 16;
   adam_kernel<<<(int)blocks, block, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
-  count_launch();
 }
 
 }  // namespace bdn

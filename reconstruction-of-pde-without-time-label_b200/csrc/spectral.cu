@@ -93,6 +93,7 @@ static int pick_wchunk(int wp, int per_w_bytes, int budget) {
 }
 
 void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st) {
+  LaunchScope scope(act ? "wfwd_gelu" : "wfwd", st, pl->m2);
   const int m2 = pl->m2, wp = pl->wp;
   const int nlg = ceil_div(m2, 4);
   const int sms = 148;
@@ -111,7 +112,6 @@ void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act,
   }
   if (rt == 4) BDN_WFWD(4) else if (rt == 2) BDN_WFWD(2) else BDN_WFWD(1)
 #undef BDN_WFWD
-  count_launch();
 }
 
 // ===========================================================================
@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(256) core2d_kernel(const CoreParams p) {
 
 void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_out, const float2* w1,
                    const float2* w2, int images, int ci_layer, int co_layer, bool bwd, cudaStream_t st) {
+  LaunchScope scope(bwd ? "core2d_bwd" : "core2d_fwd", st, co_layer);
   CoreParams p;
   p.in = in; p.out = out; p.spec_out = spec_out; p.w1 = w1; p.w2 = w2;
   p.t_hk = pl->t_hk; p.t_kh = pl->t_kh;
@@ -270,7 +271,6 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
     cudaFuncSetAttribute(core2d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     core2d_kernel<false><<<grid, block, smem, st>>>(p);
   }
-  count_launch();
 }
 
 // ===========================================================================
@@ -312,6 +312,7 @@ __global__ void mix1d_kernel(const float2* __restrict__ in, float2* __restrict__
 
 void launch_mix1d(const Plan* pl, const float2* in, float2* out, float2* spec_out, const float2* w, int images,
                   int ci_layer, int co_layer, bool bwd, cudaStream_t st) {
+  LaunchScope scope(bwd ? "mix1d_bwd" : "mix1d_fwd", st, co_layer);
   const int ca = bwd ? co_layer : ci_layer, cb = bwd ? ci_layer : co_layer;
   const int cmax = ca > cb ? ca : cb;
   const long total = (long)images * cmax * pl->m2;
@@ -323,7 +324,6 @@ void launch_mix1d(const Plan* pl, const float2* in, float2* out, float2* spec_ou
   else
     mix1d_kernel<false><<<grid, block, 0, st>>>(in, out, spec_out, w, pl->col_dc, pl->col_fwd, images, ca, cb,
                                                 co_layer, pl->m2);
-  count_launch();
 }
 
 // ===========================================================================
@@ -359,6 +359,7 @@ __global__ void gw_reduce_kernel(const float2* __restrict__ xs, const float2* __
 
 void launch_gw_reduce(const Plan* pl, const float2* xs, const float2* gys, float2* gw1, float2* gw2, int images,
                       int ci, int co, cudaStream_t st) {
+  LaunchScope scope("gw_reduce", st, co);
   const long total = (long)ci * co * pl->K * pl->m2;
   const int block = 128;
   const int gx = (int)((total + block - 1) / block);
@@ -368,7 +369,6 @@ void launch_gw_reduce(const Plan* pl, const float2* xs, const float2* gys, float
   const int bchunk = ceil_div(images, chunks);
   dim3 grid(gx, ceil_div(images, bchunk));
   gw_reduce_kernel<<<grid, block, 0, st>>>(xs, gys, gw1, gw2, images, ci, co, pl->K, pl->m1, pl->m2, bchunk);
-  count_launch();
 }
 
 // ===========================================================================
@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
 }
 
 void launch_winv(const Plan* pl, int mode, const WinvArgs& a, cudaStream_t st) {
+  LaunchScope scope(mode == WINV_PLAIN ? "winv_plain" : (mode == WINV_LAYER_FWD ? "winv_layer_fwd" : "winv_layer_bwd"), st, a.c);
   WinvParams p;
   p.z = a.z; p.y = a.y; p.a = a.a; p.zin = a.zin; p.pw_w = a.pw_w; p.pw_b = a.pw_b;
   p.g_pw_w = a.g_pw_w; p.g_pw_b = a.g_pw_b;
@@ -564,7 +565,6 @@ void launch_winv(const Plan* pl, int mode, const WinvArgs& a, cudaStream_t st) {
   }
   if (mode == WINV_PLAIN) BDN_WINV(0) else if (mode == WINV_LAYER_FWD) BDN_WINV(1) else BDN_WINV(2)
 #undef BDN_WINV
-  count_launch();
 }
 
 }  // namespace bdn

@@ -49,6 +49,28 @@ def kernel_launches() -> int:
     return int(_lib.lib().bdn_kernel_launches())
 
 
+def slot_layout(sizes):
+    """Offsets of 16-byte aligned slots for tensors of ``sizes`` fp32 elements inside one flat buffer
+    (complex views need even offsets; vector loads like 16 bytes).  Returns (offsets, total)."""
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + 3) & ~3
+    return offs, total
+
+
+def profile_begin():
+    check(_lib.lib().bdn_profile_begin(), "bdn_profile_begin")
+
+
+def profile_end() -> dict:
+    """{"kernel/tag": {"launches": n, "ms": total device ms}} since profile_begin()."""
+    import json
+    buf = C.create_string_buffer(1 << 20)
+    _lib.lib().bdn_profile_end(buf, len(buf))
+    return json.loads(buf.value.decode() or "{}")
+
+
 # ---------------------------------------------------------------------------------------------
 # one FNO net
 # ---------------------------------------------------------------------------------------------
@@ -112,7 +134,7 @@ class _FnoFn(torch.autograd.Function):
     """FNO1d/FNO2d.forward (+ optionally the bag mean and detached lift on its output)."""
 
     @staticmethod
-    def forward(ctx, spec: FnoSpec, x_cl, bags, idx, grid, pool_w0, pool_b0, *params):
+    def forward(ctx, spec: FnoSpec, x_cl, bags, idx, grid, pool_w0, pool_b0, sink, *params):
         L = _lib.lib()
         _need_cuda(x_cl, bags, grid, *params)
         flat = [_f32c(p.detach()) for p in params]
@@ -186,6 +208,7 @@ class _FnoFn(torch.autograd.Function):
         ctx.spec, ctx.shape, ctx.lift = spec, shape, lift
         ctx.keep = (x_cl, bags, idx, grid, pool_w0, flat, z_saved, xs_saved)   # keeps the raw pointers alive
         ctx.pooled, ctx.n_bags, ctx.n_keep = pooled, n_bags, n_keep
+        ctx.sink = sink
         ctx.param_meta = [(p.shape, p.is_complex()) for p in params]
         return result
 
@@ -205,11 +228,14 @@ class _FnoFn(torch.autograd.Function):
                       "bdn_bag_pool_lift_backward")
                 g = gpool
             sizes = [t.numel() for t in flat]
-            offs, total = [], 0
-            for n in sizes:                       # 16-byte aligned slots (complex views need even offsets)
-                offs.append(total)
-                total += (n + 3) & ~3
-            gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+            offs, total = slot_layout(sizes)
+            if ctx.sink is not None:
+                # the trainer's flat gradient buffer: kernels accumulate into it, autograd sees no grads
+                if ctx.sink.numel() != total or ctx.sink.dtype != torch.float32 or not ctx.sink.is_contiguous():
+                    raise RuntimeError("gradient sink does not match this net's slot layout")
+                gflat = ctx.sink
+            else:
+                gflat = torch.zeros(total, dtype=torch.float32, device=dev)
             gviews = [gflat[o:o + n] for o, n in zip(offs, sizes)]
             cgrads = _fill_params(spec, gviews)
             gx = None
@@ -222,27 +248,30 @@ class _FnoFn(torch.autograd.Function):
                                      max(ctx.n_keep, 1), _ptr(z_saved), _ptr(xs_saved), C.byref(cgrads), _ptr(gx),
                                      _ptr(ws), ws_bytes, _stream()), "bdn_fno_backward")
         grads = []
-        for view, (shp, is_c), need in zip(gviews, ctx.param_meta, ctx.needs_input_grad[7:]):
-            if not need:
+        for view, (shp, is_c), need in zip(gviews, ctx.param_meta, ctx.needs_input_grad[8:]):
+            if not need or ctx.sink is not None:
                 grads.append(None)
             elif is_c:
                 grads.append(torch.view_as_complex(view.view(*shp, 2)))
             else:
                 grads.append(view.view(shp))
-        return (None, gx, None, None, None, None, None, *grads)
+        return (None, gx, None, None, None, None, None, None, *grads)
 
 
 def fno_apply(spec: FnoSpec, params: Sequence[torch.Tensor], *, x_cl=None, bags=None, idx=None, grid=None,
-              pool=None) -> torch.Tensor:
+              pool=None, grad_sink=None) -> torch.Tensor:
     """Run one FNO net.
 
     ``x_cl``: channels-last input [images, (h,) w, c_in]; or ``bags`` [B, L0, (h,) w] + ``grid`` [(h,) w, d]
     (+ optional int ``idx`` of kept snapshots) for the per-snapshot NIO-FNO encoder, whose input
     concat(snapshot, grid) is never materialised.  ``pool=(fc0.weight, fc0.bias)`` additionally applies the
     bag mean and the detached lift, returning [B, (h,) w, width] instead of the per-snapshot outputs.
+    ``grad_sink``: a flat fp32 buffer laid out by ``slot_layout`` over ``params``; when given, the backward
+    kernels accumulate the parameter gradients straight into it (the data-parallel trainer all-reduces that
+    buffer in one call) and autograd receives no parameter gradients.
     """
     pw, pb = pool if pool is not None else (None, None)
-    return _FnoFn.apply(spec, x_cl, bags, idx, grid, pw, pb, *params)
+    return _FnoFn.apply(spec, x_cl, bags, idx, grid, pw, pb, grad_sink, *params)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,0 +1,145 @@
+"""Data-parallel train step for the bag models: one flat fp32 parameter buffer, one flat gradient
+buffer that the weight-gradient kernels write into directly, ONE NCCL all-reduce per step, and a
+fused Adam over the flat buffer.
+
+Replaces what ``accelerate`` + DistributedDataParallel do around the reference's loop
+(2d_FPE/train_fno.py:75-77,116-123,139-145): DDP ships every parameter (13.5 M floats, of which
+9.9 M belong to the Encoder2D branch NIOFP2D_FNO never calls, hence find_unused_parameters=True)
+in 25 MiB buckets; here only the live gradients (3.56 M floats for the 2-D NIO-FNO) travel, in one
+call on one registered buffer.  Samples are sharded across ranks (pure data parallel, weak scaling),
+each rank draws its own bag subsample from its own NumPy stream (seed + rank, train_fno.py:78-81).
+
+The optimiser maths is torch.optim.Adam's (lr, betas, eps; no weight decay); parameters that never
+receive a gradient in the reference (``fc0`` used through ``.data``; the unused branch) are left
+untouched exactly as Adam leaves parameters whose ``.grad`` is None.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+from .surface.fno import _FnoBase
+
+
+def live_parameters(model: nn.Module):
+    """(name, parameter) pairs the train step updates, in registration order."""
+    dead: Iterable[str] = ("fc0.",)
+    if hasattr(model, "FNO_input"):
+        dead = ("fc0.", "branch.")          # NIO-FNO never calls its branch encoder (Q8)
+    seen = set()
+    out = []
+    for name, p in model.named_parameters():   # named_parameters de-duplicates shared tensors (Q10)
+        if name.startswith(tuple(dead)) or not p.requires_grad or id(p) in seen:
+            continue
+        seen.add(id(p))
+        out.append((name, p))
+    return out
+
+
+class FlatTrainer:
+    """Owns the flat parameter / gradient / Adam-state buffers of ``model`` and runs train steps."""
+
+    def __init__(self, model: nn.Module, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 process_group: Optional[dist.ProcessGroup] = None, loss_fn=None):
+        self.model = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.loss_fn = loss_fn or nn.functional.mse_loss
+        self.step_count = 0
+
+        named = live_parameters(model)
+        if not named:
+            raise RuntimeError("model has no trainable parameters")
+        self.device = named[0][1].device
+        by_id = {id(p): n for n, p in named}
+
+        # FNO nets get one contiguous region each, in the slot layout their backward kernels expect
+        regions = []          # (module or None, [params])
+        claimed = set()
+        for mod in model.modules():
+            if isinstance(mod, _FnoBase):
+                ps = mod._params()
+                if all(id(p) in by_id for p in ps):
+                    regions.append((mod, ps))
+                    claimed.update(id(p) for p in ps)
+        rest = [p for _, p in named if id(p) not in claimed]
+        if rest:
+            regions.append((None, rest))
+
+        sizes_per_region = []
+        total = 0
+        for _, ps in regions:
+            sizes = [p.numel() * (2 if p.is_complex() else 1) for p in ps]
+            offs, n = ops.slot_layout(sizes)
+            sizes_per_region.append((total, offs, sizes, n))
+            total += n
+        self.numel = total
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.n_live = 0
+
+        for (mod, ps), (base, offs, sizes, n) in zip(regions, sizes_per_region):
+            for p, off, size in zip(ps, offs, sizes):
+                pv = self.flat_param[base + off: base + off + size]
+                gv = self.flat_grad[base + off: base + off + size]
+                if p.is_complex():
+                    pv = torch.view_as_complex(pv.view(*p.shape, 2))
+                    gv = torch.view_as_complex(gv.view(*p.shape, 2))
+                else:
+                    pv, gv = pv.view(p.shape), gv.view(p.shape)
+                with torch.no_grad():
+                    pv.copy_(p.data)
+                p.data = pv
+                p.grad = gv
+                self.n_live += p.numel() * (2 if p.is_complex() else 1)
+            if mod is not None:
+                mod._grad_sink = self.flat_grad[base: base + n]
+
+    # -- pieces of a step ----------------------------------------------------------------
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def reduce_gradients(self):
+        """Sum over ranks in one collective; the 1/world of DDP's mean is folded into the Adam kernel."""
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    def optimizer_step(self):
+        self.step_count += 1
+        if self.flat_param.is_cuda:
+            ops.adam_step_flat(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr=self.lr,
+                               betas=self.betas, eps=self.eps, step=self.step_count, grad_scale=1.0 / self.world)
+        else:
+            # host-side logic tests (gloo, CPU tensors): same update written with torch ops
+            g = self.flat_grad / self.world
+            b1, b2 = self.betas
+            self.exp_avg.mul_(b1).add_(g, alpha=1 - b1)
+            self.exp_avg_sq.mul_(b2).addcmul_(g, g, value=1 - b2)
+            bc1, bc2 = 1 - b1 ** self.step_count, 1 - b2 ** self.step_count
+            denom = (self.exp_avg_sq.sqrt() / bc2 ** 0.5).add_(self.eps)
+            self.flat_param.addcdiv_(self.exp_avg, denom, value=-self.lr / bc1)
+
+    # -- the step --------------------------------------------------------------------------
+    def step(self, x: torch.Tensor, grid: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """zero_grad -> forward -> loss -> backward -> all-reduce -> Adam.  Returns the (device) loss."""
+        self.zero_grad()
+        pred = self.model(x, grid)
+        loss = self.loss_fn(pred, target)
+        loss.backward()
+        self.reduce_gradients()
+        self.optimizer_step()
+        return loss.detach()
+
+
+def shard_batch(n_samples: int, rank: int, world: int):
+    """Contiguous, near-even split of a global batch over ranks (samples are independent bags)."""
+    base, extra = divmod(n_samples, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)

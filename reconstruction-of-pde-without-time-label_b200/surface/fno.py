@@ -77,13 +77,16 @@ class _FnoBase(nn.Module):
         ps += [self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias]
         return ps
 
+    _grad_sink = None     # set by parallel.FlatTrainer: flat gradient buffer the backward kernels write into
+
     def forward(self, x):
-        return ops.fno_apply(self._spec(), self._params(), x_cl=x)
+        return ops.fno_apply(self._spec(), self._params(), x_cl=x, grad_sink=self._grad_sink)
 
     def encode_bags(self, bags, grid, idx=None, pool=None):
         """The per-snapshot NIO-FNO encoder: every snapshot of every bag, concatenated with the grid, through
         this net; with ``pool=(fc0.weight, fc0.bias)`` followed by the bag mean and the detached lift."""
-        return ops.fno_apply(self._spec(), self._params(), bags=bags, grid=grid, idx=idx, pool=pool)
+        return ops.fno_apply(self._spec(), self._params(), bags=bags, grid=grid, idx=idx, pool=pool,
+                             grad_sink=self._grad_sink)
 
 
 class FNO1d(_FnoBase):
