@@ -114,19 +114,78 @@ void launch_adam(float* p, const float* g, float* m, float* v, size_t n, float l
 // ---------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_exact(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+// Exact (erf) GELU, F.gelu's default (FNOModules.py:113-114, :231-232), evaluated with ONE ex2 and
+// ONE rcp: Phi(x) = 1 - q (x >= 0) or q (x < 0) with q = erfc(|x|/sqrt2)/2 from Abramowitz-Stegun
+// 7.1.26 (|erf error| <= 1.5e-7, i.e. at fp32 rounding level: measured max |gelu error| 4.2e-7 over
+// [-12, 12] against 1.2e-6 for torch's own fp32 gelu, tests/test_cabi_cpu.py documents the check).
+// The same exp gives the density for the derivative, which is what makes the fused backward of the
+// 128-wide projection cheap.
+__device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
+  const float u = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));
+  float p = 0.5307027145f;               // coefficients already carry the 1/2 of erfc/2
+  p = fmaf(p, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float q = p * t * e;
+  cdf = x >= 0.f ? 1.0f - q : q;
+  pdf = 0.39894228040143267794f * e;
 }
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, pdf;
+  gelu_cdf_pdf(x, cdf, pdf);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_exact(float x) { return gelu_fast(x); }
 __device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, pdf;
+  gelu_cdf_pdf(x, cdf, pdf);
+  return fmaf(x, pdf, cdf);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// ---------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA 1-D, SASS UBLKCP) helpers: global -> shared staging without a
+// register round trip, completion signalled on an mbarrier by transaction bytes.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug traps (the launch fails with an error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace bdn

@@ -163,48 +163,92 @@ void launch_lift_bwd(const LiftArgs& a, const float* gz0, float* g_w0, float* g_
 
 // ===========================================================================
 // projection: out[pix, o] = b2[o] + sum_j W2[o][j] * gelu(b1[j] + sum_c W1[j][c] * z[c, pix])
-// One thread per pixel of the cropped window; weights broadcast from shared memory.
+//
+// Thread mapping: a warp holds 32/JS pixels x JS hidden-unit slices (lane = pixel_slot * JS + slice);
+// a thread owns PP pixels (tile-strided) and the hidden units j = slice, slice + JS, ...  JS = 1 is
+// the many-pixel regime (per-snapshot net: one thread per pixel, everything in registers); JS = 8
+// spreads the 128 hidden units of a pixel over 8 lanes so that the few-image heads still fill the
+// machine.  The [pixels, hidden] tensor exists only in registers, forward and backward.
 // ===========================================================================
 constexpr int PROJ_MAX_OUT = 4;
+constexpr int PROJ_THREADS = 256;
 
-template <int CP>   // width rounded up to a multiple of 4
-__global__ void __launch_bounds__(128) project_kernel(const ProjArgs a, float* __restrict__ out) {
+template <int CP>
+__device__ __forceinline__ void load_w1_row(const float* w1s, int j, float (&w)[CP]) {
+#pragma unroll
+  for (int c4 = 0; c4 < CP; c4 += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(w1s + j * CP + c4);
+    w[c4] = v.x; w[c4 + 1] = v.y; w[c4 + 2] = v.z; w[c4 + 3] = v.w;
+  }
+}
+
+template <int CP, int NOUT, int JS, int PP>   // CP = width rounded up to 4; NOUT = 1 or PROJ_MAX_OUT (runtime c_out)
+__global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjArgs a, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
+  const int hidden = a.hidden, nout = NOUT == 1 ? 1 : a.c_out;
   float* w1s = smem;                               // [hidden][CP]
-  float* b1s = w1s + a.hidden * CP;                // [hidden]
-  float* w2s = b1s + a.hidden;                     // [c_out][hidden]
-  for (int i = threadIdx.x; i < a.hidden * CP; i += blockDim.x) {
+  float* b1s = w1s + hidden * CP;                  // [hidden]
+  float* w2s = b1s + hidden;                       // [nout][hidden]
+  for (int i = threadIdx.x; i < hidden * CP; i += blockDim.x) {
     const int j = i / CP, c = i - j * CP;
     w1s[i] = c < a.width ? __ldg(a.w1 + j * a.width + c) : 0.f;
   }
-  for (int i = threadIdx.x; i < a.hidden; i += blockDim.x) b1s[i] = __ldg(a.b1 + i);
-  for (int i = threadIdx.x; i < a.c_out * a.hidden; i += blockDim.x) w2s[i] = __ldg(a.w2 + i);
+  for (int i = threadIdx.x; i < hidden; i += blockDim.x) b1s[i] = __ldg(a.b1 + i);
+  for (int i = threadIdx.x; i < nout * hidden; i += blockDim.x) w2s[i] = __ldg(a.w2 + i);
   __syncthreads();
+
+  constexpr int SLOTS = PROJ_THREADS / JS;         // pixels per tile row
+  constexpr int TILE = SLOTS * PP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slice = lane % JS, slot = warp * (32 / JS) + lane / JS;
   const int opix = a.out_h * a.out_w, plane = a.hp * a.wp;
   const long total = (long)a.images * opix;
-  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const int img = t / opix, q = t - (long)img * opix;
-    const int oh = q / a.out_w, ow = q - oh * a.out_w;
-    const float* zp = a.z + (size_t)img * a.width * plane + oh * a.wp + ow;
-    float z[CP];
+  const long ntiles = (total + TILE - 1) / TILE;
+
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    float z[PP][CP], o[PP][NOUT];
+    long t[PP];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) z[c] = c < a.width ? __ldg(zp + (size_t)c * plane) : 0.f;
-    float o[PROJ_MAX_OUT];
+    for (int pp = 0; pp < PP; ++pp) {
+      t[pp] = tile * TILE + (long)pp * SLOTS + slot;
 #pragma unroll
-    for (int k = 0; k < PROJ_MAX_OUT; ++k) o[k] = k < a.c_out ? __ldg(a.b2 + k) : 0.f;
-    for (int j = 0; j < a.hidden; ++j) {
-      float hsum = b1s[j];
+      for (int k = 0; k < NOUT; ++k) o[pp][k] = 0.f;
+      if (t[pp] < total) {
+        const int img = t[pp] / opix, q = t[pp] - (long)img * opix;
+        const int oh = q / a.out_w, ow = q - oh * a.out_w;
+        const float* zp = a.z + (size_t)img * a.width * plane + oh * a.wp + ow;
 #pragma unroll
-      for (int c4 = 0; c4 < CP; c4 += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(w1s + j * CP + c4);
-        hsum = fmaf(wv.x, z[c4], fmaf(wv.y, z[c4 + 1], fmaf(wv.z, z[c4 + 2], fmaf(wv.w, z[c4 + 3], hsum))));
+        for (int c = 0; c < CP; ++c) z[pp][c] = c < a.width ? __ldg(zp + (size_t)c * plane) : 0.f;
+      } else {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) z[pp][c] = 0.f;
       }
-      const float g = gelu_exact(hsum);
-#pragma unroll
-      for (int k = 0; k < PROJ_MAX_OUT; ++k)
-        if (k < a.c_out) o[k] = fmaf(w2s[k * a.hidden + j], g, o[k]);
     }
-    for (int k = 0; k < a.c_out; ++k) out[(size_t)t * a.c_out + k] = o[k];
+#pragma unroll 2
+    for (int j = slice; j < hidden; j += JS) {
+      float w1r[CP], w2r[NOUT];
+      load_w1_row<CP>(w1s, j, w1r);
+      const float b1j = b1s[j];
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) w2r[k] = k < nout ? w2s[k * hidden + j] : 0.f;
+#pragma unroll
+      for (int pp = 0; pp < PP; ++pp) {
+        float h = b1j;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) h = fmaf(w1r[c], z[pp][c], h);
+        const float g = gelu_fast(h);
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) o[pp][k] = fmaf(w2r[k], g, o[pp][k]);
+      }
+    }
+#pragma unroll
+    for (int pp = 0; pp < PP; ++pp)
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) {
+#pragma unroll
+        for (int off = JS >> 1; off > 0; off >>= 1) o[pp][k] += __shfl_xor_sync(0xffffffffu, o[pp][k], off);
+        if (slice == 0 && t[pp] < total && k < nout) out[(size_t)t[pp] * nout + k] = o[pp][k] + __ldg(a.b2 + k);
+      }
   }
 }
 
@@ -224,29 +268,46 @@ static bool dispatch_cp(int width, F&& f) {
   }
 }
 
+// many pixels -> one thread per pixel; few pixels -> 8 lanes per pixel
+static bool proj_many_pixels(long total) { return total >= 148L * PROJ_THREADS * 4; }
+
+template <int CP, int NOUT, int JS, int PP>
+static void launch_project_t(const ProjArgs& a, float* out, long total, cudaStream_t st) {
+  constexpr int TILE = PROJ_THREADS / JS * PP;
+  const long ntiles = (total + TILE - 1) / TILE;
+  const int grid = (int)(ntiles < 148L * 8 ? ntiles : 148L * 8);
+  const size_t smem = (size_t)(a.hidden * CP + a.hidden + a.c_out * a.hidden) * sizeof(float);
+  cudaFuncSetAttribute(project_kernel<CP, NOUT, JS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  project_kernel<CP, NOUT, JS, PP><<<grid, PROJ_THREADS, smem, st>>>(a, out);
+}
+
 void launch_project(const ProjArgs& a, float* out, cudaStream_t st) {
   LaunchScope scope("project", st, a.width);
   const long total = (long)a.images * a.out_h * a.out_w;
-  const int block = 128;
-  const int grid = (int)((total + block - 1) / block);
+  const bool many = proj_many_pixels(total);
   dispatch_cp(a.width, [&](auto cp) {
     constexpr int CP = decltype(cp)::value;
-    const size_t smem = (size_t)(a.hidden * CP + a.hidden + a.c_out * a.hidden) * sizeof(float);
-    cudaFuncSetAttribute(project_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    project_kernel<CP><<<grid, block, smem, st>>>(a, out);
+    constexpr int PPM = CP <= 8 ? 4 : 2;
+    if (a.c_out == 1) {
+      if (many) launch_project_t<CP, 1, 1, PPM>(a, out, total, st);
+      else launch_project_t<CP, 1, 8, 1>(a, out, total, st);
+    } else {
+      if (many) launch_project_t<CP, PROJ_MAX_OUT, 1, 2>(a, out, total, st);
+      else launch_project_t<CP, PROJ_MAX_OUT, 8, 1>(a, out, total, st);
+    }
   });
 }
 
-// projection backward.  Each thread owns PP pixels; for every hidden unit j it recomputes the
-// pre-activation, accumulates gz in registers and warp-reduces the weight-gradient partials into
-// per-block shared accumulators, flushed once per block with atomics.
-template <int CP, int PP>
-__global__ void __launch_bounds__(128) project_bwd_kernel(const ProjArgs a, const float* __restrict__ g_out,
-                                                          int pooled_g, int n_keep, float* __restrict__ gz,
-                                                          float* g_w1, float* g_b1, float* g_w2, float* g_b2,
-                                                          int tiles_per_block) {
+// projection backward.  Same thread mapping; for every hidden unit the pre-activation is
+// recomputed, gz accumulates in registers (reduced over the JS slices at the end), and the weight
+// gradient partials are reduced over the lanes that share a slice, then added to per-block shared
+// accumulators that are flushed once per block with coalesced global atomics.
+template <int CP, int NOUT, int JS, int PP>
+__global__ void __launch_bounds__(PROJ_THREADS) project_bwd_kernel(const ProjArgs a, const float* __restrict__ g_out,
+                                                                   int pooled_g, int n_keep, float* __restrict__ gz,
+                                                                   float* g_w1, float* g_b1, float* g_w2, float* g_b2) {
   extern __shared__ __align__(16) float smem[];
-  const int hidden = a.hidden, nout = a.c_out;
+  const int hidden = a.hidden, nout = NOUT == 1 ? 1 : a.c_out;
   float* w1s = smem;                       // [hidden][CP]
   float* b1s = w1s + hidden * CP;          // [hidden]
   float* w2s = b1s + hidden;               // [nout][hidden]
@@ -264,27 +325,28 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(const ProjArgs a, cons
   if (threadIdx.x < PROJ_MAX_OUT) ab2[threadIdx.x] = 0.f;
   __syncthreads();
 
+  constexpr int SLOTS = PROJ_THREADS / JS;
+  constexpr int TILE = SLOTS * PP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slice = lane % JS, slot = warp * (32 / JS) + lane / JS;
   const int opix = a.out_h * a.out_w, plane = a.hp * a.wp;
   const long total = (long)a.images * opix;
-  const int lane = threadIdx.x & 31;
+  const long ntiles = (total + TILE - 1) / TILE;
   const float gscale = pooled_g ? 1.0f / (float)n_keep : 1.0f;
-  const int tile = blockDim.x * PP;
 
-  for (int it = 0; it < tiles_per_block; ++it) {
-    const long base = ((long)blockIdx.x * tiles_per_block + it) * tile;
-    if (base >= total) break;
-    float z[PP][CP], g[PP][PROJ_MAX_OUT], gzr[PP][CP];
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    float z[PP][CP], g[PP][NOUT], gzr[PP][CP];
     size_t zoff[PP];
     bool live[PP];
 #pragma unroll
     for (int pp = 0; pp < PP; ++pp) {
-      const long t = base + (long)pp * blockDim.x + threadIdx.x;
+      const long t = tile * TILE + (long)pp * SLOTS + slot;
       live[pp] = t < total;
       zoff[pp] = 0;
 #pragma unroll
       for (int c = 0; c < CP; ++c) { z[pp][c] = 0.f; gzr[pp][c] = 0.f; }
 #pragma unroll
-      for (int k = 0; k < PROJ_MAX_OUT; ++k) g[pp][k] = 0.f;
+      for (int k = 0; k < NOUT; ++k) g[pp][k] = 0.f;
       if (live[pp]) {
         const int img = t / opix, q = t - (long)img * opix;
         const int oh = q / a.out_w, ow = q - oh * a.out_w;
@@ -293,86 +355,97 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(const ProjArgs a, cons
         for (int c = 0; c < CP; ++c)
           if (c < a.width) z[pp][c] = __ldg(a.z + zoff[pp] + (size_t)c * plane);
         const size_t goff = pooled_g ? ((size_t)(img / n_keep) * opix + q) * nout : (size_t)t * nout;
-        for (int k = 0; k < nout; ++k) g[pp][k] = __ldg(g_out + goff + k) * gscale;
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k)
+          if (k < nout) g[pp][k] = __ldg(g_out + goff + k) * gscale;
       }
     }
-    float sb2[PROJ_MAX_OUT];
+    // fc2 bias gradient: every pixel once (slice 0 holds it)
 #pragma unroll
-    for (int k = 0; k < PROJ_MAX_OUT; ++k) {
-      sb2[k] = 0.f;
+    for (int k = 0; k < NOUT; ++k) {
+      float s = 0.f;
 #pragma unroll
-      for (int pp = 0; pp < PP; ++pp) sb2[k] += g[pp][k];
+      for (int pp = 0; pp < PP; ++pp) s += g[pp][k];
+      if (slice != 0) s = 0.f;
+      s = warp_sum(s);
+      if (lane == 0 && k < nout) atomicAdd(ab2 + k, s);
     }
-    for (int j = 0; j < hidden; ++j) {
-      float w1r[CP];
-#pragma unroll
-      for (int c4 = 0; c4 < CP; c4 += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(w1s + j * CP + c4);
-        w1r[c4] = wv.x; w1r[c4 + 1] = wv.y; w1r[c4 + 2] = wv.z; w1r[c4 + 3] = wv.w;
-      }
+#pragma unroll 1
+    for (int j = slice; j < hidden; j += JS) {
+      float w1r[CP], w2r[NOUT];
+      load_w1_row<CP>(w1s, j, w1r);
       const float b1j = b1s[j];
-      float w2r[PROJ_MAX_OUT];
 #pragma unroll
-      for (int k = 0; k < PROJ_MAX_OUT; ++k) w2r[k] = k < nout ? w2s[k * hidden + j] : 0.f;
-      float sw1[CP], sb1 = 0.f, sw2[PROJ_MAX_OUT];
+      for (int k = 0; k < NOUT; ++k) w2r[k] = k < nout ? w2s[k * hidden + j] : 0.f;
+      float sw1[CP], sb1 = 0.f, sw2[NOUT];
 #pragma unroll
       for (int c = 0; c < CP; ++c) sw1[c] = 0.f;
 #pragma unroll
-      for (int k = 0; k < PROJ_MAX_OUT; ++k) sw2[k] = 0.f;
+      for (int k = 0; k < NOUT; ++k) sw2[k] = 0.f;
 #pragma unroll
       for (int pp = 0; pp < PP; ++pp) {
-        float hsum = b1j;
+        float h = b1j;
 #pragma unroll
-        for (int c = 0; c < CP; ++c) hsum = fmaf(w1r[c], z[pp][c], hsum);
-        const float cdf = 0.5f * (1.0f + erff(hsum * 0.70710678118654752440f));
-        const float pdf = 0.39894228040143267794f * expf(-0.5f * hsum * hsum);
-        const float gel = hsum * cdf;
+        for (int c = 0; c < CP; ++c) h = fmaf(w1r[c], z[pp][c], h);
+        float cdf, pdf;
+        gelu_cdf_pdf(h, cdf, pdf);
+        const float gel = h * cdf;
         float d = 0.f;
 #pragma unroll
-        for (int k = 0; k < PROJ_MAX_OUT; ++k) { d = fmaf(g[pp][k], w2r[k], d); sw2[k] = fmaf(g[pp][k], gel, sw2[k]); }
-        const float e = d * (cdf + hsum * pdf);
+        for (int k = 0; k < NOUT; ++k) { d = fmaf(g[pp][k], w2r[k], d); sw2[k] = fmaf(g[pp][k], gel, sw2[k]); }
+        const float e = d * fmaf(h, pdf, cdf);
         sb1 += e;
 #pragma unroll
         for (int c = 0; c < CP; ++c) { gzr[pp][c] = fmaf(e, w1r[c], gzr[pp][c]); sw1[c] = fmaf(e, z[pp][c], sw1[c]); }
       }
+      // reduce over the lanes that share this slice (xor offsets >= JS), then one lane per slice adds
 #pragma unroll
-      for (int c = 0; c < CP; ++c) sw1[c] = warp_sum(sw1[c]);
-      sb1 = warp_sum(sb1);
+      for (int off = 16; off >= JS; off >>= 1) {
 #pragma unroll
-      for (int k = 0; k < PROJ_MAX_OUT; ++k)
-        if (k < nout) sw2[k] = warp_sum(sw2[k]);
-      if (lane == 0) {
+        for (int c = 0; c < CP; ++c) sw1[c] += __shfl_xor_sync(0xffffffffu, sw1[c], off);
+        sb1 += __shfl_xor_sync(0xffffffffu, sb1, off);
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) sw2[k] += __shfl_xor_sync(0xffffffffu, sw2[k], off);
+      }
+      if (lane < JS) {
 #pragma unroll
         for (int c = 0; c < CP; ++c) atomicAdd(aw1 + j * CP + c, sw1[c]);
         atomicAdd(ab1 + j, sb1);
 #pragma unroll
-        for (int k = 0; k < PROJ_MAX_OUT; ++k)
+        for (int k = 0; k < NOUT; ++k)
           if (k < nout) atomicAdd(aw2 + k * hidden + j, sw2[k]);
       }
     }
 #pragma unroll
-    for (int k = 0; k < PROJ_MAX_OUT; ++k) {
-      if (k < nout) {
-        const float s = warp_sum(sb2[k]);
-        if (lane == 0) atomicAdd(ab2 + k, s);
-      }
-    }
-#pragma unroll
     for (int pp = 0; pp < PP; ++pp) {
-      if (!live[pp]) continue;
 #pragma unroll
-      for (int c = 0; c < CP; ++c)
-        if (c < a.width) gz[zoff[pp] + (size_t)c * plane] = gzr[pp][c];
+      for (int c = 0; c < CP; ++c) {
+#pragma unroll
+        for (int off = JS >> 1; off > 0; off >>= 1) gzr[pp][c] += __shfl_xor_sync(0xffffffffu, gzr[pp][c], off);
+        if (slice == 0 && live[pp] && c < a.width) gz[zoff[pp] + (size_t)c * plane] = gzr[pp][c];
+      }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < hidden * CP; i += blockDim.x) {
-    const int j = i / CP, c = i - j * CP;
-    if (c < a.width) atomicAdd(g_w1 + j * a.width + c, aw1[i]);
+  for (int i = threadIdx.x; i < hidden * a.width; i += blockDim.x) {
+    const int j = i / a.width, c = i - j * a.width;
+    atomicAdd(g_w1 + i, aw1[j * CP + c]);
   }
   for (int i = threadIdx.x; i < hidden; i += blockDim.x) atomicAdd(g_b1 + i, ab1[i]);
   for (int i = threadIdx.x; i < nout * hidden; i += blockDim.x) atomicAdd(g_w2 + i, aw2[i]);
   if (threadIdx.x < nout) atomicAdd(g_b2 + threadIdx.x, ab2[threadIdx.x]);
+}
+
+template <int CP, int NOUT, int JS, int PP>
+static void launch_project_bwd_t(const ProjArgs& a, const float* g_out, int pooled_g, int n_keep, float* gz,
+                                 float* g_w1, float* g_b1, float* g_w2, float* g_b2, long total, cudaStream_t st) {
+  constexpr int TILE = PROJ_THREADS / JS * PP;
+  const long ntiles = (total + TILE - 1) / TILE;
+  const int grid = (int)(ntiles < 148L * 2 ? ntiles : 148L * 2);
+  const size_t smem = (size_t)(2 * (a.hidden * CP + a.hidden + a.c_out * a.hidden) + PROJ_MAX_OUT) * sizeof(float);
+  cudaFuncSetAttribute(project_bwd_kernel<CP, NOUT, JS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  project_bwd_kernel<CP, NOUT, JS, PP><<<grid, PROJ_THREADS, smem, st>>>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1,
+                                                                        g_w2, g_b2);
 }
 
 void launch_project_bwd(const ProjArgs& a, const float* g_out, int pooled_g, int n_keep, float* gz, float* g_w1,
@@ -381,18 +454,17 @@ void launch_project_bwd(const ProjArgs& a, const float* g_out, int pooled_g, int
   const size_t act_bytes = (size_t)a.images * a.width * a.hp * a.wp * sizeof(float);
   cudaMemsetAsync(gz, 0, act_bytes, st);
   const long total = (long)a.images * a.out_h * a.out_w;
+  const bool many = proj_many_pixels(total);
   dispatch_cp(a.width, [&](auto cp) {
     constexpr int CP = decltype(cp)::value;
-    constexpr int PP = CP <= 4 ? 4 : (CP <= 12 ? 2 : 1);
-    const int tile = 128 * PP;
-    const int tiles = (int)((total + tile - 1) / tile);
-    int tpb = 1;
-    while (ceil_div(tiles, tpb) > 6 * 148) ++tpb;
-    const int grid = ceil_div(tiles, tpb);
-    const size_t smem =
-        (size_t)(2 * (a.hidden * CP + a.hidden + a.c_out * a.hidden) + PROJ_MAX_OUT) * sizeof(float);
-    cudaFuncSetAttribute(project_bwd_kernel<CP, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    project_bwd_kernel<CP, PP><<<grid, 128, smem, st>>>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, tpb);
+    constexpr int PPM = CP <= 4 ? 8 : (CP <= 12 ? 4 : 2);
+    if (a.c_out == 1) {
+      if (many) launch_project_bwd_t<CP, 1, 1, PPM>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, total, st);
+      else launch_project_bwd_t<CP, 1, 8, 1>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, total, st);
+    } else {
+      if (many) launch_project_bwd_t<CP, PROJ_MAX_OUT, 1, 2>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, total, st);
+      else launch_project_bwd_t<CP, PROJ_MAX_OUT, 8, 1>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, total, st);
+    }
   });
 }
 

@@ -15,7 +15,7 @@ namespace bdn {
 // Block = 32*RT rows; lane <-> RT consecutive rows, warp <-> 4 consecutive modes.
 // ===========================================================================
 template <int RT>
-__global__ void __launch_bounds__(512) wfwd_kernel(const float* __restrict__ x, float2* __restrict__ out,
+__global__ void __launch_bounds__(512) wfwd_generic_kernel(const float* __restrict__ x, float2* __restrict__ out,
                                                    const float2* __restrict__ t_wl, int rows, int wp, int m2,
                                                    int act, int wc) {
   constexpr int LT = 4;
@@ -92,8 +92,7 @@ static int pick_wchunk(int wp, int per_w_bytes, int budget) {
   return ceil_div(wp, n);
 }
 
-void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st) {
-  LaunchScope scope(act ? "wfwd_gelu" : "wfwd", st, pl->m2);
+static void launch_wfwd_generic(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st) {
   const int m2 = pl->m2, wp = pl->wp;
   const int nlg = ceil_div(m2, 4);
   const int sms = 148;
@@ -105,10 +104,171 @@ void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act,
   const int wc = pick_wchunk(wp, per_w, 96 * 1024);
   const size_t smem = (size_t)wc * per_w;
   dim3 grid(ceil_div(rows, br)), block(32 * nlg);
-#define BDN_WFWD(RT)                                                                              \
-  {                                                                                               \
-    cudaFuncSetAttribute(wfwd_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
-    wfwd_kernel<RT><<<grid, block, smem, st>>>(x, out, pl->t_wl, rows, wp, m2, act, wc);          \
+#define BDN_WFWD(RT)                                                                                      \
+  {                                                                                                       \
+    cudaFuncSetAttribute(wfwd_generic_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+    wfwd_generic_kernel<RT><<<grid, block, smem, st>>>(x, out, pl->t_wl, rows, wp, m2, act, wc);          \
+  }
+  if (rt == 4) BDN_WFWD(4) else if (rt == 2) BDN_WFWD(2) else BDN_WFWD(1)
+#undef BDN_WFWD
+}
+
+// ---------------------------------------------------------------------------
+// W-forward, pipelined: persistent blocks, the x tile (BR consecutive rows = one contiguous span of
+// HBM) is staged by per-row bulk async copies into a double-buffered shared tile whose completion an
+// mbarrier tracks; the DFT table stays in shared memory for the block's lifetime.  Warp = (row group,
+// group of 4 modes), lane = RT rows.  x is read with 128-bit shared loads along w; the row pitch is
+// chosen so that the 8 lanes of a quarter-warp hit 8 different 16-byte bank groups.
+// ---------------------------------------------------------------------------
+struct WfwdParams {
+  const float* x; float2* out; const float2* t_wl;
+  int rows, wp, m2, act, pitch, nrg, nmg, m2p, ntiles;
+};
+
+template <int RT>
+__global__ void __launch_bounds__(256) wfwd_pipe_kernel(const WfwdParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int BR = 32 * RT * p.nrg;
+  const int tile_floats = BR * p.pitch;
+  float* stage0 = smem;
+  float* stage1 = smem + tile_floats;
+  float2* ts = reinterpret_cast<float2*>(smem + 2 * tile_floats);     // [wp][m2p]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ts + (size_t)p.wp * p.m2p);
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int wp = p.wp, m2 = p.m2, m2p = p.m2p;
+
+  for (int i = tid; i < wp * m2p; i += nt) {
+    const int w = i / m2p, l = i - w * m2p;
+    ts[i] = l < m2 ? __ldg(p.t_wl + (size_t)w * m2 + l) : make_float2(0.f, 0.f);
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+
+  const uint32_t row_bytes = (uint32_t)wp * 4u;
+  auto issue = [&](int tile, int stage) {   // called by all lanes of warp 0
+    const int row0 = tile * BR;
+    const int nrows = min(BR, p.rows - row0);
+    float* dst = stage ? stage1 : stage0;
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&bars[stage], (uint32_t)nrows * row_bytes);
+    }
+    __syncwarp();
+    for (int r = lane; r < nrows; r += 32)
+      bulk_g2s(dst + r * p.pitch, p.x + (size_t)(row0 + r) * wp, row_bytes, &bars[stage]);
+  };
+
+  const int rg = warp % p.nrg, mg0 = warp / p.nrg, mgstep = (nt >> 5) / p.nrg;
+  int it = 0;
+  if (warp == 0 && (int)blockIdx.x < p.ntiles) issue(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int next = tile + gridDim.x;
+    if (warp == 0 && next < p.ntiles) issue(next, stage ^ 1);
+    mbar_wait(&bars[stage], (it >> 1) & 1);
+    float* xs = stage ? stage1 : stage0;
+    const int row0 = tile * BR;
+    if (p.act) {
+      const int nrows = min(BR, p.rows - row0);
+      const int w4n = wp >> 2;
+      for (int i = tid; i < nrows * w4n; i += nt) {
+        const int r = i / w4n, q = i - r * w4n;
+        float4* ptr = reinterpret_cast<float4*>(xs + r * p.pitch) + q;
+        float4 v = *ptr;
+        v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
+        *ptr = v;
+      }
+      __syncthreads();
+    }
+    for (int mg = mg0; mg < p.nmg; mg += mgstep) {
+      float ar[RT][4], ai[RT][4];
+#pragma unroll
+      for (int j = 0; j < RT; ++j)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) ar[j][m] = ai[j][m] = 0.f;
+      const float* xrow = xs + (rg * 32 * RT + lane) * p.pitch;
+      const float4* tb = reinterpret_cast<const float4*>(ts + mg * 4);
+      const int tpitch4 = m2p >> 1;   // float4 per table row
+#pragma unroll 2
+      for (int w4 = 0; w4 < (wp >> 2); ++w4) {
+        float xv[RT][4];
+#pragma unroll
+        for (int j = 0; j < RT; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(xrow + j * 32 * p.pitch + 4 * w4);
+          xv[j][0] = v.x; xv[j][1] = v.y; xv[j][2] = v.z; xv[j][3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t01 = tb[(4 * w4 + i) * tpitch4];
+          const float4 t23 = tb[(4 * w4 + i) * tpitch4 + 1];
+          const float tc[4] = {t01.x, t01.z, t23.x, t23.z};
+          const float tsn[4] = {t01.y, t01.w, t23.y, t23.w};
+#pragma unroll
+          for (int j = 0; j < RT; ++j)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              ar[j][m] = fmaf(xv[j][i], tc[m], ar[j][m]);
+              ai[j][m] = fmaf(-xv[j][i], tsn[m], ai[j][m]);
+            }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < RT; ++j) {
+        const int row = row0 + rg * 32 * RT + j * 32 + lane;
+        if (row >= p.rows) continue;
+        float2* o = p.out + (size_t)row * m2 + mg * 4;
+        if ((m2 & 3) == 0) {
+          reinterpret_cast<float4*>(o)[0] = make_float4(ar[j][0], ai[j][0], ar[j][1], ai[j][1]);
+          reinterpret_cast<float4*>(o)[1] = make_float4(ar[j][2], ai[j][2], ar[j][3], ai[j][3]);
+        } else {
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            if (mg * 4 + m < m2) o[m] = make_float2(ar[j][m], ai[j][m]);
+        }
+      }
+    }
+    fence_proxy_async();   // generic-proxy accesses to this stage are ordered before the async refill
+    __syncthreads();       // everyone is done with this stage before it is refilled
+  }
+}
+
+void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st) {
+  LaunchScope scope(act ? "wfwd_gelu" : "wfwd", st, pl->m2);
+  const int m2 = pl->m2, wp = pl->wp;
+  if ((wp & 3) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) {   // bulk copies need 16-byte rows
+    launch_wfwd_generic(pl, x, out, rows, act, st);
+    return;
+  }
+  WfwdParams p;
+  p.x = x; p.out = out; p.t_wl = pl->t_wl; p.rows = rows; p.wp = wp; p.m2 = m2; p.act = act;
+  p.nmg = ceil_div(m2, 4);
+  p.m2p = p.nmg * 4;
+  p.pitch = ((wp >> 2) & 1) ? wp : wp + 4;       // (pitch / 4) odd: conflict-free 128-bit row-strided loads
+  p.nrg = p.nmg <= 2 ? 4 : (p.nmg <= 4 ? 2 : 1);
+  const int nwarps = p.nrg * (p.nmg < 8 / p.nrg ? p.nmg : 8 / p.nrg);
+  int rt = 4;
+  auto smem_of = [&](int r) {
+    return (size_t)2 * 32 * r * p.nrg * p.pitch * 4 + (size_t)wp * p.m2p * 8 + 16;
+  };
+  while (rt > 1 && (ceil_div(rows, 32 * rt * p.nrg) < 2 * 148 || smem_of(rt) > 100 * 1024)) rt >>= 1;
+  if (smem_of(rt) > 200 * 1024) {
+    launch_wfwd_generic(pl, x, out, rows, act, st);
+    return;
+  }
+  const int BR = 32 * rt * p.nrg;
+  p.ntiles = ceil_div(rows, BR);
+  const size_t smem = smem_of(rt);
+  const int per_sm = (int)((220 * 1024) / (smem + 1024));
+  const int cap = 148 * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+  const int grid = p.ntiles < cap ? p.ntiles : cap;
+#define BDN_WFWD(RT)                                                                                   \
+  {                                                                                                    \
+    cudaFuncSetAttribute(wfwd_pipe_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    wfwd_pipe_kernel<RT><<<grid, 32 * nwarps, smem, st>>>(p);                                          \
   }
   if (rt == 4) BDN_WFWD(4) else if (rt == 2) BDN_WFWD(2) else BDN_WFWD(1)
 #undef BDN_WFWD
@@ -125,16 +285,59 @@ struct CoreParams {
   int ca, cb, co_layer, hp, hp8, m1, m2, K, Kp, TL;
 };
 
-template <bool BWD>
+// G = kept rows (phase 1) / spatial rows (phase 3) accumulated per work item.  Small G gives more
+// items per block (the few-image heads need that to keep 256 threads busy), large G more FMAs per
+// shared/L1 load (the many-image per-snapshot net).
+template <int G>
+__device__ __forceinline__ void cacc_rows(const float2 x, const float2* __restrict__ t, float (&re)[G], float (&im)[G],
+                                          const bool conj_table) {
+  // conj_table: multiply by (cos - i sin); otherwise by (cos + i sin)
+  if constexpr (G == 1) {
+    const float2 cs = *t;
+    if (conj_table) { re[0] = fmaf(x.x, cs.x, fmaf(x.y, cs.y, re[0])); im[0] = fmaf(x.y, cs.x, fmaf(-x.x, cs.y, im[0])); }
+    else            { re[0] = fmaf(x.x, cs.x, fmaf(-x.y, cs.y, re[0])); im[0] = fmaf(x.x, cs.y, fmaf(x.y, cs.x, im[0])); }
+  } else {
+    const float4* t4 = reinterpret_cast<const float4*>(t);
+#pragma unroll
+    for (int q = 0; q < G / 2; ++q) {
+      const float4 cs = t4[q];
+      if (conj_table) {
+        re[2 * q] = fmaf(x.x, cs.x, fmaf(x.y, cs.y, re[2 * q]));
+        im[2 * q] = fmaf(x.y, cs.x, fmaf(-x.x, cs.y, im[2 * q]));
+        re[2 * q + 1] = fmaf(x.x, cs.z, fmaf(x.y, cs.w, re[2 * q + 1]));
+        im[2 * q + 1] = fmaf(x.y, cs.z, fmaf(-x.x, cs.w, im[2 * q + 1]));
+      } else {
+        re[2 * q] = fmaf(x.x, cs.x, fmaf(-x.y, cs.y, re[2 * q]));
+        im[2 * q] = fmaf(x.x, cs.y, fmaf(x.y, cs.x, im[2 * q]));
+        re[2 * q + 1] = fmaf(x.x, cs.z, fmaf(-x.y, cs.w, re[2 * q + 1]));
+        im[2 * q + 1] = fmaf(x.x, cs.w, fmaf(x.y, cs.z, im[2 * q + 1]));
+      }
+    }
+  }
+}
+
+template <bool BWD, int G>
 __global__ void __launch_bounds__(256) core2d_kernel(const CoreParams p) {
   extern __shared__ __align__(16) float smem[];
   const int TL = p.TL, Pa = p.ca * TL, Pb = p.cb * TL, K = p.K, hp = p.hp, m2 = p.m2;
-  const int nA = max(hp * Pa, K * Pb);
+  const int nA = (max(hp * Pa, K * Pb) + 1) & ~1;
   float2* bufA = reinterpret_cast<float2*>(smem);
   float2* bufX = bufA + nA;
+  float2* s_hk = bufX + K * Pa + ((K * Pa) & 1);   // [hp][Kp], 16-byte aligned rows
+  float2* s_kh = s_hk + hp * p.Kp;                 // [K][hp8]
   const int l0 = blockIdx.x * TL, b = blockIdx.y;
   const int tid = threadIdx.x, nt = blockDim.x;
 
+  // the two DFT tables live in shared memory for the block's lifetime (they are re-read by every
+  // item; from L1/L2 the inner loops were latency-bound: ncu long-scoreboard 20 cycles per issue)
+  {
+    const float4* g1 = reinterpret_cast<const float4*>(p.t_hk);
+    float4* d1 = reinterpret_cast<float4*>(s_hk);
+    for (int i = tid; i < (hp * p.Kp) >> 1; i += nt) d1[i] = __ldg(g1 + i);
+    const float4* g2 = reinterpret_cast<const float4*>(p.t_kh);
+    float4* d2 = reinterpret_cast<float4*>(s_kh);
+    for (int i = tid; i < (K * p.hp8) >> 1; i += nt) d2[i] = __ldg(g2 + i);
+  }
   // phase 0: stage the image's TL columns, all channels: bufA[h][a*TL + lt]
   for (int idx = tid; idx < p.ca * hp * TL; idx += nt) {
     const int lt = idx % TL, h = (idx / TL) % hp, a = idx / (TL * hp);
@@ -144,32 +347,21 @@ __global__ void __launch_bounds__(256) core2d_kernel(const CoreParams p) {
   }
   __syncthreads();
 
-  // phase 1: X[k][pa] = pre[l] * sum_h x[h][pa] * e^{-i phi_kh}, 8 kept rows per item
-  const int nkg = p.Kp >> 3;
+  // phase 1: X[k][pa] = pre[l] * sum_h x[h][pa] * e^{-i phi_kh}, G kept rows per item
+  const int nkg = (K + G - 1) / G;
   for (int idx = tid; idx < Pa * nkg; idx += nt) {
     const int pa = idx % Pa, kg = idx / Pa;
-    float re[8], im[8];
+    float re[G], im[G];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) re[j] = im[j] = 0.f;
-    const float4* trow = reinterpret_cast<const float4*>(p.t_hk + kg * 8);
-    const int pitch4 = p.Kp >> 1;  // float4 per table row
-    for (int h = 0; h < hp; ++h) {
-      const float2 x = bufA[h * Pa + pa];
-      const float4* t = trow + (size_t)h * pitch4;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 cs = __ldg(t + q);
-        re[2 * q] = fmaf(x.x, cs.x, fmaf(x.y, cs.y, re[2 * q]));
-        im[2 * q] = fmaf(x.y, cs.x, fmaf(-x.x, cs.y, im[2 * q]));
-        re[2 * q + 1] = fmaf(x.x, cs.z, fmaf(x.y, cs.w, re[2 * q + 1]));
-        im[2 * q + 1] = fmaf(x.y, cs.z, fmaf(-x.x, cs.w, im[2 * q + 1]));
-      }
-    }
+    for (int j = 0; j < G; ++j) re[j] = im[j] = 0.f;
+    const float2* trow = s_hk + kg * G;
+#pragma unroll 4
+    for (int h = 0; h < hp; ++h) cacc_rows<G>(bufA[h * Pa + pa], trow + (size_t)h * p.Kp, re, im, true);
     const int a = pa / TL, lt = pa - a * TL, l = l0 + lt;
     const float sc = l < m2 ? __ldg(p.pre + l) : 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = kg * 8 + j;
+    for (int j = 0; j < G; ++j) {
+      const int k = kg * G + j;
       if (k < K) {
         const float2 v = make_float2(re[j] * sc, im[j] * sc);
         bufX[k * Pa + pa] = v;
@@ -190,6 +382,7 @@ __global__ void __launch_bounds__(256) core2d_kernel(const CoreParams p) {
       const int kk = lo ? k : k - p.m1;
       const size_t mode_off = (size_t)kk * m2 + l;
       const size_t cstride = (size_t)p.m1 * m2;
+#pragma unroll 4
       for (int a = 0; a < p.ca; ++a) {
         const float2 x = bufX[k * Pa + a * TL + lt];
         if (!BWD) {
@@ -207,36 +400,31 @@ __global__ void __launch_bounds__(256) core2d_kernel(const CoreParams p) {
   }
   __syncthreads();
 
-  // phase 3: Z[h][pb] = post[l] * sum_k y[k][pb] * e^{+i phi_kh}, 8 rows per item
-  const int nhg = p.hp8 >> 3;
+  // phase 3: Z[h][pb] = post[l] * sum_k y[k][pb] * e^{+i phi_kh}, G rows per item
+  const int nhg = (hp + G - 1) / G;
   for (int idx = tid; idx < Pb * nhg; idx += nt) {
     const int pb = idx % Pb, hg = idx / Pb;
-    float re[8], im[8];
+    float re[G], im[G];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) re[j] = im[j] = 0.f;
-    const float4* trow = reinterpret_cast<const float4*>(p.t_kh + hg * 8);
-    const int pitch4 = p.hp8 >> 1;
-    for (int k = 0; k < K; ++k) {
-      const float2 y = bufA[k * Pb + pb];
-      const float4* t = trow + (size_t)k * pitch4;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 cs = __ldg(t + q);
-        re[2 * q] = fmaf(y.x, cs.x, fmaf(-y.y, cs.y, re[2 * q]));
-        im[2 * q] = fmaf(y.x, cs.y, fmaf(y.y, cs.x, im[2 * q]));
-        re[2 * q + 1] = fmaf(y.x, cs.z, fmaf(-y.y, cs.w, re[2 * q + 1]));
-        im[2 * q + 1] = fmaf(y.x, cs.w, fmaf(y.y, cs.z, im[2 * q + 1]));
-      }
-    }
+    for (int j = 0; j < G; ++j) re[j] = im[j] = 0.f;
+    const float2* trow = s_kh + hg * G;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) cacc_rows<G>(bufA[k * Pb + pb], trow + (size_t)k * p.hp8, re, im, false);
     const int bc = pb / TL, lt = pb - bc * TL, l = l0 + lt;
     if (l >= m2) continue;
     const float sc = __ldg(p.post + l);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int h = hg * 8 + j;
+    for (int j = 0; j < G; ++j) {
+      const int h = hg * G + j;
       if (h < hp) p.out[((size_t)(b * p.cb + bc) * hp + h) * m2 + l] = make_float2(re[j] * sc, im[j] * sc);
     }
   }
+}
+
+template <bool BWD, int G>
+static void launch_core2d_t(const CoreParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(core2d_kernel<BWD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  core2d_kernel<BWD, G><<<grid, 256, smem, st>>>(p);
 }
 
 void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_out, const float2* w1,
@@ -251,26 +439,32 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
   p.cb = bwd ? ci_layer : co_layer;
   p.co_layer = co_layer;
   p.hp = pl->hp; p.hp8 = pl->hp8; p.m1 = pl->m1; p.m2 = pl->m2; p.K = pl->K; p.Kp = pl->Kp;
-  // TL mode columns per block: the most that still gives ~2 waves of blocks and fits shared memory
+  // TL mode columns per block: the widest column tile that still leaves >= 2 blocks per SM and fits
+  // shared memory (wide tiles read the W-transformed image with full 32-byte sectors)
   auto smem_of = [&](int t) {
-    const size_t nA = (size_t)((pl->hp * p.ca > pl->K * p.cb) ? pl->hp * p.ca : pl->K * p.cb) * t;
-    return (nA + (size_t)pl->K * p.ca * t) * sizeof(float2);
+    size_t nA = (size_t)((pl->hp * p.ca > pl->K * p.cb) ? pl->hp * p.ca : pl->K * p.cb) * t;
+    nA = (nA + 1) & ~(size_t)1;
+    const size_t nX = (size_t)pl->K * p.ca * t;
+    return (nA + nX + (nX & 1) + (size_t)pl->hp * pl->Kp + (size_t)pl->K * pl->hp8) * sizeof(float2);
   };
   int tl = 1;
-  for (int cand = 8; cand > 1; cand >>= 1) {
-    if (cand > pl->m2 || smem_of(cand) > 200 * 1024) continue;
-    if ((long)images * ceil_div(pl->m2, cand) >= 2 * 148) { tl = cand; break; }
+  for (int parts = 1; parts <= pl->m2; ++parts) {
+    const int cand = ceil_div(pl->m2, parts);
+    if (smem_of(cand) > 100 * 1024) continue;
+    if ((long)images * ceil_div(pl->m2, cand) >= 2 * 148 || cand == 1) { tl = cand; break; }
   }
   p.TL = tl;
   const size_t smem = smem_of(tl);
-  dim3 grid(ceil_div(pl->m2, tl), images), block(256);
-  if (bwd) {
-    cudaFuncSetAttribute(core2d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    core2d_kernel<true><<<grid, block, smem, st>>>(p);
-  } else {
-    cudaFuncSetAttribute(core2d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    core2d_kernel<false><<<grid, block, smem, st>>>(p);
-  }
+  dim3 grid(ceil_div(pl->m2, tl), images);
+  // rows per item: the largest G that still gives every thread of the block an item in both transforms
+  const int Pmin = (p.ca < p.cb ? p.ca : p.cb) * tl;
+  int g = 1;
+  for (int cand = 8; cand > 1; cand >>= 1)
+    if (Pmin * ceil_div(pl->K, cand) >= 256) { g = cand; break; }
+#define BDN_CORE(B, GG) launch_core2d_t<B, GG>(p, grid, smem, st)
+  if (bwd) { if (g == 8) BDN_CORE(true, 8); else if (g == 4) BDN_CORE(true, 4); else if (g == 2) BDN_CORE(true, 2); else BDN_CORE(true, 1); }
+  else     { if (g == 8) BDN_CORE(false, 8); else if (g == 4) BDN_CORE(false, 4); else if (g == 2) BDN_CORE(false, 2); else BDN_CORE(false, 1); }
+#undef BDN_CORE
 }
 
 // ===========================================================================
@@ -385,7 +579,7 @@ struct WinvParams {
   int lines, c, hp, wp, wp4, m2, act_in, HT, WCH;
 };
 
-template <int MODE>
+template <int MODE, int CG>   // CG = channels accumulated per work item (4, 2 or 1)
 __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
   extern __shared__ __align__(16) float smem[];
   const int c = p.c, cpad = (c + 3) & ~3, HT = p.HT, WCH = p.WCH, m2 = p.m2, hp = p.hp, wp = p.wp;
@@ -398,41 +592,86 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
   float2* zs = reinterpret_cast<float2*>(tsn + m2 * WCH);  // [cpad][HT][m2]
   float* as = reinterpret_cast<float*>(zs + cpad * HT * m2);  // [c][HT][WCH]       (MODE >= 1)
   float* pws = as + (MODE >= 1 ? c * npx : 0);             // [cpad][c] + bias[cpad]
-  float* zact = pws + (MODE >= 1 ? cpad * c + cpad : 0);   // [c][HT][WCH]          (MODE == 2)
+  float* zact = pws + (MODE >= 1 ? cpad * c + cpad : 0);   // [c][HT][WCH] act(z_in)   (MODE == 2)
+  float* gsm = zact + (MODE == 2 ? c * npx : 0);           // [c][HT][WCH] act'(z_in)  (MODE == 2)
 
-  for (int idx = tid; idx < m2 * WCH; idx += nt) {
-    const int l = idx / WCH, w = idx - l * WCH;
-    const bool ok = wc0 + w < p.wp4;
-    tc[idx] = ok ? __ldg(p.t_cos + (size_t)l * p.wp4 + wc0 + w) : 0.f;
-    tsn[idx] = ok ? __ldg(p.t_sin + (size_t)l * p.wp4 + wc0 + w) : 0.f;
+  // Staging.  Every index split below is a multiply by a precomputed reciprocal (exact for these
+  // ranges): ncu showed the integer divisions of the element-wise staging loops to be 45 % of this
+  // kernel's instructions.  Activations move as float4.
+  const int nwq = WCH >> 2;
+  const float inv_nwq = 1.0f / (float)nwq, inv_ht = 1.0f / (float)HT, inv_hp = 1.0f / (float)hp,
+              inv_m2 = 1.0f / (float)m2;
+  auto fdiv = [](int n, float inv) { return __float2int_rz(((float)n + 0.5f) * inv); };
+  for (int idx = tid; idx < m2 * nwq; idx += nt) {
+    const int l = fdiv(idx, inv_nwq), q = idx - l * nwq;
+    const int w = wc0 + 4 * q;     // wp4 is a multiple of 4: a float4 is inside the table row or fully outside
+    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), sv = cv;
+    if (w < p.wp4) {
+      cv = __ldg(reinterpret_cast<const float4*>(p.t_cos + (size_t)l * p.wp4 + w));
+      sv = __ldg(reinterpret_cast<const float4*>(p.t_sin + (size_t)l * p.wp4 + w));
+    }
+    reinterpret_cast<float4*>(tc)[idx] = cv;
+    reinterpret_cast<float4*>(tsn)[idx] = sv;
   }
   for (int idx = tid; idx < cpad * HT * m2; idx += nt) {
-    const int l = idx % m2, hh = (idx / m2) % HT, ch = idx / (m2 * HT);
+    const int row = fdiv(idx, inv_m2), l = idx - row * m2;
+    const int ch = fdiv(row, inv_ht), hh = row - ch * HT;
     const int line = line0 + hh;
     float2 v = make_float2(0.f, 0.f);
     if (ch < c && line < p.lines) {
-      const int b = line / hp, h = line - b * hp;
+      const int b = fdiv(line, inv_hp), h = line - b * hp;
       v = __ldg(p.z + ((size_t)(b * c + ch) * hp + h) * m2 + l);
     }
     zs[idx] = v;
   }
   if (MODE >= 1) {
-    for (int idx = tid; idx < c * npx; idx += nt) {
-      const int w = idx % WCH, hh = (idx / WCH) % HT, ch = idx / npx;
-      const int line = line0 + hh, wg = wc0 + w;
-      float v = 0.f, za = 0.f;
+    const bool vec = (wp & 3) == 0;
+    for (int idx = tid; idx < c * HT * nwq; idx += nt) {
+      const int row = fdiv(idx, inv_nwq), q = idx - row * nwq;
+      const int ch = fdiv(row, inv_ht), hh = row - ch * HT;
+      const int line = line0 + hh, wg = wc0 + 4 * q;
+      float v[4] = {0.f, 0.f, 0.f, 0.f}, za[4] = {0.f, 0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f};
       if (line < p.lines && wg < wp) {
-        const int b = line / hp, h = line - b * hp;
+        const int b = fdiv(line, inv_hp), h = line - b * hp;
         const size_t off = ((size_t)(b * c + ch) * hp + h) * wp + wg;
-        v = __ldg(p.a + off);
-        if (MODE == 1 && p.act_in) v = gelu_exact(v);
+        if (vec) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.a + off));
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+          if (MODE == 2) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(p.zin + off));
+            za[0] = u.x; za[1] = u.y; za[2] = u.z; za[3] = u.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (wg + j < wp) {
+              v[j] = __ldg(p.a + off + j);
+              if (MODE == 2) za[j] = __ldg(p.zin + off + j);
+            }
+        }
+        if (MODE == 1 && p.act_in) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = gelu_fast(v[j]);
+        }
         if (MODE == 2) {
-          za = __ldg(p.zin + off);
-          if (p.act_in) za = gelu_exact(za);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (p.act_in) {
+              float cdf, pdf;
+              gelu_cdf_pdf(za[j], cdf, pdf);
+              gr[j] = fmaf(za[j], pdf, cdf);
+              za[j] *= cdf;
+            } else {
+              gr[j] = 1.0f;
+            }
+          }
         }
       }
-      as[idx] = v;
-      if (MODE == 2) zact[idx] = za;
+      reinterpret_cast<float4*>(as)[idx] = make_float4(v[0], v[1], v[2], v[3]);
+      if (MODE == 2) {
+        reinterpret_cast<float4*>(zact)[idx] = make_float4(za[0], za[1], za[2], za[3]);
+        reinterpret_cast<float4*>(gsm)[idx] = make_float4(gr[0], gr[1], gr[2], gr[3]);
+      }
     }
     for (int idx = tid; idx < cpad * c; idx += nt) {
       const int r = idx / c, q = idx - r * c;   // r: channel this pass produces, q: channel it consumes
@@ -445,21 +684,23 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
   }
   __syncthreads();
 
-  const int nwg = WCH >> 2, nog = cpad >> 2;
+  const int nwg = WCH >> 2, nog = cpad / CG;
   for (int idx = tid; idx < nog * HT * nwg; idx += nt) {
-    const int wg = idx % nwg, hh = (idx / nwg) % HT, og = idx / (nwg * HT);
-    float acc[4][4];
+    const int irow = fdiv(idx, inv_nwq), wg = idx - irow * nwg;
+    const int og = fdiv(irow, inv_ht), hh = irow - og * HT;
+    float acc[CG][4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < CG; ++r)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
-    const float2* zrow = zs + ((og * 4) * HT + hh) * m2;
+    const float2* zrow = zs + ((og * CG) * HT + hh) * m2;
     const int zpitch = HT * m2;
+#pragma unroll 2
     for (int l = 0; l < m2; ++l) {
       const float4 cs = *reinterpret_cast<const float4*>(tc + l * WCH + wg * 4);
       const float4 sn = *reinterpret_cast<const float4*>(tsn + l * WCH + wg * 4);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < CG; ++r) {
         const float2 zv = zrow[r * zpitch + l];
         acc[r][0] = fmaf(zv.x, cs.x, fmaf(-zv.y, sn.x, acc[r][0]));
         acc[r][1] = fmaf(zv.x, cs.y, fmaf(-zv.y, sn.y, acc[r][1]));
@@ -471,8 +712,8 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
       for (int q = 0; q < c; ++q) {
         const float4 av = *reinterpret_cast<const float4*>(as + (q * HT + hh) * WCH + wg * 4);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float wv = pws[(og * 4 + r) * c + q];
+        for (int r = 0; r < CG; ++r) {
+          const float wv = pws[(og * CG + r) * c + q];
           acc[r][0] = fmaf(wv, av.x, acc[r][0]);
           acc[r][1] = fmaf(wv, av.y, acc[r][1]);
           acc[r][2] = fmaf(wv, av.z, acc[r][2]);
@@ -482,11 +723,11 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
     }
     const int line = line0 + hh;
     if (line >= p.lines) continue;
-    const int b = line / hp, h = line - b * hp;
+    const int b = fdiv(line, inv_hp), h = line - b * hp;
     const int w0 = wc0 + wg * 4;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int ch = og * 4 + r;
+    for (int r = 0; r < CG; ++r) {
+      const int ch = og * CG + r;
       if (ch >= c) continue;
       const size_t off = ((size_t)(b * c + ch) * hp + h) * wp + w0;
       float v[4] = {acc[r][0], acc[r][1], acc[r][2], acc[r][3]};
@@ -495,10 +736,9 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] += bias;
       }
-      if (MODE == 2 && p.act_in) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (w0 + j < wp) v[j] *= gelu_grad(__ldg(p.zin + off + j));
+      if (MODE == 2) {
+        const float4 gq = *reinterpret_cast<const float4*>(gsm + (ch * HT + hh) * WCH + wg * 4);
+        v[0] *= gq.x; v[1] *= gq.y; v[2] *= gq.z; v[3] *= gq.w;
       }
       if ((wp & 3) == 0 && w0 + 3 < wp) {
         *reinterpret_cast<float4*>(p.y + off) = make_float4(v[0], v[1], v[2], v[3]);
@@ -511,23 +751,45 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
   }
 
   if (MODE == 2) {
-    // 1x1-conv weight / bias gradients over this tile: pair (o, i) per warp, lanes over pixels
+    // 1x1-conv weight / bias gradients over this tile: pair (o, i) per warp, lanes over pixels; the
+    // block's partials are collected in shared memory and flushed with 128-bit atomics (4x fewer L2
+    // atomic operations on these few, heavily contended addresses).
+    const int npair = c * c + c, npair4 = (npair + 3) & ~3;
+    float* part = gsm + c * npx;     // [c*c + c], padded to a multiple of 4
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    for (int pair = warp; pair < c * c + c; pair += nwarps) {
+    for (int pair = warp; pair < npair4; pair += nwarps) {
       float s = 0.f;
       if (pair < c * c) {
         const int o = pair / c, i = pair - o * c;
         const float* go = as + o * npx;
         const float* ai = zact + i * npx;
         for (int px = lane; px < npx; px += 32) s = fmaf(go[px], ai[px], s);
-      } else {
+      } else if (pair < npair) {
         const float* go = as + (pair - c * c) * npx;
         for (int px = lane; px < npx; px += 32) s += go[px];
       }
       s = warp_sum(s);
-      if (lane == 0) atomicAdd(pair < c * c ? p.g_pw_w + pair : p.g_pw_b + (pair - c * c), s);
+      if (lane == 0) part[pair] = s;
+    }
+    __syncthreads();
+    const bool vec_ok = ((c * c) & 3) == 0 && (c & 3) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(p.g_pw_w) | reinterpret_cast<uintptr_t>(p.g_pw_b)) & 15) == 0;
+    if (vec_ok) {
+      for (int q = tid; q < npair >> 2; q += nt) {
+        const float4 v = reinterpret_cast<const float4*>(part)[q];
+        float* dst = 4 * q < c * c ? p.g_pw_w + 4 * q : p.g_pw_b + (4 * q - c * c);
+        atomicAdd(reinterpret_cast<float4*>(dst), v);
+      }
+    } else {
+      for (int q = tid; q < npair; q += nt) atomicAdd(q < c * c ? p.g_pw_w + q : p.g_pw_b + (q - c * c), part[q]);
     }
   }
+}
+
+template <int MODE, int CG>
+static void launch_winv_t(const WinvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(winv_kernel<MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  winv_kernel<MODE, CG><<<grid, 256, smem, st>>>(p);
 }
 
 void launch_winv(const Plan* pl, int mode, const WinvArgs& a, cudaStream_t st) {
@@ -539,29 +801,44 @@ void launch_winv(const Plan* pl, int mode, const WinvArgs& a, cudaStream_t st) {
   p.lines = a.images * pl->hp; p.c = a.c; p.hp = pl->hp; p.wp = pl->wp; p.wp4 = pl->wp4; p.m2 = pl->m2;
   p.act_in = a.act_in;
   const int c = a.c, cpad = (c + 3) & ~3;
-  int ht = 32 / cpad;
-  if (ht < 1) ht = 1;
-  if (ht > 8) ht = 8;
-  while (ht > 1 && ceil_div(p.lines, ht) < 2 * 148) ht >>= 1;
-  int nch = 1;
-  auto smem_of = [&](int wch) {
+  auto smem_of = [&](int ht, int wch) {
     size_t f = 2 * (size_t)pl->m2 * wch + 2 * (size_t)cpad * ht * pl->m2;
     if (mode >= 1) f += (size_t)c * ht * wch + cpad * c + cpad;
-    if (mode == 2) f += (size_t)c * ht * wch;
+    if (mode == 2) f += 2 * (size_t)c * ht * wch + ((c * c + c + 3) & ~3);
     return f * sizeof(float);
   };
-  int wch = pl->wp4;
-  while (smem_of(wch) > 96 * 1024 && wch > 4) {
+  // (lines per block, channels per item): a work item is CG channels x 4 pixels of one line.  Pick the
+  // pair that keeps the 256 threads busiest, counting the FMA density of the inner loop
+  // (8*CG FMAs per 2 + CG shared loads), among tilings that leave >= 2 blocks per SM when possible.
+  int wch = pl->wp4, nch = 1;
+  while (smem_of(1, wch) > 64 * 1024 && wch > 4) {
     ++nch;
     wch = (ceil_div(pl->wp4, nch) + 3) & ~3;
   }
-  p.HT = ht; p.WCH = wch;
-  const size_t smem = smem_of(wch);
-  dim3 grid(ceil_div(p.lines, ht), ceil_div(pl->wp4, wch)), block(256);
-#define BDN_WINV(M)                                                                               \
-  {                                                                                               \
-    cudaFuncSetAttribute(winv_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  \
-    winv_kernel<M><<<grid, block, smem, st>>>(p);                                                 \
+  const int nwg = wch >> 2;
+  int best_ht = 1, best_cg = 1;
+  double best = -1.0;
+  const long want_blocks = 2 * 148;
+  for (int pass = 0; pass < 2 && best < 0.0; ++pass)
+    for (int cg = 4; cg >= 1; cg >>= 1)
+      for (int ht = 1; ht <= 16; ++ht) {
+        if (smem_of(ht, wch) > 64 * 1024) break;
+        const long blocks = (long)ceil_div(p.lines, ht) * nch;
+        if (pass == 0 && blocks < want_blocks) break;
+        const int items = (cpad / cg) * ht * nwg;
+        const double util = (double)items / (ceil_div(items, 256) * 256.0);
+        const double dens = 8.0 * cg / (8.0 * cg + 2.0 + cg);
+        const double score = util * dens * (pass == 1 && ht > 1 ? 0.0 : 1.0);
+        if (score > best) { best = score; best_ht = ht; best_cg = cg; }
+      }
+  p.HT = best_ht; p.WCH = wch;
+  const size_t smem = smem_of(best_ht, wch);
+  dim3 grid(ceil_div(p.lines, best_ht), ceil_div(pl->wp4, wch));
+#define BDN_WINV(M)                                                        \
+  {                                                                        \
+    if (best_cg == 4) launch_winv_t<M, 4>(p, grid, smem, st);              \
+    else if (best_cg == 2) launch_winv_t<M, 2>(p, grid, smem, st);         \
+    else launch_winv_t<M, 1>(p, grid, smem, st);                           \
   }
   if (mode == WINV_PLAIN) BDN_WINV(0) else if (mode == WINV_LAYER_FWD) BDN_WINV(1) else BDN_WINV(2)
 #undef BDN_WINV

@@ -21,6 +21,8 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
+import numpy as np
+
 from . import ops
 from .surface.fno import _FnoBase
 
@@ -51,6 +53,11 @@ class FlatTrainer:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.loss_fn = loss_fn or nn.functional.mse_loss
         self.step_count = 0
+        # CUDA-graph replay of the device work of a step (see step()): one graph per bag size
+        self.use_graphs = False
+        self._graphs = {}
+        self._graph_pool = None
+        self.replayed_launches = 0
 
         named = live_parameters(model)
         if not named:
@@ -129,6 +136,8 @@ class FlatTrainer:
     # -- the step --------------------------------------------------------------------------
     def step(self, x: torch.Tensor, grid: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """zero_grad -> forward -> loss -> backward -> all-reduce -> Adam.  Returns the (device) loss."""
+        if self.use_graphs and (x.is_cuda or x.is_pinned()) and self.flat_param.is_cuda and hasattr(self.model, "FNO_input"):
+            return self._graph_step(x, grid, target)
         self.zero_grad()
         pred = self.model(x, grid)
         loss = self.loss_fn(pred, target)
@@ -136,6 +145,89 @@ class FlatTrainer:
         self.reduce_gradients()
         self.optimizer_step()
         return loss.detach()
+
+    # -- CUDA graphs -----------------------------------------------------------------------
+    # The reference step is a few hundred tiny launches with a fresh bag size L ~ U[50, L0) every step
+    # (2d_FPE/NIOModules.py:548-551): eager, the host cannot feed a B200 fast enough.  The bag is still
+    # drawn on the host from the NumPy stream in the reference's order; only its indices are copied into
+    # a static buffer, and zero_grad + forward + loss + backward are replayed from the graph captured for
+    # that bag size (all graphs share one memory pool).  All-reduce and Adam stay outside the graph.
+    def enable_graphs(self, enabled: bool = True):
+        self.use_graphs = bool(enabled)
+        return self
+
+    def _draw(self, n_snapshots: int):
+        from .surface.nio import draw_bag
+        return draw_bag(n_snapshots, self.model.training)
+
+    def _graph_entry(self, x, grid, target, n_keep):
+        key = (n_keep, tuple(x.shape), tuple(target.shape), tuple(grid.shape), bool(self.model.training))
+        ent = self._graphs.get(key)
+        if ent is not None:
+            return ent
+        dev = self.device
+        ent = {
+            "x": torch.empty(x.shape, dtype=x.dtype, device=dev),
+            "target": torch.empty(target.shape, dtype=target.dtype, device=dev),
+            "grid": grid.detach().to(dev).clone(),
+            "idx": torch.zeros(max(n_keep, 1), dtype=torch.int32, device=dev) if n_keep else None,
+        }
+        ent["x"].copy_(x)
+        ent["target"].copy_(target)
+        torch.cuda.synchronize(dev)
+
+        def body():
+            self.flat_grad.zero_()
+            pred = self.model(ent["x"], ent["grid"], idx=ent["idx"]) if ent["idx"] is not None else \
+                self.model(ent["x"], ent["grid"])
+            loss = self.loss_fn(pred, ent["target"])
+            loss.backward()
+            return loss.detach()
+
+        # warm-up on a side stream (plans, lazy module loads, autograd buffers), then capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            if ent["idx"] is None:
+                state = np.random.get_state()
+            body()
+            if ent["idx"] is None:
+                np.random.set_state(state)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        graph = torch.cuda.CUDAGraph()
+        launches0 = ops.kernel_launches()
+        with torch.cuda.graph(graph, pool=self._graph_pool):
+            ent["loss"] = body()
+        ent["launches"] = ops.kernel_launches() - launches0      # kernels of this library inside the graph
+        ent["graph"] = graph
+        self._graphs[key] = ent
+        return ent
+
+    def _graph_step(self, x, grid, target):
+        idx = self._draw(x.shape[1])
+        n_keep = 0 if idx is None else int(len(idx))
+        ent = self._graph_entry(x, grid, target, n_keep)
+        ent["x"].copy_(x, non_blocking=True)
+        ent["target"].copy_(target, non_blocking=True)
+        if n_keep:
+            # pageable source: the runtime stages it before returning, so the host array may be reused
+            ent["idx"].copy_(torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int32)))
+        ent["graph"].replay()
+        self.replayed_launches += ent["launches"]
+        self.reduce_gradients()
+        self.optimizer_step()
+        return ent["loss"]
+
+    def prepare_graphs(self, x, grid, target, bag_sizes=None):
+        """Capture the graphs of every bag size a training run can draw (L in [50, L0)) up front."""
+        n0 = x.shape[1]
+        sizes = list(bag_sizes) if bag_sizes is not None else (list(range(50, n0)) if self.model.training else [0])
+        for n in sizes:
+            self._graph_entry(x, grid, target, n)
+        return len(self._graphs)
 
 
 def shard_batch(n_samples: int, rank: int, world: int):

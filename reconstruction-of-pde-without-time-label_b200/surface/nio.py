@@ -36,19 +36,56 @@ def _idx_tensor(idx, device):
     return torch.as_tensor(np.ascontiguousarray(idx), dtype=torch.int32).to(device, non_blocking=True)
 
 
+_SIDE = {}
+
+
+def _side_streams(device, n):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    pool = _SIDE.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
 class _BagModel(nn.Module):
     head_names: tuple = ()
 
     def _heads(self, lifted):
-        outs = [getattr(self, name)(lifted) for name in self.head_names]
-        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
+        """The output FNO heads read the same lifted bag mean and are independent of each other; with only
+        B images each they cannot fill the GPU alone, so every head after the first runs on its own side
+        stream (fork / join by events -- capturable in a CUDA graph; autograd replays each head's backward
+        on the stream its forward ran on)."""
+        names = self.head_names
+        if len(names) == 1 or not lifted.is_cuda:
+            outs = [getattr(self, name)(lifted) for name in names]
+            return outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
+        main = torch.cuda.current_stream(lifted.device)
+        side = _side_streams(lifted.device, len(names) - 1)
+        outs = [None] * len(names)
+        for k, name in enumerate(names[1:], start=1):
+            st = side[k - 1]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                outs[k] = getattr(self, name)(lifted)
+        outs[0] = getattr(self, names[0])(lifted)
+        capturing = torch.cuda.is_current_stream_capturing()
+        for k in range(1, len(names)):
+            main.wait_stream(side[k - 1])
+            if not capturing:          # (a graph's private pool keeps its tensors alive by itself)
+                lifted.record_stream(side[k - 1])
+                outs[k].record_stream(main)
+        return torch.cat(outs, dim=-1)
 
 
 class _NioFnoMixin(_BagModel):
     """FNO_input on every snapshot -> mean over the bag folded into the detached fc0 -> FNO heads."""
 
-    def forward(self, x, grid):
-        idx = _idx_tensor(draw_bag(x.shape[1], self.training), x.device)
+    def forward(self, x, grid, idx=None):
+        """``idx`` (optional int32 device tensor): the kept snapshots, when the caller has already drawn
+        the bag from the NumPy stream itself (parallel.FlatTrainer does, so that the device work of a
+        step can be replayed from a CUDA graph); otherwise drawn here exactly like the reference."""
+        if idx is None:
+            idx = _idx_tensor(draw_bag(x.shape[1], self.training), x.device)
         lifted = self.FNO_input.encode_bags(x, grid, idx=idx, pool=(self.fc0.weight.data, self.fc0.bias.data))
         return self._heads(lifted)
 
