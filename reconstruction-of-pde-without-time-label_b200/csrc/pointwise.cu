@@ -80,71 +80,113 @@ void launch_lift(const LiftArgs& a, float* z0, cudaStream_t st) {
 }
 
 // lift backward: g_w0[c][i] += sum gz0[c] * in_i, g_b0[c] += sum gz0[c], gx_cl[.., i] = sum_c W0[c][i] gz0[c]
-// A block stages a tile of TP pixels (gz0 for all channels, the inputs) and reduces the outer product.
+// A block stages a tile of TP pixels (gz0 for all channels, the inputs; every thread loads), computes
+// gx from shared memory, and reduces the outer product with 128-bit row-strided shared loads
+// (pitch TP + 4: conflict-free).  TP = 64 when there are few pixels (the heads), 256 otherwise.
+template <int TP>
 __global__ void __launch_bounds__(256) lift_bwd_kernel(const LiftParams p, const float* __restrict__ gz0,
                                                        float* g_w0, float* g_b0, float* __restrict__ gx_cl,
                                                        int tiles_per_block) {
-  constexpr int TP = 256;
-  extern __shared__ float smem[];
+  constexpr int PT = TP + 4;
+  extern __shared__ __align__(16) float smem[];
   const int C = p.width, CI = p.c_in;
-  float* gs = smem;                  // [C][TP]
-  float* xs = gs + C * TP;           // [CI][TP]
-  float* ws = xs + CI * TP;          // [C][CI]
-  float* acc = ws + C * CI;          // [C*CI + C]
+  float* gs = smem;                  // [C][PT]
+  float* xs = gs + C * PT;           // [CI][PT]
+  float* ws = xs + CI * PT;          // [C][CI]
+  float* acc = ws + ((C * CI + 3) & ~3);   // [C*CI + C] (+ pad)
+  long* s_goff = reinterpret_cast<long*>(acc + ((C * CI + C + 3) & ~3) + 4);   // [TP] offset of the pixel in a gz plane, -1 = dead
   const int npair = C * CI + C;
-  for (int i = threadIdx.x; i < C * CI; i += blockDim.x) ws[i] = __ldg(p.w0 + i);
-  for (int i = threadIdx.x; i < npair; i += blockDim.x) acc[i] = 0.f;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < C * CI; i += nt) ws[i] = __ldg(p.w0 + i);
+  for (int i = tid; i < ((npair + 3) & ~3); i += nt) acc[i] = 0.f;
   const int plane = p.hp * p.wp, hw = p.h * p.w;
   const long total = (long)p.images * hw;
-  const int sub = blockDim.x / npair > 0 ? blockDim.x / npair : 1;   // pixel sub-slices per pair
+  const int sub = nt / npair > 0 ? nt / npair : 1;   // pixel sub-slices per pair
+  const float inv_tp = 1.0f / (float)TP, inv_ci = 1.0f / (float)CI;
+  auto fdiv = [](int n, float inv) { return __float2int_rz(((float)n + 0.5f) * inv); };
   for (int it = 0; it < tiles_per_block; ++it) {
     const long t0 = ((long)blockIdx.x * tiles_per_block + it) * TP;
     if (t0 >= total) break;
     __syncthreads();
-    {
-      const int tp = threadIdx.x;      // TP == blockDim.x
-      const long t = t0 + tp;
-      float in[LIFT_MAX_CIN];
+    if (tid < TP) {
+      const long t = t0 + tid;
+      long off = -1;
       if (t < total) {
         const int img = t / hw, pix = t - (long)img * hw;
         const int hh = pix / p.w, ww = pix - hh * p.w;
-        lift_fetch(p, img, pix, in);
-        const float* g = gz0 + (size_t)img * C * plane + hh * p.wp + ww;
-        float gx[LIFT_MAX_CIN];
-        for (int i = 0; i < CI; ++i) gx[i] = 0.f;
-        for (int c = 0; c < C; ++c) {
-          const float gv = __ldg(g + (size_t)c * plane);
-          gs[c * TP + tp] = gv;
-          if (gx_cl != nullptr)
-            for (int i = 0; i < CI; ++i) gx[i] = fmaf(ws[c * CI + i], gv, gx[i]);
-        }
-        for (int i = 0; i < CI; ++i) xs[i * TP + tp] = in[i];
-        if (gx_cl != nullptr)
-          for (int i = 0; i < CI; ++i) gx_cl[(size_t)t * CI + i] = gx[i];
-      } else {
-        for (int c = 0; c < C; ++c) gs[c * TP + tp] = 0.f;
-        for (int i = 0; i < CI; ++i) xs[i * TP + tp] = 0.f;
+        off = (long)img * C * plane + hh * p.wp + ww;
       }
+      s_goff[tid] = off;
     }
     __syncthreads();
-    for (int item = threadIdx.x; item < npair * sub; item += blockDim.x) {
+    for (int idx = tid; idx < C * TP; idx += nt) {
+      const int c = fdiv(idx, inv_tp), tp = idx - c * TP;
+      const long off = s_goff[tp];
+      gs[c * PT + tp] = off >= 0 ? __ldg(gz0 + off + (size_t)c * plane) : 0.f;
+    }
+    for (int idx = tid; idx < CI * TP; idx += nt) {
+      const int tp = fdiv(idx, inv_ci), i = idx - tp * CI;
+      const long t = t0 + tp;
+      float v = 0.f;
+      if (t < total) {
+        if (p.x_cl != nullptr) {
+          v = __ldg(p.x_cl + (size_t)t * CI + i);
+        } else {
+          const int img = t / hw, pix = t - (long)img * hw;
+          if (i == 0) {
+            const int b = img / p.n_keep, l = img - b * p.n_keep;
+            const int snap = p.idx != nullptr ? __ldg(p.idx + l) : l;
+            v = __ldg(p.bags + ((size_t)b * p.bag_len + snap) * hw + pix);
+          } else {
+            v = __ldg(p.grid + (size_t)pix * p.grid_dim + (i - 1));
+          }
+        }
+      }
+      xs[i * PT + tp] = v;
+    }
+    __syncthreads();
+    if (gx_cl != nullptr) {
+      for (int idx = tid; idx < CI * TP; idx += nt) {
+        const int tp = fdiv(idx, inv_ci), i = idx - tp * CI;
+        const long t = t0 + tp;
+        if (t >= total) continue;
+        float gx = 0.f;
+        for (int c = 0; c < C; ++c) gx = fmaf(ws[c * CI + i], gs[c * PT + tp], gx);
+        gx_cl[(size_t)t * CI + i] = gx;
+      }
+    }
+    for (int item = tid; item < npair * sub; item += nt) {
       const int pair = item % npair, sl = item / npair;
-      const int lo = sl * TP / sub, hi = (sl + 1) * TP / sub;
+      const int lo = sl * (TP / 4) / sub, hi = (sl + 1) * (TP / 4) / sub;   // float4 chunks
       float s = 0.f;
       if (pair < C * CI) {
-        const float* g = gs + (pair / CI) * TP;
-        const float* x = xs + (pair % CI) * TP;
-        for (int q = lo; q < hi; ++q) s = fmaf(g[q], x[q], s);
+        const float4* g = reinterpret_cast<const float4*>(gs + (pair / CI) * PT);
+        const float4* x = reinterpret_cast<const float4*>(xs + (pair % CI) * PT);
+        for (int q = lo; q < hi; ++q) {
+          const float4 a4 = g[q], b4 = x[q];
+          s = fmaf(a4.x, b4.x, fmaf(a4.y, b4.y, fmaf(a4.z, b4.z, fmaf(a4.w, b4.w, s))));
+        }
       } else {
-        const float* g = gs + (pair - C * CI) * TP;
-        for (int q = lo; q < hi; ++q) s += g[q];
+        const float4* g = reinterpret_cast<const float4*>(gs + (pair - C * CI) * PT);
+        for (int q = lo; q < hi; ++q) {
+          const float4 a4 = g[q];
+          s += (a4.x + a4.y) + (a4.z + a4.w);
+        }
       }
-      atomicAdd(acc + pair, s);
+      if (sub > 1) atomicAdd(acc + pair, s); else acc[pair] += s;
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < npair; i += blockDim.x)
-    atomicAdd(i < C * CI ? g_w0 + i : g_b0 + (i - C * CI), acc[i]);
+  const bool vec_ok = ((C * CI) & 3) == 0 && (C & 3) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(g_w0) | reinterpret_cast<uintptr_t>(g_b0)) & 15) == 0;
+  if (vec_ok) {
+    for (int q = tid; q < npair >> 2; q += nt) {
+      float* dst = 4 * q < C * CI ? g_w0 + 4 * q : g_b0 + (4 * q - C * CI);
+      atomicAdd(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(acc)[q]);
+    }
+  } else {
+    for (int i = tid; i < npair; i += nt) atomicAdd(i < C * CI ? g_w0 + i : g_b0 + (i - C * CI), acc[i]);
+  }
 }
 
 void launch_lift_bwd(const LiftArgs& a, const float* gz0, float* g_w0, float* g_b0, float* gx_cl,
@@ -152,13 +194,21 @@ void launch_lift_bwd(const LiftArgs& a, const float* gz0, float* g_w0, float* g_
   LaunchScope scope("lift_bwd", st, a.width);
   const LiftParams p = make_lift_params(a);
   const long total = (long)a.images * a.h * a.w;
-  const int tiles = (int)((total + 255) / 256);
+  const bool few = total < 148L * 256 * 2;
+  const int tp = few ? 64 : 256;
+  const int tiles = (int)((total + tp - 1) / tp);
   int tpb = 1;
-  while (ceil_div(tiles, tpb) > 8 * 148) ++tpb;
+  while (ceil_div(tiles, tpb) > 4 * 148) ++tpb;
   const int grid = ceil_div(tiles, tpb);
-  const size_t smem = (size_t)((a.width + a.c_in) * 256 + 2 * a.width * a.c_in + a.width) * sizeof(float);
-  cudaFuncSetAttribute(lift_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  lift_bwd_kernel<<<grid, 256, smem, st>>>(p, gz0, g_w0, g_b0, gx_cl, tpb);
+  const size_t smem = (size_t)((a.width + a.c_in) * (tp + 4) + ((a.width * a.c_in + 3) & ~3) +
+                               ((a.width * a.c_in + a.width + 3) & ~3) + 4) * sizeof(float) + (size_t)tp * sizeof(long) + 16;
+  if (few) {
+    cudaFuncSetAttribute(lift_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    lift_bwd_kernel<64><<<grid, 256, smem, st>>>(p, gz0, g_w0, g_b0, gx_cl, tpb);
+  } else {
+    cudaFuncSetAttribute(lift_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    lift_bwd_kernel<256><<<grid, 256, smem, st>>>(p, gz0, g_w0, g_b0, gx_cl, tpb);
+  }
 }
 
 // ===========================================================================
@@ -427,12 +477,30 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_bwd_kernel(const ProjArg
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < hidden * a.width; i += blockDim.x) {
-    const int j = i / a.width, c = i - j * a.width;
-    atomicAdd(g_w1 + i, aw1[j * CP + c]);
+  // flush: 128-bit atomics where the layout allows (4x fewer L2 atomic operations on contended lines)
+  const bool h4 = (hidden & 3) == 0;       // keeps every shared accumulator array 16-byte aligned
+  auto vec_ok = [h4](const void* ptr, int n) { return h4 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (n & 3) == 0; };
+  if (a.width == CP && vec_ok(g_w1, hidden * CP)) {
+    for (int i = threadIdx.x; i < (hidden * CP) >> 2; i += blockDim.x)
+      atomicAdd(reinterpret_cast<float4*>(g_w1) + i, reinterpret_cast<const float4*>(aw1)[i]);
+  } else {
+    for (int i = threadIdx.x; i < hidden * a.width; i += blockDim.x) {
+      const int j = i / a.width, c = i - j * a.width;
+      atomicAdd(g_w1 + i, aw1[j * CP + c]);
+    }
   }
-  for (int i = threadIdx.x; i < hidden; i += blockDim.x) atomicAdd(g_b1 + i, ab1[i]);
-  for (int i = threadIdx.x; i < nout * hidden; i += blockDim.x) atomicAdd(g_w2 + i, aw2[i]);
+  if (vec_ok(g_b1, hidden)) {
+    for (int i = threadIdx.x; i < hidden >> 2; i += blockDim.x)
+      atomicAdd(reinterpret_cast<float4*>(g_b1) + i, reinterpret_cast<const float4*>(ab1)[i]);
+  } else {
+    for (int i = threadIdx.x; i < hidden; i += blockDim.x) atomicAdd(g_b1 + i, ab1[i]);
+  }
+  if (vec_ok(g_w2, nout * hidden)) {
+    for (int i = threadIdx.x; i < (nout * hidden) >> 2; i += blockDim.x)
+      atomicAdd(reinterpret_cast<float4*>(g_w2) + i, reinterpret_cast<const float4*>(aw2)[i]);
+  } else {
+    for (int i = threadIdx.x; i < nout * hidden; i += blockDim.x) atomicAdd(g_w2 + i, aw2[i]);
+  }
   if (threadIdx.x < nout) atomicAdd(g_b2 + threadIdx.x, ab2[threadIdx.x]);
 }
 
@@ -441,7 +509,9 @@ static void launch_project_bwd_t(const ProjArgs& a, const float* g_out, int pool
                                  float* g_w1, float* g_b1, float* g_w2, float* g_b2, long total, cudaStream_t st) {
   constexpr int TILE = PROJ_THREADS / JS * PP;
   const long ntiles = (total + TILE - 1) / TILE;
-  const int grid = (int)(ntiles < 148L * 2 ? ntiles : 148L * 2);
+  const long cap = JS == 1 ? 148L * 2 : 148L * 4;
+  const long rounds = (ntiles + cap - 1) / cap;
+  const int grid = (int)((ntiles + rounds - 1) / rounds);      // balanced: every block runs `rounds` tiles
   const size_t smem = (size_t)(2 * (a.hidden * CP + a.hidden + a.c_out * a.hidden) + PROJ_MAX_OUT) * sizeof(float);
   cudaFuncSetAttribute(project_bwd_kernel<CP, NOUT, JS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   project_bwd_kernel<CP, NOUT, JS, PP><<<grid, PROJ_THREADS, smem, st>>>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1,

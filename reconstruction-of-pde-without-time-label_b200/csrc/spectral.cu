@@ -137,10 +137,6 @@ __global__ void __launch_bounds__(256) wfwd_pipe_kernel(const WfwdParams p) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int wp = p.wp, m2 = p.m2, m2p = p.m2p;
 
-  for (int i = tid; i < wp * m2p; i += nt) {
-    const int w = i / m2p, l = i - w * m2p;
-    ts[i] = l < m2 ? __ldg(p.t_wl + (size_t)w * m2 + l) : make_float2(0.f, 0.f);
-  }
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -156,15 +152,24 @@ __global__ void __launch_bounds__(256) wfwd_pipe_kernel(const WfwdParams p) {
     if (lane == 0) {
       fence_proxy_async();
       mbar_expect_tx(&bars[stage], (uint32_t)nrows * row_bytes);
+      // the tile is one contiguous span of HBM: a single bulk copy when no row padding is needed
+      if (p.pitch == wp) bulk_g2s(dst, p.x + (size_t)row0 * wp, (uint32_t)nrows * row_bytes, &bars[stage]);
     }
     __syncwarp();
-    for (int r = lane; r < nrows; r += 32)
-      bulk_g2s(dst + r * p.pitch, p.x + (size_t)(row0 + r) * wp, row_bytes, &bars[stage]);
+    if (p.pitch != wp)
+      for (int r = lane; r < nrows; r += 32)
+        bulk_g2s(dst + r * p.pitch, p.x + (size_t)(row0 + r) * wp, row_bytes, &bars[stage]);
   };
+  if (warp == 0 && (int)blockIdx.x < p.ntiles) issue(blockIdx.x, 0);   // in flight while the table loads
+
+  for (int i = tid; i < wp * m2p; i += nt) {
+    const int w = i / m2p, l = i - w * m2p;
+    ts[i] = l < m2 ? __ldg(p.t_wl + (size_t)w * m2 + l) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
 
   const int rg = warp % p.nrg, mg0 = warp / p.nrg, mgstep = (nt >> 5) / p.nrg;
   int it = 0;
-  if (warp == 0 && (int)blockIdx.x < p.ntiles) issue(blockIdx.x, 0);
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int stage = it & 1;
     const int next = tile + gridDim.x;
@@ -316,8 +321,8 @@ __device__ __forceinline__ void cacc_rows(const float2 x, const float2* __restri
   }
 }
 
-template <bool BWD, int G>
-__global__ void __launch_bounds__(256) core2d_kernel(const CoreParams p) {
+template <bool BWD, int G1, int G3>   // kept rows per phase-1 item, spatial rows per phase-3 item
+__global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
   extern __shared__ __align__(16) float smem[];
   const int TL = p.TL, Pa = p.ca * TL, Pb = p.cb * TL, K = p.K, hp = p.hp, m2 = p.m2;
   const int nA = (max(hp * Pa, K * Pb) + 1) & ~1;
@@ -329,14 +334,16 @@ __global__ void __launch_bounds__(256) core2d_kernel(const CoreParams p) {
   const int tid = threadIdx.x, nt = blockDim.x;
 
   // the two DFT tables live in shared memory for the block's lifetime (they are re-read by every
-  // item; from L1/L2 the inner loops were latency-bound: ncu long-scoreboard 20 cycles per issue)
-  {
-    const float4* g1 = reinterpret_cast<const float4*>(p.t_hk);
-    float4* d1 = reinterpret_cast<float4*>(s_hk);
-    for (int i = tid; i < (hp * p.Kp) >> 1; i += nt) d1[i] = __ldg(g1 + i);
-    const float4* g2 = reinterpret_cast<const float4*>(p.t_kh);
-    float4* d2 = reinterpret_cast<float4*>(s_kh);
-    for (int i = tid; i < (K * p.hp8) >> 1; i += nt) d2[i] = __ldg(g2 + i);
+  // item; from L1/L2 the inner loops were latency-bound: ncu long-scoreboard 20 cycles per issue).
+  // Both are contiguous in HBM: two bulk async copies, in flight while phase 0 stages the image.
+  uint64_t* tbar = reinterpret_cast<uint64_t*>(s_kh + K * p.hp8);
+  if (tid == 0) {
+    mbar_init(tbar, 1);
+    mbar_init_fence();
+    const uint32_t b1 = (uint32_t)(hp * p.Kp) * 8u, b2 = (uint32_t)(K * p.hp8) * 8u;
+    mbar_expect_tx(tbar, b1 + b2);
+    bulk_g2s(s_hk, p.t_hk, b1, tbar);
+    bulk_g2s(s_kh, p.t_kh, b2, tbar);
   }
   // phase 0: stage the image's TL columns, all channels: bufA[h][a*TL + lt]
   for (int idx = tid; idx < p.ca * hp * TL; idx += nt) {
@@ -345,9 +352,11 @@ __global__ void __launch_bounds__(256) core2d_kernel(const CoreParams p) {
     bufA[h * Pa + a * TL + lt] =
         l < m2 ? __ldg(p.in + ((size_t)(b * p.ca + a) * hp + h) * m2 + l) : make_float2(0.f, 0.f);
   }
-  __syncthreads();
+  __syncthreads();          // also publishes the mbarrier init to the waiting threads
+  mbar_wait(tbar, 0);
 
-  // phase 1: X[k][pa] = pre[l] * sum_h x[h][pa] * e^{-i phi_kh}, G kept rows per item
+  // phase 1: X[k][pa] = pre[l] * sum_h x[h][pa] * e^{-i phi_kh}, G1 kept rows per item
+  constexpr int G = G1;
   const int nkg = (K + G - 1) / G;
   for (int idx = tid; idx < Pa * nkg; idx += nt) {
     const int pa = idx % Pa, kg = idx / Pa;
@@ -400,31 +409,31 @@ __global__ void __launch_bounds__(256) core2d_kernel(const CoreParams p) {
   }
   __syncthreads();
 
-  // phase 3: Z[h][pb] = post[l] * sum_k y[k][pb] * e^{+i phi_kh}, G rows per item
-  const int nhg = (hp + G - 1) / G;
+  // phase 3: Z[h][pb] = post[l] * sum_k y[k][pb] * e^{+i phi_kh}, G3 rows per item
+  const int nhg = (hp + G3 - 1) / G3;
   for (int idx = tid; idx < Pb * nhg; idx += nt) {
     const int pb = idx % Pb, hg = idx / Pb;
-    float re[G], im[G];
+    float re[G3], im[G3];
 #pragma unroll
-    for (int j = 0; j < G; ++j) re[j] = im[j] = 0.f;
-    const float2* trow = s_kh + hg * G;
+    for (int j = 0; j < G3; ++j) re[j] = im[j] = 0.f;
+    const float2* trow = s_kh + hg * G3;
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) cacc_rows<G>(bufA[k * Pb + pb], trow + (size_t)k * p.hp8, re, im, false);
+    for (int k = 0; k < K; ++k) cacc_rows<G3>(bufA[k * Pb + pb], trow + (size_t)k * p.hp8, re, im, false);
     const int bc = pb / TL, lt = pb - bc * TL, l = l0 + lt;
     if (l >= m2) continue;
     const float sc = __ldg(p.post + l);
 #pragma unroll
-    for (int j = 0; j < G; ++j) {
-      const int h = hg * G + j;
+    for (int j = 0; j < G3; ++j) {
+      const int h = hg * G3 + j;
       if (h < hp) p.out[((size_t)(b * p.cb + bc) * hp + h) * m2 + l] = make_float2(re[j] * sc, im[j] * sc);
     }
   }
 }
 
-template <bool BWD, int G>
-static void launch_core2d_t(const CoreParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  cudaFuncSetAttribute(core2d_kernel<BWD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  core2d_kernel<BWD, G><<<grid, 256, smem, st>>>(p);
+template <bool BWD, int G1, int G3>
+static void launch_core2d_t(const CoreParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(core2d_kernel<BWD, G1, G3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  core2d_kernel<BWD, G1, G3><<<grid, threads, smem, st>>>(p);
 }
 
 void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_out, const float2* w1,
@@ -445,7 +454,7 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
     size_t nA = (size_t)((pl->hp * p.ca > pl->K * p.cb) ? pl->hp * p.ca : pl->K * p.cb) * t;
     nA = (nA + 1) & ~(size_t)1;
     const size_t nX = (size_t)pl->K * p.ca * t;
-    return (nA + nX + (nX & 1) + (size_t)pl->hp * pl->Kp + (size_t)pl->K * pl->hp8) * sizeof(float2);
+    return (nA + nX + (nX & 1) + (size_t)pl->hp * pl->Kp + (size_t)pl->K * pl->hp8) * sizeof(float2) + 16;
   };
   int tl = 1;
   for (int parts = 1; parts <= pl->m2; ++parts) {
@@ -456,15 +465,36 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
   p.TL = tl;
   const size_t smem = smem_of(tl);
   dim3 grid(ceil_div(pl->m2, tl), images);
-  // rows per item: the largest G that still gives every thread of the block an item in both transforms
-  const int Pmin = (p.ca < p.cb ? p.ca : p.cb) * tl;
-  int g = 1;
-  for (int cand = 8; cand > 1; cand >>= 1)
-    if (Pmin * ceil_div(pl->K, cand) >= 256) { g = cand; break; }
-#define BDN_CORE(B, GG) launch_core2d_t<B, GG>(p, grid, smem, st)
-  if (bwd) { if (g == 8) BDN_CORE(true, 8); else if (g == 4) BDN_CORE(true, 4); else if (g == 2) BDN_CORE(true, 2); else BDN_CORE(true, 1); }
-  else     { if (g == 8) BDN_CORE(false, 8); else if (g == 4) BDN_CORE(false, 4); else if (g == 2) BDN_CORE(false, 2); else BDN_CORE(false, 1); }
+  // Work items: phase 1 has Pa * ceil(K / G1), phase 3 has Pb * ceil(hp / G3).  With few images (the
+  // heads) every block should run as many threads as it has items (latency-bound); with many images
+  // (the per-snapshot net) larger G gives more FMAs per shared-memory load.
+  const int Pa = p.ca * tl, Pb = p.cb * tl;
+  int g1 = 1, g3 = 1;
+  const int target = 384;
+  for (int cand = 4; cand >= 1; cand >>= 1)
+    if (Pa * ceil_div(pl->K, cand) >= target || cand == 1) { g1 = cand; break; }
+  for (int cand = 8; cand >= 1; cand >>= 1)
+    if (Pb * ceil_div(pl->hp, cand) >= target || cand == 1) { g3 = cand; break; }
+  const int items1 = Pa * ceil_div(pl->K, g1), items3 = Pb * ceil_div(pl->hp, g3);
+  const int most = items1 > items3 ? items1 : items3;
+  int threads = ceil_div(most, ceil_div(most, 1024));      // balanced rounds when one block cannot hold all items
+  threads = (threads + 31) & ~31;
+  if (threads < 128) threads = 128;
+  if (threads > 1024) threads = 1024;
+#define BDN_CORE3(B, A1)                                                              \
+  {                                                                                   \
+    if (g3 == 8) launch_core2d_t<B, A1, 8>(p, grid, threads, smem, st);               \
+    else if (g3 == 4) launch_core2d_t<B, A1, 4>(p, grid, threads, smem, st);          \
+    else if (g3 == 2) launch_core2d_t<B, A1, 2>(p, grid, threads, smem, st);          \
+    else launch_core2d_t<B, A1, 1>(p, grid, threads, smem, st);                       \
+  }
+#define BDN_CORE(B)                                                                   \
+  {                                                                                   \
+    if (g1 == 4) BDN_CORE3(B, 4) else if (g1 == 2) BDN_CORE3(B, 2) else BDN_CORE3(B, 1) \
+  }
+  if (bwd) BDN_CORE(true) else BDN_CORE(false)
 #undef BDN_CORE
+#undef BDN_CORE3
 }
 
 // ===========================================================================
@@ -751,25 +781,36 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
   }
 
   if (MODE == 2) {
-    // 1x1-conv weight / bias gradients over this tile: pair (o, i) per warp, lanes over pixels; the
-    // block's partials are collected in shared memory and flushed with 128-bit atomics (4x fewer L2
-    // atomic operations on these few, heavily contended addresses).
+    // 1x1-conv weight / bias gradients over this tile.  Thread = (pair (o, i), pixel slice): 128-bit
+    // loads along the pixels (row-strided, conflict-free for the padded widths used), partial sums
+    // joined in shared memory, then one flush per block with 128-bit atomics (4x fewer L2 atomic
+    // operations on these few, heavily contended addresses).
     const int npair = c * c + c, npair4 = (npair + 3) & ~3;
     float* part = gsm + c * npx;     // [c*c + c], padded to a multiple of 4
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    for (int pair = warp; pair < npair4; pair += nwarps) {
+    for (int q = tid; q < npair4; q += nt) part[q] = 0.f;
+    __syncthreads();
+    const int nsl = nt / npair > 0 ? nt / npair : 1;           // pixel slices (threads per pair)
+    const int nq = npx >> 2;                                   // float4 chunks per channel plane (WCH % 4 == 0)
+    for (int item = tid; item < npair * nsl; item += nt) {
+      const int pair = item % npair, sl = item / npair;
+      const int q0 = (int)((long)sl * nq / nsl), q1 = (int)((long)(sl + 1) * nq / nsl);
       float s = 0.f;
       if (pair < c * c) {
         const int o = pair / c, i = pair - o * c;
-        const float* go = as + o * npx;
-        const float* ai = zact + i * npx;
-        for (int px = lane; px < npx; px += 32) s = fmaf(go[px], ai[px], s);
-      } else if (pair < npair) {
-        const float* go = as + (pair - c * c) * npx;
-        for (int px = lane; px < npx; px += 32) s += go[px];
+        const float4* go = reinterpret_cast<const float4*>(as + o * npx);
+        const float4* ai = reinterpret_cast<const float4*>(zact + i * npx);
+        for (int q = q0; q < q1; ++q) {
+          const float4 g4 = go[q], a4 = ai[q];
+          s = fmaf(g4.x, a4.x, fmaf(g4.y, a4.y, fmaf(g4.z, a4.z, fmaf(g4.w, a4.w, s))));
+        }
+      } else {
+        const float4* go = reinterpret_cast<const float4*>(as + (pair - c * c) * npx);
+        for (int q = q0; q < q1; ++q) {
+          const float4 g4 = go[q];
+          s += (g4.x + g4.y) + (g4.z + g4.w);
+        }
       }
-      s = warp_sum(s);
-      if (lane == 0) part[pair] = s;
+      if (nsl > 1) atomicAdd(part + pair, s); else part[pair] = s;
     }
     __syncthreads();
     const bool vec_ok = ((c * c) & 3) == 0 && (c & 3) == 0 &&
