@@ -76,6 +76,13 @@ int bdn_spectral_backward(const BdnSpectralShape* s, const float* gy, const floa
                           const float* w1, const float* w2, float* gx, float* gw1, float* gw2,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* One stage on its own, for stage-level parity tests and kernel benchmarks: the pruned forward
+ * DFT along W of `rows` rows (the rfft of 1d_FPE/FNOModules.py:50 / the W pass of rfft2,
+ * 2d_FPE/FNOModules.py:163, kept bins only).  x: [rows, wp]; out: [rows, m2] complex.
+ * act != 0 applies the exact GELU on load.  prec = BDN_PREC_TF32 runs the tcgen05 kernel. */
+int bdn_stage_wfwd(int32_t hp, int32_t wp, int32_t m1, int32_t m2, int32_t rows, const float* x, float* out,
+                   int32_t act, int32_t prec, void* stream);
+
 /* ---------------------------------------------------------------------------
  * A whole FNO net: FNO1d.forward 1d_FPE/FNOModules.py:99-122,
  *                  FNO2d.forward 2d_FPE/FNOModules.py:218-240.

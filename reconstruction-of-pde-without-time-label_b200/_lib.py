@@ -57,6 +57,7 @@ EXPORTS = {
     "bdn_spectral_forward": (C.c_int, [C.POINTER(SpectralShape), _fp, _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "bdn_spectral_backward": (C.c_int, [C.POINTER(SpectralShape), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                                         C.c_size_t, _fp]),
+    "bdn_stage_wfwd": (C.c_int, [C.c_int32] * 5 + [_fp, _fp, C.c_int32, C.c_int32, _fp]),
     "bdn_fno_act_floats": (C.c_size_t, [C.POINTER(FnoShape)]),
     "bdn_fno_spec_floats": (C.c_size_t, [C.POINTER(FnoShape)]),
     "bdn_fno_workspace_bytes": (C.c_size_t, [C.POINTER(FnoShape)]),

@@ -135,6 +135,11 @@ const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2) {
   pl->col_fwd = upload(col_fwd);
   pl->col_dc = upload(col_dc);
   pl->tc_fwd_b = nullptr; pl->tc_inv_b = nullptr;
+  if ((wp & 3) == 0 && tc_n_pad(m2) <= 256) {
+    std::vector<float> img;
+    tc_build_b_image(wp, m2, img);
+    pl->tc_fwd_b = upload(img);      // optional: a failed upload only disables the tensor-core path
+  }
 
   if (!pl->t_wl || !pl->t_lw_cos || !pl->t_lw_sin || !pl->col_fwd || !pl->col_dc ||
       (ndim == 2 && (!pl->t_hk || !pl->t_kh))) {
@@ -318,6 +323,19 @@ int bdn_spectral_backward(const BdnSpectralShape* s, const float* gy, const floa
   return check_cuda("bdn_spectral_backward");
 }
 
+int bdn_stage_wfwd(int32_t hp, int32_t wp, int32_t m1, int32_t m2, int32_t rows, const float* x, float* out,
+                   int32_t act, int32_t prec, void* stream) {
+  const int ndim = hp > 1 ? 2 : 1;
+  int rc = check_modes(ndim, hp, wp, m1, m2);
+  if (rc != BDN_OK) return rc;
+  if (!x || !out || rows < 0) return set_error(BDN_ERR_INVALID, "bad arguments");
+  if (rows == 0) return BDN_OK;
+  const Plan* pl = get_plan(ndim, hp, wp, m1, m2);
+  if (!pl) return BDN_ERR_CUDA;
+  launch_wfwd(pl, x, (float2*)out, rows, act, (cudaStream_t)stream, prec);
+  return check_cuda("bdn_stage_wfwd");
+}
+
 // ---------------------------------------------------------------------------
 // a whole FNO net
 // ---------------------------------------------------------------------------
@@ -414,7 +432,7 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
   for (int k = 0; k < s->n_layers; ++k) {
     const int act_in = k > 0;
     float2* xs_k = xs_saved ? (float2*)(xs_saved + (size_t)k * ksp) : nullptr;
-    launch_wfwd(pl, zbuf(k), X1, rows, act_in, st);
+    launch_wfwd(pl, zbuf(k), X1, rows, act_in, st, s->prec);
     if (s->ndim == 2)
       launch_core2d(pl, X1, Z, xs_k, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], s->images, s->width,
                     s->width, false, st);
@@ -457,7 +475,7 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
                      g->fc1_b, g->fc2_w, g->fc2_b, st);
   const int rows = s->images * s->width * s->hp;
   for (int k = s->n_layers - 1; k >= 0; --k) {
-    launch_wfwd(pl, gz[cur], G1, rows, 0, st);
+    launch_wfwd(pl, gz[cur], G1, rows, 0, st, s->prec);
     if (s->ndim == 2)
       launch_core2d(pl, G1, GZ, GY, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], s->images, s->width,
                     s->width, true, st);

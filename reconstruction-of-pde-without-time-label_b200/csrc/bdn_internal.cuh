@@ -26,8 +26,8 @@ struct Plan {
   float* col_fwd;    // [m2]  c_l / (hp*wp)   Hermitian doubling + irfft normalisation
   float* col_dc;     // [m2]  1-D: 0.5 at l = 0 (reference halves the DC bin), else 1
   // TF32 tensor-core path: the W tables as K-major GEMM operands (see tc_gemm.cu)
-  float* tc_fwd_b;   // [n_pad = 2*m2 rounded up to 16][k_pad = wp rounded up to 8]
-  float* tc_inv_b;   // [n_pad = wp rounded up to 16][k_pad = 2*m2 rounded up to 8]
+  float* tc_fwd_b;   // [ceil(wp/32)][2*m2 rounded up to 16][32] fp32, 128-byte-swizzled smem image (or null)
+  float* tc_inv_b;   // reserved for the inverse transform
 };
 
 const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2);   // nullptr on failure
@@ -51,7 +51,8 @@ struct LaunchScope {
 // kernel launchers (spectral.cu)
 // ---------------------------------------------------------------------------
 // rows x wp real -> rows x m2 complex; act != 0 applies exact GELU on load.
-void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st);
+// prec = BDN_PREC_TF32 routes eligible calls (no activation on load, shape fits) to the tcgen05 kernel.
+void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st, int prec = 0);
 
 // 2-D middle stage for one pass over `images` images:
 //   in  [images, ca, hp, m2] complex  --H fwd, *pre--> spec_out [images, ca, K, m2] (if non-null)
@@ -65,6 +66,18 @@ void launch_mix1d(const Plan* pl, const float2* in, float2* out, float2* spec_ou
 // gw[i,o,k,l] += sum_b conj(xs[b,i,k,l]) * gys[b,o,k,l]   (split into w1 / w2 halves in 2-D)
 void launch_gw_reduce(const Plan* pl, const float2* xs, const float2* gys, float2* gw1, float2* gw2,
                       int images, int ci, int co, cudaStream_t st);
+
+// ---------------------------------------------------------------------------
+// tensor-core path (tc_gemm.cu)
+// ---------------------------------------------------------------------------
+}  // namespace bdn
+#include <vector>
+namespace bdn {
+int tc_n_pad(int m2);
+int tc_kch(int wp);
+void tc_build_b_image(int wp, int m2, std::vector<float>& img);     // host image of the swizzled DFT operand
+bool tc_wfwd_supported(const Plan* pl, const float* x);
+bool launch_wfwd_tc(const Plan* pl, const float* x, float2* out, int rows, cudaStream_t st);
 
 enum WinvMode { WINV_PLAIN = 0, WINV_LAYER_FWD = 1, WINV_LAYER_BWD = 2 };
 struct WinvArgs {

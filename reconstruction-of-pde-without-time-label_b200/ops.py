@@ -71,6 +71,19 @@ def profile_end() -> dict:
     return json.loads(buf.value.decode() or "{}")
 
 
+def stage_wfwd(x: torch.Tensor, m2: int, *, hp: int = 1, m1: int = 0, act: bool = False, prec: int = PREC_FP32):
+    """One stage on its own (tests, kernel benchmarks): pruned forward DFT along the last axis of
+    x [rows, wp] -> complex64 [rows, m2].  ``prec=PREC_TF32`` runs the tcgen05 tensor-core kernel."""
+    _need_cuda(x)
+    xc = _f32c(x)
+    rows, wp = xc.shape
+    out = torch.empty(rows, m2, 2, dtype=torch.float32, device=xc.device)
+    with torch.cuda.device(xc.device):
+        check(_lib.lib().bdn_stage_wfwd(hp, wp, m1, m2, rows, _ptr(xc), _ptr(out), int(act), prec, _stream()),
+              "bdn_stage_wfwd")
+    return torch.view_as_complex(out)
+
+
 # ---------------------------------------------------------------------------------------------
 # one FNO net
 # ---------------------------------------------------------------------------------------------

@@ -300,3 +300,26 @@ def test_graph_replay_matches_eager_steps():
     for a, b in zip(l_eager, l_graph):
         assert abs(a - b) <= 1e-6 * max(abs(a), 1.0)
     assert rel_err(graphed.flat_param, eager.flat_param) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# stage level: the W-forward pruned DFT, fp32 CUDA-core kernel and TF32 tcgen05 kernel
+# ---------------------------------------------------------------------------------------------
+TF32_TOL = 2e-3     # BASELINE.json north_star: stated bound of the TF32 tensor-core mode
+
+
+@pytest.mark.parametrize("rows,wp,m2,hp,m1", [(4 * 4 * 76, 76, 12, 76, 12), (1000, 76, 32, 76, 32),
+                                              (300, 100, 12, 100, 12), (129, 76, 12, 76, 12)])
+def test_stage_wfwd_fp32_and_tf32_tensor_core(rows, wp, m2, hp, m1):
+    g = torch.Generator().manual_seed(rows + wp)
+    x = torch.randn(rows, wp, generator=g)
+    want = torch.from_numpy(dft64.wfwd(x.numpy(), m2))
+    got32 = ops.stage_wfwd(x.to(DEV), m2, hp=hp, m1=m1)
+    assert rel_err(got32, want) < TOL
+    launches0 = ops.kernel_launches()
+    got_tc = ops.stage_wfwd(x.to(DEV), m2, hp=hp, m1=m1, prec=ops.PREC_TF32)
+    torch.cuda.synchronize()
+    assert ops.kernel_launches() == launches0 + 1
+    err = rel_err(got_tc, want)
+    assert err < TF32_TOL, f"tcgen05 TF32 W-forward: rel err {err:.3e}"
+    assert err > 1e-7           # it really ran in TF32 (the fp32 kernel would be ~1e-7)
