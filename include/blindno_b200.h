@@ -144,7 +144,9 @@ typedef struct BdnLiftInput {
 
 /* Buffers kept from forward to backward (caller-owned, sizes below). */
 size_t bdn_fno_act_floats(const BdnFnoShape* s);    /* z: (n_layers+1) x [images,width,hp,wp] */
-size_t bdn_fno_spec_floats(const BdnFnoShape* s);   /* xs: n_layers x [images,width,K,m2,2]   */
+size_t bdn_fno_spec_floats(const BdnFnoShape* s);   /* xs: n_layers x [images,width,K,m2,2]
+                                                        (+ n_layers x [m2,K,width,width,2]: mode-major
+                                                        weight copy, few-image 2-D nets only)      */
 size_t bdn_fno_workspace_bytes(const BdnFnoShape* s);
 
 /* out: [images, out_h, out_w, c_out] channels-last.  z_saved / xs_saved may be

@@ -364,13 +364,20 @@ static size_t kspec_floats1(const BdnFnoShape* s) {
 size_t bdn_fno_act_floats(const BdnFnoShape* s) {
   return check_fno(s) == BDN_OK ? (size_t)(s->n_layers + 1) * act_floats1(s) : 0;
 }
+// Few-image nets (the output heads) keep a mode-major copy of their spectral weights next to the saved
+// spectra: core2d blocks then own a single mode column each and read its coefficients contiguously.
+static bool use_mode_major(const BdnFnoShape* s) { return s->ndim == 2 && (long)s->images * s->m2 < 4L * 2 * 148; }
+static size_t wt_floats1(const BdnFnoShape* s) { return (size_t)s->m2 * 2 * s->m1 * s->width * s->width * 2; }
+
 size_t bdn_fno_spec_floats(const BdnFnoShape* s) {
-  return check_fno(s) == BDN_OK ? (size_t)s->n_layers * kspec_floats1(s) : 0;
+  if (check_fno(s) != BDN_OK) return 0;
+  return (size_t)s->n_layers * kspec_floats1(s) + (use_mode_major(s) ? (size_t)s->n_layers * wt_floats1(s) : 0);
 }
 size_t bdn_fno_workspace_bytes(const BdnFnoShape* s) {
   if (check_fno(s) != BDN_OK) return 0;
   return 2 * align_up(spec1_bytes(s->images, s->width, s->hp, s->m2)) + 2 * align_up(act_floats1(s) * sizeof(float)) +
-         align_up(kspec_floats1(s) * sizeof(float)) + 256;
+         align_up(kspec_floats1(s) * sizeof(float)) +
+         (use_mode_major(s) ? align_up((size_t)s->n_layers * wt_floats1(s) * sizeof(float)) : 0) + 256;
 }
 
 static LiftArgs make_lift(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftInput* in) {
@@ -426,6 +433,14 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
   if (!X1 || !Z || (!z_saved && (!zping[0] || !zping[1])))
     return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
   auto zbuf = [&](int k) { return z_saved ? z_saved + (size_t)k * act : zping[k & 1]; };
+  float2* wt = nullptr;
+  if (use_mode_major(s)) {
+    wt = xs_saved ? (float2*)(xs_saved + (size_t)s->n_layers * ksp)
+                  : (float2*)cv.take((size_t)s->n_layers * wt_floats1(s) * sizeof(float));
+    if (!wt) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+    launch_spec_weights_mode_major(pl, p->spec_w1, p->spec_w2, s->n_layers, s->width, s->width, wt, st);
+  }
+  const size_t wt1 = wt_floats1(s) / 2;   // float2 per layer
 
   launch_lift(make_lift(s, p, in), zbuf(0), st);
   const int rows = s->images * s->width * s->hp;
@@ -435,7 +450,7 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
     launch_wfwd(pl, zbuf(k), X1, rows, act_in, st, s->prec);
     if (s->ndim == 2)
       launch_core2d(pl, X1, Z, xs_k, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], s->images, s->width,
-                    s->width, false, st);
+                    s->width, false, st, wt ? wt + (size_t)k * wt1 : nullptr);
     else
       launch_mix1d(pl, X1, Z, xs_k, (const float2*)p->spec_w1[k], s->images, s->width, s->width, false, st);
     WinvArgs wa{};
@@ -470,6 +485,8 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
   float2* GY = (float2*)cv.take(ksp * sizeof(float));
   if (!G1 || !GZ || !gz[0] || !gz[1] || !GY) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
 
+  const float2* wt = use_mode_major(s) ? (const float2*)(xs_saved + (size_t)s->n_layers * ksp) : nullptr;
+  const size_t wt1 = wt_floats1(s) / 2;
   int cur = 0;
   launch_project_bwd(make_proj(s, p, z_saved + (size_t)s->n_layers * act), g_out, pooled_g, n_keep, gz[cur], g->fc1_w,
                      g->fc1_b, g->fc2_w, g->fc2_b, st);
@@ -478,7 +495,7 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
     launch_wfwd(pl, gz[cur], G1, rows, 0, st, s->prec);
     if (s->ndim == 2)
       launch_core2d(pl, G1, GZ, GY, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], s->images, s->width,
-                    s->width, true, st);
+                    s->width, true, st, wt ? wt + (size_t)k * wt1 : nullptr);
     else
       launch_mix1d(pl, G1, GZ, GY, (const float2*)p->spec_w1[k], s->images, s->width, s->width, true, st);
     launch_gw_reduce(pl, (const float2*)(xs_saved + (size_t)k * ksp), GY, (float2*)g->spec_w1[k],

@@ -57,9 +57,12 @@ void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act,
 // 2-D middle stage for one pass over `images` images:
 //   in  [images, ca, hp, m2] complex  --H fwd, *pre--> spec_out [images, ca, K, m2] (if non-null)
 //   --mix with W (fwd: W[a][b]; bwd: conj(W[b][a]))--> --H inv, *post--> out [images, cb, hp, m2]
+// wt (optional): mode-major copy of (w1, w2) made by launch_spec_weights_mode_major.
 void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_out,
                    const float2* w1, const float2* w2, int images, int ci_layer, int co_layer,
-                   bool bwd, cudaStream_t st);
+                   bool bwd, cudaStream_t st, const float2* wt = nullptr);
+void launch_spec_weights_mode_major(const Plan* pl, const float* const* w1, const float* const* w2, int n_layers,
+                                    int ci, int co, float2* wt, cudaStream_t st);
 // 1-D middle stage (no H transform): in [images, ca, m2] -> out [images, cb, m2]
 void launch_mix1d(const Plan* pl, const float2* in, float2* out, float2* spec_out, const float2* w,
                   int images, int ci_layer, int co_layer, bool bwd, cudaStream_t st);

@@ -348,6 +348,11 @@ void launch_project(const ProjArgs& a, float* out, cudaStream_t st) {
   });
 }
 
+template <int CP>
+__host__ __device__ constexpr int proj_nvp() { return CP + 2 <= 8 ? 8 : (CP + 2 <= 16 ? 16 : 32); }
+template <int CP, int NOUT, int JS>
+__host__ __device__ constexpr bool proj_treduce() { return NOUT == 1 && JS == 1 && CP <= 12; }
+
 // projection backward.  Same thread mapping; for every hidden unit the pre-activation is
 // recomputed, gz accumulates in registers (reduced over the JS slices at the end), and the weight
 // gradient partials are reduced over the lanes that share a slice, then added to per-block shared
@@ -365,6 +370,11 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_bwd_kernel(const ProjArg
   float* ab1 = aw1 + hidden * CP;          // [hidden]
   float* aw2 = ab1 + hidden;               // [nout][hidden]
   float* ab2 = aw2 + nout * hidden;        // [PROJ_MAX_OUT]
+  constexpr bool TREDUCE = proj_treduce<CP, NOUT, JS>();
+  constexpr int NVP = proj_nvp<CP>();
+  float* wacc = ab2 + PROJ_MAX_OUT;        // [warps][hidden][NVP] warp-private accumulators (TREDUCE)
+  if constexpr (TREDUCE)
+    for (int i = threadIdx.x; i < (PROJ_THREADS / 32) * hidden * NVP; i += blockDim.x) wacc[i] = 0.f;
   for (int i = threadIdx.x; i < hidden * CP; i += blockDim.x) {
     const int j = i / CP, c = i - j * CP;
     w1s[i] = c < a.width ? __ldg(a.w1 + j * a.width + c) : 0.f;
@@ -448,22 +458,55 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_bwd_kernel(const ProjArg
 #pragma unroll
         for (int c = 0; c < CP; ++c) { gzr[pp][c] = fmaf(e, w1r[c], gzr[pp][c]); sw1[c] = fmaf(e, z[pp][c], sw1[c]); }
       }
-      // reduce over the lanes that share this slice (xor offsets >= JS), then one lane per slice adds
+      if constexpr (TREDUCE) {
+        // Transpose-reduce: the NV = CP + 2 per-lane partials (padded to NVP, a power of two) are summed
+        // over the warp so that lane (v * 32 / NVP) ends up with the total of value v: NVP - 1 + log2(32 / NVP)
+        // shuffles instead of 5 * NV, and the totals are added to warp-private shared accumulators (no atomics).
+        float val[NVP];
 #pragma unroll
-      for (int off = 16; off >= JS; off >>= 1) {
+        for (int c = 0; c < CP; ++c) val[c] = sw1[c];
+        val[CP] = sb1;
+        val[CP + 1] = sw2[0];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) sw1[c] += __shfl_xor_sync(0xffffffffu, sw1[c], off);
-        sb1 += __shfl_xor_sync(0xffffffffu, sb1, off);
+        for (int v = CP + 2; v < NVP; ++v) val[v] = 0.f;
+        int n = NVP;
 #pragma unroll
-        for (int k = 0; k < NOUT; ++k) sw2[k] += __shfl_xor_sync(0xffffffffu, sw2[k], off);
-      }
-      if (lane < JS) {
+        for (int off = 16; off >= 32 / NVP; off >>= 1) {
+          const bool up = (lane & off) != 0;
+          n >>= 1;
 #pragma unroll
-        for (int c = 0; c < CP; ++c) atomicAdd(aw1 + j * CP + c, sw1[c]);
-        atomicAdd(ab1 + j, sb1);
+          for (int i = 0; i < NVP / 2; ++i) {
+            if (i < n) {
+              const float send = up ? val[i] : val[i + n];
+              const float keep = up ? val[i + n] : val[i];
+              val[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+        }
 #pragma unroll
-        for (int k = 0; k < NOUT; ++k)
-          if (k < nout) atomicAdd(aw2 + k * hidden + j, sw2[k]);
+        for (int off = 16 / NVP; off > 0; off >>= 1) val[0] += __shfl_xor_sync(0xffffffffu, val[0], off);
+        if ((lane & (32 / NVP - 1)) == 0) {
+          float* dst = wacc + ((size_t)warp * hidden + j) * NVP + lane / (32 / NVP);
+          *dst += val[0];
+        }
+      } else {
+        // reduce over the lanes that share this slice (xor offsets >= JS), then one lane per slice adds
+#pragma unroll
+        for (int off = 16; off >= JS; off >>= 1) {
+#pragma unroll
+          for (int c = 0; c < CP; ++c) sw1[c] += __shfl_xor_sync(0xffffffffu, sw1[c], off);
+          sb1 += __shfl_xor_sync(0xffffffffu, sb1, off);
+#pragma unroll
+          for (int k = 0; k < NOUT; ++k) sw2[k] += __shfl_xor_sync(0xffffffffu, sw2[k], off);
+        }
+        if (lane < JS) {
+#pragma unroll
+          for (int c = 0; c < CP; ++c) atomicAdd(aw1 + j * CP + c, sw1[c]);
+          atomicAdd(ab1 + j, sb1);
+#pragma unroll
+          for (int k = 0; k < NOUT; ++k)
+            if (k < nout) atomicAdd(aw2 + k * hidden + j, sw2[k]);
+        }
       }
     }
 #pragma unroll
@@ -477,6 +520,18 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_bwd_kernel(const ProjArg
     }
   }
   __syncthreads();
+  if constexpr (TREDUCE) {
+    for (int i = threadIdx.x; i < hidden * (CP + 2); i += blockDim.x) {
+      const int j = i / (CP + 2), v = i - j * (CP + 2);
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < PROJ_THREADS / 32; ++w) s += wacc[((size_t)w * hidden + j) * NVP + v];
+      if (v < CP) aw1[j * CP + v] = s;
+      else if (v == CP) ab1[j] = s;
+      else aw2[j] = s;
+    }
+    __syncthreads();
+  }
   // flush: 128-bit atomics where the layout allows (4x fewer L2 atomic operations on contended lines)
   const bool h4 = (hidden & 3) == 0;       // keeps every shared accumulator array 16-byte aligned
   auto vec_ok = [h4](const void* ptr, int n) { return h4 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (n & 3) == 0; };
@@ -512,7 +567,8 @@ static void launch_project_bwd_t(const ProjArgs& a, const float* g_out, int pool
   const long cap = JS == 1 ? 148L * 2 : 148L * 4;
   const long rounds = (ntiles + cap - 1) / cap;
   const int grid = (int)((ntiles + rounds - 1) / rounds);      // balanced: every block runs `rounds` tiles
-  const size_t smem = (size_t)(2 * (a.hidden * CP + a.hidden + a.c_out * a.hidden) + PROJ_MAX_OUT) * sizeof(float);
+  size_t smem = (size_t)(2 * (a.hidden * CP + a.hidden + a.c_out * a.hidden) + PROJ_MAX_OUT) * sizeof(float);
+  if (proj_treduce<CP, NOUT, JS>()) smem += (size_t)(PROJ_THREADS / 32) * a.hidden * proj_nvp<CP>() * sizeof(float);
   cudaFuncSetAttribute(project_bwd_kernel<CP, NOUT, JS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   project_bwd_kernel<CP, NOUT, JS, PP><<<grid, PROJ_THREADS, smem, st>>>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1,
                                                                         g_w2, g_b2);

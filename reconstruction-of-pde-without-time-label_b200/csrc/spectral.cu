@@ -286,6 +286,7 @@ void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act,
 struct CoreParams {
   const float2* in; float2* out; float2* spec_out;
   const float2* w1; const float2* w2;
+  const float2* wt;      // optional mode-major copy [m2][K][ci][co] (few-image regime, see spec_weights_mode_major)
   const float2* t_hk; const float2* t_kh;
   const float* pre; const float* post;
   int ca, cb, co_layer, hp, hp8, m1, m2, K, Kp, TL;
@@ -382,31 +383,60 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
   __syncthreads();
 
   // phase 2: per-mode channel mix.  fwd: y_b = sum_a x_a W[a][b]; bwd: y_b = sum_a x_a conj(W[b][a])
-  for (int idx = tid; idx < K * Pb; idx += nt) {
-    const int lt = idx % TL, k = (idx / TL) % K, bc = idx / (TL * K);
-    const int l = l0 + lt;
-    float yr = 0.f, yi = 0.f;
-    if (l < m2) {
-      const bool lo = k < p.m1;
-      const float2* wsel = lo ? p.w1 : p.w2;
-      const int kk = lo ? k : k - p.m1;
-      const size_t mode_off = (size_t)kk * m2 + l;
-      const size_t cstride = (size_t)p.m1 * m2;
+  if (p.wt != nullptr) {
+    // mode-major weights: the K*ci*co coefficients of one mode column are contiguous, so a block that owns
+    // few columns reads them with full sectors (the parameter layout has the mode index innermost: one
+    // 8-byte element per 32-byte sector for a single column)
+    const int ci = BWD ? p.cb : p.ca, co = p.co_layer;
+    for (int idx = tid; idx < K * Pb; idx += nt) {
+      const int bc = idx % p.cb, k = (idx / p.cb) % K, lt = idx / (p.cb * K);
+      const int l = l0 + lt;
+      float yr = 0.f, yi = 0.f;
+      if (l < m2) {
+        const float2* wm = p.wt + ((size_t)l * K + k) * ci * co;
 #pragma unroll 4
-      for (int a = 0; a < p.ca; ++a) {
-        const float2 x = bufX[k * Pa + a * TL + lt];
-        if (!BWD) {
-          const float2 w = __ldg(wsel + (size_t)(a * p.co_layer + bc) * cstride + mode_off);
-          yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
-          yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
-        } else {
-          const float2 w = __ldg(wsel + (size_t)(bc * p.co_layer + a) * cstride + mode_off);
-          yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
-          yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
+        for (int a = 0; a < p.ca; ++a) {
+          const float2 x = bufX[k * Pa + a * TL + lt];
+          if (!BWD) {
+            const float2 w = __ldg(wm + a * co + bc);
+            yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
+            yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
+          } else {
+            const float2 w = __ldg(wm + bc * co + a);
+            yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
+            yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
+          }
         }
       }
+      bufA[k * Pb + bc * TL + lt] = make_float2(yr, yi);
     }
-    bufA[k * Pb + bc * TL + lt] = make_float2(yr, yi);
+  } else {
+    for (int idx = tid; idx < K * Pb; idx += nt) {
+      const int lt = idx % TL, k = (idx / TL) % K, bc = idx / (TL * K);
+      const int l = l0 + lt;
+      float yr = 0.f, yi = 0.f;
+      if (l < m2) {
+        const bool lo = k < p.m1;
+        const float2* wsel = lo ? p.w1 : p.w2;
+        const int kk = lo ? k : k - p.m1;
+        const size_t mode_off = (size_t)kk * m2 + l;
+        const size_t cstride = (size_t)p.m1 * m2;
+#pragma unroll 4
+        for (int a = 0; a < p.ca; ++a) {
+          const float2 x = bufX[k * Pa + a * TL + lt];
+          if (!BWD) {
+            const float2 w = __ldg(wsel + (size_t)(a * p.co_layer + bc) * cstride + mode_off);
+            yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
+            yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
+          } else {
+            const float2 w = __ldg(wsel + (size_t)(bc * p.co_layer + a) * cstride + mode_off);
+            yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
+            yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
+          }
+        }
+      }
+      bufA[k * Pb + bc * TL + lt] = make_float2(yr, yi);
+    }
   }
   __syncthreads();
 
@@ -437,11 +467,48 @@ static void launch_core2d_t(const CoreParams& p, dim3 grid, int threads, size_t 
   core2d_kernel<BWD, G1, G3><<<grid, threads, smem, st>>>(p);
 }
 
+// Mode-major copy of the spectral weights of up to BDN_MAX_LAYERS layers: wt[layer][l][k][i][o] (k over
+// the 2*m1 kept rows, weights1 then weights2) from the parameter layout [i][o][m1][m2] (x2 tensors).
+struct WtParams {
+  const float2* w1[8]; const float2* w2[8];
+  float2* wt; int ci, co, m1, m2, n_layers;
+};
+
+__global__ void spec_weights_mode_major_kernel(const WtParams p) {
+  const int K = 2 * p.m1;
+  const long per_layer = (long)p.m2 * K * p.ci * p.co;
+  const int layer = blockIdx.y;
+  const float2* w1 = p.w1[layer];
+  const float2* w2 = p.w2[layer];
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < per_layer; idx += (long)gridDim.x * blockDim.x) {
+    const int o = idx % p.co, i = (idx / p.co) % p.ci, k = (idx / ((long)p.co * p.ci)) % K,
+              l = idx / ((long)p.co * p.ci * K);
+    const bool lo = k < p.m1;
+    const int kk = lo ? k : k - p.m1;
+    p.wt[layer * per_layer + idx] = __ldg((lo ? w1 : w2) + ((size_t)(i * p.co + o) * p.m1 + kk) * p.m2 + l);
+  }
+}
+
+void launch_spec_weights_mode_major(const Plan* pl, const float* const* w1, const float* const* w2, int n_layers,
+                                    int ci, int co, float2* wt, cudaStream_t st) {
+  LaunchScope scope("spec_w_mode_major", st, co);
+  WtParams p;
+  for (int k = 0; k < 8; ++k) {
+    p.w1[k] = k < n_layers ? reinterpret_cast<const float2*>(w1[k]) : nullptr;
+    p.w2[k] = k < n_layers ? reinterpret_cast<const float2*>(w2[k]) : nullptr;
+  }
+  p.wt = wt; p.ci = ci; p.co = co; p.m1 = pl->m1; p.m2 = pl->m2; p.n_layers = n_layers;
+  const long per_layer = (long)pl->m2 * pl->K * ci * co;
+  dim3 grid((unsigned)((per_layer + 255) / 256 < 148 * 8 ? (per_layer + 255) / 256 : 148 * 8), n_layers);
+  spec_weights_mode_major_kernel<<<grid, 256, 0, st>>>(p);
+}
+
 void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_out, const float2* w1,
-                   const float2* w2, int images, int ci_layer, int co_layer, bool bwd, cudaStream_t st) {
+                   const float2* w2, int images, int ci_layer, int co_layer, bool bwd, cudaStream_t st,
+                   const float2* wt) {
   LaunchScope scope(bwd ? "core2d_bwd" : "core2d_fwd", st, co_layer);
   CoreParams p;
-  p.in = in; p.out = out; p.spec_out = spec_out; p.w1 = w1; p.w2 = w2;
+  p.in = in; p.out = out; p.spec_out = spec_out; p.w1 = w1; p.w2 = w2; p.wt = wt;
   p.t_hk = pl->t_hk; p.t_kh = pl->t_kh;
   p.pre = bwd ? pl->col_fwd : pl->col_dc;
   p.post = bwd ? pl->col_dc : pl->col_fwd;
@@ -471,7 +538,7 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
   // (the per-snapshot net) larger G gives more FMAs per shared-memory load.
   const int Pa = p.ca * tl, Pb = p.cb * tl;
   int g1 = 1, g3 = 1;
-  const int target = 384;
+  const int target = 256;
   for (int cand = 4; cand >= 1; cand >>= 1)
     if (Pa * ceil_div(pl->K, cand) >= target || cand == 1) { g1 = cand; break; }
   for (int cand = 8; cand >= 1; cand >>= 1)

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (FnoGrads, FnoParams, FnoShape, LiftInput, MAX_LAYERS, PREC_FP32, PREC_TF32, SpectralShape,
                    check, pad_amount)
 
-__all__ = ["FnoSpec", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat", "kernel_launches",
+__all__ = ["FnoSpec", "set_precision", "stage_wfwd", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat", "kernel_launches",
            "PREC_FP32", "PREC_TF32"]
 
 
@@ -43,6 +43,18 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise RuntimeError(f"blindno_b200 ops are fp32, got {t.dtype}")
     return t.contiguous()
+
+
+def set_precision(module, prec: int):
+    """Select the arithmetic of the DFT GEMMs for every FNO net under ``module``: PREC_FP32 (CUDA-core FFMA,
+    the 1e-5 parity mode, default) or PREC_TF32 (tcgen05 tensor cores where a stage has a tensor-core
+    kernel, TF32 operands / fp32 accumulation; bound 2e-3, tests/test_gpu_parity.py)."""
+    if prec not in (PREC_FP32, PREC_TF32):
+        raise ValueError(f"unknown precision {prec}")
+    for m in module.modules():
+        if hasattr(m, "_spec") and hasattr(m, "spectral_list"):
+            m.precision = prec
+    return module
 
 
 def kernel_launches() -> int:

@@ -55,7 +55,10 @@ def test_shape_validation_without_gpu():
     ok = _shape()
     assert L.bdn_fno_workspace_bytes(C.byref(ok)) > 0
     assert L.bdn_fno_act_floats(C.byref(ok)) == 3 * 4 * 4 * 76 * 76
-    assert L.bdn_fno_spec_floats(C.byref(ok)) == 2 * 4 * 4 * 24 * 12 * 2
+    # kept spectra of every layer + (few-image nets only) the mode-major copy of the spectral weights
+    assert L.bdn_fno_spec_floats(C.byref(ok)) == 2 * 4 * 4 * 24 * 12 * 2 + 2 * 12 * 24 * 4 * 4 * 2
+    many = _shape(images=400)
+    assert L.bdn_fno_spec_floats(C.byref(many)) == 2 * 400 * 4 * 24 * 12 * 2
     # overlapping row blocks (Q14), too many columns, too many layers, 1-D with rows
     for bad in (_shape(m1=39), _shape(m2=40), _shape(n_layers=9), _shape(ndim=1), _shape(width=0)):
         assert L.bdn_fno_workspace_bytes(C.byref(bad)) == 0
