@@ -230,6 +230,72 @@ class FlatTrainer:
         return len(self._graphs)
 
 
+class HostPipeline:
+    """Feeds a FlatTrainer from HOST (pinned) batches without stalling the device.
+
+    The reference loop (2d_FPE/train_fno.py:139-145) moves every batch to the device, steps, and calls
+    ``loss.item()`` -- a full host<->device round trip per step.  Here the same three things happen for
+    every step, pipelined: the host->device copy of batch i+1 runs on a copy stream while step i
+    computes (two device staging slots), and the loss of step i is copied to pinned host memory
+    asynchronously and read one step later.  ``step`` returns the previous step's loss as a float
+    (``None`` on the first call); ``flush`` returns the last one.
+    """
+
+    def __init__(self, trainer: FlatTrainer, grid: torch.Tensor):
+        self.trainer, self.grid = trainer, grid
+        dev = trainer.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.slots = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.loss_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.i = 0
+        self._pending = False
+        self.h2d_bytes = 0
+
+    def _issue(self, k: int, hx: torch.Tensor, hy: torch.Tensor):
+        dev = self.trainer.device
+        if self.slots[k] is None or self.slots[k][0].shape != hx.shape or self.slots[k][1].shape != hy.shape:
+            self.slots[k] = (torch.empty(hx.shape, dtype=hx.dtype, device=dev),
+                             torch.empty(hy.shape, dtype=hy.dtype, device=dev))
+        else:
+            self.copy_stream.wait_event(self.consumed[k])      # the step that read this slot has copied it out
+        with torch.cuda.stream(self.copy_stream):
+            self.slots[k][0].copy_(hx, non_blocking=True)
+            self.slots[k][1].copy_(hy, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        self.h2d_bytes = (hx.numel() * hx.element_size() + hy.numel() * hy.element_size())
+
+    def step(self, hx: torch.Tensor, hy: torch.Tensor, next_batch=None):
+        """Step on the host batch (hx, hy); ``next_batch=(hx', hy')`` starts its upload behind this step."""
+        k = self.i & 1
+        if not self._pending:
+            self._issue(k, hx, hy)
+        main = torch.cuda.current_stream(self.trainer.device)
+        main.wait_event(self.ready[k])
+        loss = self.trainer.step(self.slots[k][0], self.grid, self.slots[k][1])
+        self.consumed[k].record(main)
+        self.loss_host[k].copy_(loss, non_blocking=True)
+        self.loss_done[k].record(main)
+        self._pending = next_batch is not None
+        if self._pending:
+            self._issue(k ^ 1, *next_batch)
+        prev = None
+        if self.i > 0:
+            self.loss_done[k ^ 1].synchronize()
+            prev = float(self.loss_host[k ^ 1])
+        self.i += 1
+        return prev
+
+    def flush(self):
+        if self.i == 0:
+            return None
+        k = (self.i - 1) & 1
+        self.loss_done[k].synchronize()
+        return float(self.loss_host[k])
+
+
 def shard_batch(n_samples: int, rank: int, world: int):
     """Contiguous, near-even split of a global batch over ranks (samples are independent bags)."""
     base, extra = divmod(n_samples, world)
