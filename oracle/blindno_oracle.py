@@ -24,6 +24,13 @@ Reference lines followed (all relative to /root/reference):
   niofp2d_fno_forward    2d_FPE/NIOModules.py:543-581
   niofp1d_fno_forward    1d_FPE/NIOModules.py:119-155, 1d_GPE/NIOModules.py:262-289
   draw_bag               2d_FPE/NIOModules.py:548-551 (np.random.randint, then choice)
+  conv_block             1d_GPE/Baselines.py:40-52    (Conv2d, train-mode BatchNorm2d, LeakyReLU(0.2))
+  encoder1d_forward      1d_GPE/Baselines.py:254-287  (1d_FPE skips final_conv4: 1d_FPE/Baselines.py:279)
+  encoder2d_forward      2d_FPE/Baselines.py:186-249
+  ffn_forward            1d_GPE/DeepONetModules.py:155-185 (BatchNorm1d AFTER LeakyReLU(0.01))
+  deeponet_forward       1d_GPE/DeepONetModules.py:142-151 ((branch @ trunk.T + b0) / sqrt(p))
+  nio1d_forward          1d_GPE/NIOModules.py:192-223 (NIOFP_schrodinger), 1d_FPE/NIOModules.py:47-84 (NIOFP)
+  nio2d_forward          2d_FPE/NIOModules.py:46-83 (NIOFP2D)
 """
 from __future__ import annotations
 
@@ -205,6 +212,89 @@ def niofp1d_fno_forward(p, x, grid, heads=("fno_drift", "fno_diffusion"), idx=No
 # ----------------------------------------------------------------------------
 # a whole train step on the CPU (bench.py cpu_baseline / --impl reference)
 # ----------------------------------------------------------------------------
+# ----------------------------------------------------------------------------
+# NIO: DeepONet(branch CNN, trunk FFN) per snapshot -> bag mean + detached fc0 -> FNO heads  (A9, A10)
+# ----------------------------------------------------------------------------
+def conv_block(p, prefix, x, stride, padding, training, slope=0.2):
+    """ConvBlock: Conv2d -> BatchNorm2d (batch statistics in training mode, running ones in eval) ->
+    LeakyReLU(0.2).  The running statistics are not updated here (they are not an output of the path)."""
+    y = F.conv2d(x, p[prefix + "layers.0.weight"], p[prefix + "layers.0.bias"], stride=stride, padding=padding)
+    y = F.batch_norm(y, p[prefix + "layers.1.running_mean"].clone(), p[prefix + "layers.1.running_var"].clone(),
+                     p[prefix + "layers.1.weight"], p[prefix + "layers.1.bias"], training=training,
+                     momentum=0.1, eps=1e-5)
+    return F.leaky_relu(y, slope)
+
+
+def encoder1d_forward(p, x, prefix, training, use_final_conv4=True):
+    """Encoder: [B, L, N] -> [B, L, n_basis]."""
+    nb, nl, n = x.shape
+    y = x.reshape(nb * nl, 1, 1, n)
+    for name in ("conv1", "conv2", "conv3"):
+        y = conv_block(p, f"{prefix}{name}.", y, (1, 2), (0, 1), training)
+    y = conv_block(p, f"{prefix}final_conv1.", y, (1, 1), (0, 1), training)
+    y = conv_block(p, f"{prefix}final_conv2.", y, (1, 1), (0, 0), training)
+    y = conv_block(p, f"{prefix}final_conv3.", y, (1, 1), (0, 0), training)
+    if use_final_conv4:
+        y = conv_block(p, f"{prefix}final_conv4.", y, (1, 1), (0, 0), training)
+    y = y.reshape(nb, nl, -1)
+    return F.linear(y, p[prefix + "linear.weight"], p[prefix + "linear.bias"])
+
+
+def encoder2d_forward(p, x, prefix, training):
+    """Encoder2D: [B, L, 1, nx, ny] -> [B, L, n_basis]."""
+    nb, nl = x.shape[:2]
+    y = x.reshape(nb * nl, *x.shape[2:])
+    y = conv_block(p, prefix + "convblock1.", y, (1, 2), (0, 3), training)
+    for name, stride in (("2_1", 2), ("2_2", 1), ("3_1", 2), ("3_2", 1), ("4_1", 2), ("4_2", 1), ("7_1", 2), ("7_2", 2)):
+        y = conv_block(p, f"{prefix}convblock{name}.", y, (stride, stride), (1, 1), training)
+    y = conv_block(p, prefix + "convblock7_3.", y, (1, 1), (0, 0), training)
+    y = y.reshape(nb, nl, -1)
+    return F.linear(y, p[prefix + "linear.weight"], p[prefix + "linear.bias"])
+
+
+def ffn_forward(p, x, prefix, training):
+    """FFN trunk: LeakyReLU(0.01)(input) -> per hidden layer BatchNorm1d(LeakyReLU(Linear)) -> Linear."""
+    y = F.leaky_relu(F.linear(x, p[prefix + "input_layer.weight"], p[prefix + "input_layer.bias"]), 0.01)
+    k = 0
+    while f"{prefix}hidden_layers.{k}.weight" in p:
+        y = F.leaky_relu(F.linear(y, p[f"{prefix}hidden_layers.{k}.weight"], p[f"{prefix}hidden_layers.{k}.bias"]), 0.01)
+        y = F.batch_norm(y, p[f"{prefix}batch_layers.{k}.running_mean"].clone(),
+                         p[f"{prefix}batch_layers.{k}.running_var"].clone(), p[f"{prefix}batch_layers.{k}.weight"],
+                         p[f"{prefix}batch_layers.{k}.bias"], training=training, momentum=0.1, eps=1e-5)
+        k += 1
+    return F.linear(y, p[prefix + "output_layer.weight"], p[prefix + "output_layer.bias"])
+
+
+def deeponet_forward(p, coeff, basis):
+    """(weights @ basis.T + b0) / sqrt(p), p = number of basis functions."""
+    return (torch.matmul(coeff, basis.T) + p["deeponet.b0"]) / basis.shape[1] ** 0.5
+
+
+def nio1d_forward(p, x, grid, heads=("fno_V",), idx=None, training=False, use_final_conv4=True):
+    """NIOFP_schrodinger / NIOFP: x [B, L0, N], grid [N, 1] -> [B, N, len(heads)]."""
+    if idx is not None:
+        x = x[:, torch.as_tensor(idx)]
+    coeff = encoder1d_forward(p, x, "branch.", training, use_final_conv4)
+    basis = ffn_forward(p, grid, "trunk.", training)
+    s = deeponet_forward(p, coeff, basis)                        # [B, L, N]
+    lifted = bag_pool_lift(s, grid, p["fc0.weight"], p["fc0.bias"])
+    outs = [fno1d_forward(p, lifted, prefix=h + ".") for h in heads]
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
+
+
+def nio2d_forward(p, x, grid, heads=("fno_drift", "fno_diffusion"), idx=None, training=False):
+    """NIOFP2D: x [B, L0, nx, ny], grid [nx, ny, 2] -> [B, nx, ny, len(heads)]."""
+    if idx is not None:
+        x = x[:, torch.as_tensor(idx)]
+    nx, ny = grid.shape[:2]
+    coeff = encoder2d_forward(p, x.unsqueeze(2), "branch.", training)
+    basis = ffn_forward(p, grid.reshape(-1, 2), "trunk.", training)
+    s = deeponet_forward(p, coeff, basis).reshape(x.shape[0], x.shape[1], nx, ny)
+    lifted = bag_pool_lift(s, grid, p["fc0.weight"], p["fc0.bias"])
+    outs = [fno2d_forward(p, lifted, prefix=h + ".") for h in heads]
+    return torch.cat(outs, dim=-1)
+
+
 def trainable(p):
     """The tensors Adam actually updates: everything reached by autograd.
     ``fc0.*`` is detached and the unused ``branch.*`` never gets a grad."""

@@ -1,0 +1,4 @@
+"""NIOModules of the reference directory 2d_FPE, routed to blindno_b200 (see blindno_b200/dropin/__init__.py)."""
+from blindno_b200.dropin import _export
+
+_export("2d_FPE", "NIOModules", globals())

@@ -176,6 +176,54 @@ def main():
     _module_case("niofp1d_gpe_fno_eval", m, torch.randn(2, 6, 32, generator=g.manual_seed(15)),
                  extra_args=(grid1,), grid=grid1.numpy())
 
+    # ---- NIO models (DeepONet branch CNN + trunk FFN -> bag mean -> FNO heads) -------------
+    # The encoders' default widths make the parameters large (1.5 M / 9.9 M floats), so these
+    # fixtures store the construction SEED instead of the state_dict (tests rebuild the weights with
+    # the surface classes, whose seeded init is identical: tests/test_surface_cpu.py), plus inputs,
+    # outputs, and the gradients of everything but the conv stack, whose gradients are stored as norms.
+    def _nio_case(name, module, x, grid, seed, **meta):
+        out, gy = _run(module, (x, grid), 98)
+        small = [(k, p.grad) for k, p in module.named_parameters()
+                 if p.grad is not None and not k.startswith(("branch.conv", "branch.final_conv", "deeponet."))]
+        big = [(k, torch.stack([p.grad.double().norm(), p.grad.double().sum()]))
+               for k, p in module.named_parameters()
+               if p.grad is not None and k.startswith(("branch.conv", "branch.final_conv"))]
+        b0g = [("deeponet.b0", module.deeponet.b0.grad)]
+        nograd = [k for k, p in module.named_parameters() if p.grad is None]
+        _save(name, x=_np(x), y=_np(out), gy=_np(gy), nograd=np.array(nograd, dtype="U"),
+              **{f"meta.{k}": np.asarray(v) for k, v in dict(meta, grid=grid.numpy(), weight_seed=seed).items()},
+              **_pack("g.", small + b0g), **_pack("gnorm.", big))
+
+    NG = load_reference("1d_GPE", "NIOModules")
+    torch.manual_seed(51)
+    m = NG.NIOFP_schrodinger(1, 3, 100, 25, 2, 8, 9, 1, "cpu").train()
+    grid1 = torch.linspace(0, 1, 128).unsqueeze(-1)
+    np.random.seed(7)
+    state = np.random.get_state()
+    n_keep = np.random.randint(50, 52)
+    idx = np.random.choice(52, n_keep)
+    np.random.set_state(state)
+    _nio_case("nio1d_gpe_train", m, torch.randn(2, 52, 128, generator=g.manual_seed(21)), grid1, 51,
+              np_seed=7, idx=idx, ctor=np.array([1, 3, 100, 25, 2, 8, 9, 1]))
+
+    N1 = load_reference("1d_FPE", "NIOModules")
+    torch.manual_seed(52)
+    m = N1.NIOFP(1, 3, 100, 25, 2, 10, 7, 2, "cpu").eval()
+    grid1 = torch.linspace(0, 1, 80).unsqueeze(-1)
+    _nio_case("nio1d_fpe_eval", m, torch.randn(2, 5, 80, generator=g.manual_seed(22)), grid1, 52,
+              ctor=np.array([1, 3, 100, 25, 2, 10, 7, 2]))
+
+    N2 = load_reference("2d_FPE", "NIOModules")
+    torch.manual_seed(53)
+    m = N2.NIOFP2D(2, 3, 100, 25, 2, 6, 5, 2).train()
+    np.random.seed(8)
+    state = np.random.get_state()
+    n_keep = np.random.randint(50, 51)
+    idx = np.random.choice(51, n_keep)
+    np.random.set_state(state)
+    _nio_case("nio2d_fpe_train", m, torch.randn(1, 51, 61, 61, generator=g.manual_seed(23)), grid2d(61), 53,
+              np_seed=8, idx=idx, ctor=np.array([2, 3, 100, 25, 2, 6, 5, 2]))
+
     # ---- one default-shape spectral layer (heads: C=12, 76x76, m=32), weights from a seed
     torch.manual_seed(41)
     layer = F2.SpectralConv2d(12, 12, 32, 32)

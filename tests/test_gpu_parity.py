@@ -355,3 +355,31 @@ def test_tf32_mode_whole_model_within_stated_bound():
         if v is not None:
             worst = max(worst, rel_err(got[k].grad, v))
     assert worst < TF32_GRAD_TOL, f"worst gradient rel err in TF32 mode: {worst:.3e}"
+
+
+# ---------------------------------------------------------------------------------------------
+# NIO models (DeepONet branch CNN on cuDNN, trunk FFN, pool-before-contract tail, our bag pool + FNO heads)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["nio1d_gpe_train", "nio1d_fpe_eval", "nio2d_fpe_train"])
+def test_nio_models_golden(name):
+    from tests.test_oracle_golden import build_nio_from_fixture
+    fx, model, heads, training = build_nio_from_fixture(name)
+    model = model.to(DEV).train(training)
+    if training:
+        np.random.seed(int(fx.meta("np_seed")))
+    # cuDNN convolutions in TF32 would break the fp32 bound: the reference scripts run them in fp32 too
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = model(fx.t("x").to(DEV), fx.t("meta.grid").to(DEV))
+        assert y.shape == fx.t("y").shape
+        assert rel_err(y, fx.t("y")) < 5e-5      # conv + BatchNorm stack on cuDNN vs MKL: different summation order
+        y.backward(fx.t("gy").to(DEV))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    got = dict(model.named_parameters())
+    for k, g in fx.grads.items():
+        assert got[k].grad is not None, k
+        assert rel_err(got[k].grad, g) < 2e-3, k     # gradients pass through train-mode BatchNorm of tiny batches
+    for k in fx.nograd:
+        assert got[k].grad is None, k

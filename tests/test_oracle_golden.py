@@ -134,3 +134,52 @@ def test_live_reference_default_shape_model():
     np.random.seed(2)
     got = O.niofp2d_fno_forward(p, x, grid, idx=O.draw_bag(100, True))
     assert rel_err(got, want) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# NIO (DeepONet branch + trunk) fixtures: weights rebuilt from the stored construction seed
+# ---------------------------------------------------------------------------------------------
+NIO_CASES = {
+    "nio1d_gpe_train": ("1d_GPE", "NIOFP_schrodinger", ("fno_V",), True),
+    "nio1d_fpe_eval": ("1d_FPE", "NIOFP", ("fno_drift", "fno_diffusion"), False),
+    "nio2d_fpe_train": ("2d_FPE", "NIOFP2D", ("fno_drift", "fno_diffusion"), True),
+}
+
+
+def build_nio_from_fixture(name, device="cpu"):
+    """The surface model of a NIO fixture with the reference's seeded initial weights."""
+    from blindno_b200.surface import nio
+    variant, cls, heads, training = NIO_CASES[name]
+    fx = Fixture(name)
+    torch.manual_seed(int(fx.meta("weight_seed")))
+    args = tuple(int(v) for v in fx.meta("ctor"))
+    extra = ("cpu",) if variant.startswith("1d") else ()
+    model = nio.make_models(variant)[cls](*args, *extra)
+    return fx, model.train(training), heads, training
+
+
+@pytest.mark.parametrize("name", list(NIO_CASES))
+def test_nio_oracle_matches_reference_golden(name):
+    fx, model, heads, training = build_nio_from_fixture(name)
+    variant = NIO_CASES[name][0]
+    p = {k: v.detach().clone().requires_grad_((v.is_floating_point() or v.is_complex()) and "running" not in k)
+         for k, v in model.state_dict().items() if not k.startswith("deeponet.branch.") and not k.startswith("deeponet.trunk.")}
+    idx = fx.meta("idx") if training else None
+    grid = fx.t("meta.grid")
+    if variant.startswith("1d"):
+        y = O.nio1d_forward(p, fx.t("x"), grid, heads=heads, idx=idx, training=training,
+                            use_final_conv4=(variant != "1d_FPE"))
+    else:
+        y = O.nio2d_forward(p, fx.t("x"), grid, heads=heads, idx=idx, training=training)
+    assert y.shape == fx.t("y").shape
+    assert rel_err(y, fx.t("y")) < 2e-5
+    y.backward(fx.t("gy"))
+    for k, g in fx.grads.items():
+        assert p[k].grad is not None, k
+        assert rel_err(p[k].grad, g) < 5e-4, k
+    norms = fx.group("gnorm.")
+    biggest = max(v[0].item() for v in norms.values())
+    for k, stats in norms.items():     # (conv biases before a train-mode BatchNorm have an exactly-zero gradient: noise only)
+        got = p[k].grad.double()
+        assert abs(got.norm().item() - stats[0].item()) <= 1e-3 * max(stats[0].item(), 1e-3 * biggest), k
+    assert p["fc0.weight"].grad is None and p["fc0.bias"].grad is None

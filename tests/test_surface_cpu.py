@@ -96,3 +96,48 @@ def test_live_state_dict_and_seeded_init_parity(variant, cls, args):
     for k in a:
         assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
     assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
+
+
+# ---------------------------------------------------------------------------------------------
+# drop-in module files: the imports the unchanged reference scripts perform
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant,imports", [
+    ("2d_FPE", {"NIOModules": ["NIOFP2D", "NIOFP2D_FNO", "NIOFP2D_FNO_attn"]}),                 # 2d_FPE/train_fno.py:8
+    ("2d_Non_conservative_FPE", {"NIOModules": ["NIOFP2D", "NIOFP2D_FNO", "PermInvUNet_attn"]}),
+    ("1d_FPE", {"NIOModules": ["NIOFP", "NIOFP_FNO"], "FNOModules": ["FNO1d", "FNO2d", "FNO3d"]}),  # 1d_FPE/train_fno.py:7
+    ("1d_GPE", {"NIOModules": ["NIOFP_schrodinger"], "Baselines": ["Encoder", "Encoder2D", "Encoder3D"],
+                "DeepONetModules": ["FeedForwardNN", "DeepOnetNoBiasOrg", "FFN"]}),               # 1d_GPE/train_nio_GPE.py:7
+])
+def test_dropin_modules_resolve_the_scripts_imports(variant, imports):
+    import importlib
+    import subprocess
+    import sys
+    from blindno_b200 import dropin
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim_dir = os.path.join(os.path.dirname(dropin.__file__), variant)
+    # (1) through PYTHONPATH, in a clean interpreter, exactly as a script's `from NIOModules import ...`
+    lines = [f"from {m} import {', '.join(names)}" for m, names in imports.items()]
+    lines.append("import NIOModules; print(sorted(n for n in dir(NIOModules) if n.startswith('NIOFP')))")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([shim_dir, root]))
+    res = subprocess.run([sys.executable, "-c", "\n".join(lines)], capture_output=True, text=True, env=env)
+    assert res.returncode == 0, res.stderr[-2000:]
+    # (2) through install()
+    saved = {k: sys.modules.get(k) for k in ("NIOModules", "FNOModules", "DeepONetModules", "Baselines", "debug_tools")}
+    try:
+        dropin.install(variant)
+        for m, names in imports.items():
+            mod = importlib.import_module(m)
+            for n in names:
+                assert hasattr(mod, n), (m, n)
+        accelerated = nio.make_models(variant)
+        import NIOModules
+        for n in [n for n in imports["NIOModules"] if n in accelerated]:
+            assert getattr(NIOModules, n).__name__ == n
+        with pytest.raises(NotImplementedError):
+            dropin.exports(variant, "NIOModules")["PermInvUNet_attn"]()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
