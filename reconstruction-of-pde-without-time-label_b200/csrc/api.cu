@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -20,6 +21,14 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("BDN_PDL");      // opt-in: measured neutral under CUDA-graph replay (profiles/README.md)
+    return e && e[0] == '1';
+  }();
+  return on;
+}
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;

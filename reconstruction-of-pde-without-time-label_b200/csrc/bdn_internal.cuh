@@ -202,6 +202,36 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch.  A step is a chain of ~90 short dependent kernels; with the launch
+// attribute below the next kernel's blocks are scheduled while the previous kernel drains, and wait in
+// pdl_wait() until that kernel has completed and flushed its memory.  Every kernel of this library calls
+// pdl_launch_dependents() at its very top and pdl_wait() before it touches anything a previous kernel
+// may have written (loads of the constant DFT tables are hoisted above the wait).  Both are no-ops for
+// launches without the attribute.  Opt-in with BDN_PDL=1 in the environment (off by default: it measured
+// neutral once the step is replayed from a CUDA graph, 1.402 ms vs 1.381 ms per step).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace bdn

@@ -34,6 +34,8 @@ __device__ __forceinline__ void lift_fetch(const LiftParams& p, int img, int pix
 constexpr int LIFT_MAX_CIN = 32;
 
 __global__ void __launch_bounds__(256) lift_kernel(const LiftParams p, float* __restrict__ z0) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float smem[];
   float* ws = smem;                        // [width][c_in]
   float* bs = smem + p.width * p.c_in;     // [width]
@@ -76,7 +78,7 @@ void launch_lift(const LiftArgs& a, float* z0, cudaStream_t st) {
   const int block = 256;
   const int grid = (int)((total + block - 1) / block);
   const size_t smem = (size_t)(a.width * a.c_in + a.width) * sizeof(float);
-  lift_kernel<<<grid, block, smem, st>>>(p, z0);
+  launch_k(lift_kernel, dim3(grid), dim3(block), smem, st, p, z0);
 }
 
 // lift backward: g_w0[c][i] += sum gz0[c] * in_i, g_b0[c] += sum gz0[c], gx_cl[.., i] = sum_c W0[c][i] gz0[c]
@@ -87,6 +89,8 @@ template <int TP>
 __global__ void __launch_bounds__(256) lift_bwd_kernel(const LiftParams p, const float* __restrict__ gz0,
                                                        float* g_w0, float* g_b0, float* __restrict__ gx_cl,
                                                        int tiles_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int PT = TP + 4;
   extern __shared__ __align__(16) float smem[];
   const int C = p.width, CI = p.c_in;
@@ -204,10 +208,10 @@ void launch_lift_bwd(const LiftArgs& a, const float* gz0, float* g_w0, float* g_
                                ((a.width * a.c_in + a.width + 3) & ~3) + 4) * sizeof(float) + (size_t)tp * sizeof(long) + 16;
   if (few) {
     cudaFuncSetAttribute(lift_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    lift_bwd_kernel<64><<<grid, 256, smem, st>>>(p, gz0, g_w0, g_b0, gx_cl, tpb);
+    launch_k(lift_bwd_kernel<64>, dim3(grid), dim3(256), smem, st, p, gz0, g_w0, g_b0, gx_cl, tpb);
   } else {
     cudaFuncSetAttribute(lift_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    lift_bwd_kernel<256><<<grid, 256, smem, st>>>(p, gz0, g_w0, g_b0, gx_cl, tpb);
+    launch_k(lift_bwd_kernel<256>, dim3(grid), dim3(256), smem, st, p, gz0, g_w0, g_b0, gx_cl, tpb);
   }
 }
 
@@ -234,6 +238,8 @@ __device__ __forceinline__ void load_w1_row(const float* w1s, int j, float (&w)[
 
 template <int CP, int NOUT, int JS, int PP>   // CP = width rounded up to 4; NOUT = 1 or PROJ_MAX_OUT (runtime c_out)
 __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjArgs a, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   const int hidden = a.hidden, nout = NOUT == 1 ? 1 : a.c_out;
   float* w1s = smem;                               // [hidden][CP]
@@ -328,7 +334,7 @@ static void launch_project_t(const ProjArgs& a, float* out, long total, cudaStre
   const int grid = (int)(ntiles < 148L * 8 ? ntiles : 148L * 8);
   const size_t smem = (size_t)(a.hidden * CP + a.hidden + a.c_out * a.hidden) * sizeof(float);
   cudaFuncSetAttribute(project_kernel<CP, NOUT, JS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  project_kernel<CP, NOUT, JS, PP><<<grid, PROJ_THREADS, smem, st>>>(a, out);
+  launch_k(project_kernel<CP, NOUT, JS, PP>, dim3(grid), dim3(PROJ_THREADS), smem, st, a, out);
 }
 
 void launch_project(const ProjArgs& a, float* out, cudaStream_t st) {
@@ -361,6 +367,8 @@ template <int CP, int NOUT, int JS, int PP>
 __global__ void __launch_bounds__(PROJ_THREADS) project_bwd_kernel(const ProjArgs a, const float* __restrict__ g_out,
                                                                    int pooled_g, int n_keep, float* __restrict__ gz,
                                                                    float* g_w1, float* g_b1, float* g_w2, float* g_b2) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   const int hidden = a.hidden, nout = NOUT == 1 ? 1 : a.c_out;
   float* w1s = smem;                       // [hidden][CP]
@@ -570,7 +578,7 @@ static void launch_project_bwd_t(const ProjArgs& a, const float* g_out, int pool
   size_t smem = (size_t)(2 * (a.hidden * CP + a.hidden + a.c_out * a.hidden) + PROJ_MAX_OUT) * sizeof(float);
   if (proj_treduce<CP, NOUT, JS>()) smem += (size_t)(PROJ_THREADS / 32) * a.hidden * proj_nvp<CP>() * sizeof(float);
   cudaFuncSetAttribute(project_bwd_kernel<CP, NOUT, JS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  project_bwd_kernel<CP, NOUT, JS, PP><<<grid, PROJ_THREADS, smem, st>>>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1,
+  launch_k(project_bwd_kernel<CP, NOUT, JS, PP>, dim3(grid), dim3(PROJ_THREADS), smem, st, a, g_out, pooled_g, n_keep, gz, g_w1, g_b1,
                                                                         g_w2, g_b2);
 }
 
@@ -600,6 +608,8 @@ void launch_project_bwd(const ProjArgs& a, const float* g_out, int pooled_g, int
 __global__ void pool_lift_kernel(const float* __restrict__ s, const float* __restrict__ grid,
                                  const float* __restrict__ w0, const float* __restrict__ b0,
                                  float* __restrict__ out, int n_bags, int n_keep, int npix, int gd, int width) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)n_bags * npix;
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= total) return;
@@ -620,12 +630,14 @@ void launch_pool_lift(const float* s, const float* grid, const float* w0, const 
   LaunchScope scope("pool_lift", st);
   const long total = (long)n_bags * npix;
   const int block = 64;
-  pool_lift_kernel<<<(int)((total + block - 1) / block), block, 0, st>>>(s, grid, w0, b0, out, n_bags, n_keep, npix,
+  launch_k(pool_lift_kernel, dim3((int)((total + block - 1) / block)), dim3(block), 0, st, s, grid, w0, b0, out, n_bags, n_keep, npix,
                                                                          grid_dim, width);
 }
 
 __global__ void pool_lift_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w0,
                                      float* __restrict__ gpool, long total, int gd, int width) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= total) return;
   float acc = 0.f;
@@ -638,7 +650,7 @@ void launch_pool_lift_bwd(const float* g, const float* w0, float* gpool, int n_b
   LaunchScope scope("pool_lift_bwd", st);
   const long total = (long)n_bags * npix;
   const int block = 128;
-  pool_lift_bwd_kernel<<<(int)((total + block - 1) / block), block, 0, st>>>(g, w0, gpool, total, grid_dim, width);
+  launch_k(pool_lift_bwd_kernel, dim3((int)((total + block - 1) / block)), dim3(block), 0, st, g, w0, gpool, total, grid_dim, width);
 }
 
 // ===========================================================================
@@ -647,6 +659,8 @@ void launch_pool_lift_bwd(const float* g, const float* w0, float* gpool, int n_b
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float bc1,
                             float bc2_sqrt, float grad_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
@@ -665,7 +679,7 @@ void launch_adam(float* p, const float* g, float* m, float* v, size_t n, float l
   const int block = 256;
   size_t blocks = (n + block - 1) / block;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  adam_kernel<<<(int)blocks, block, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  launch_k(adam_kernel, dim3((int)blocks), dim3(block), 0, st, p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
 }
 
 }  // namespace bdn

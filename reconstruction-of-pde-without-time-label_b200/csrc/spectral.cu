@@ -18,6 +18,8 @@ template <int RT>
 __global__ void __launch_bounds__(512) wfwd_generic_kernel(const float* __restrict__ x, float2* __restrict__ out,
                                                    const float2* __restrict__ t_wl, int rows, int wp, int m2,
                                                    int act, int wc) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int LT = 4;
   constexpr int BR = 32 * RT;
   constexpr int PITCH = BR + 4;
@@ -107,7 +109,7 @@ static void launch_wfwd_generic(const Plan* pl, const float* x, float2* out, int
 #define BDN_WFWD(RT)                                                                                      \
   {                                                                                                       \
     cudaFuncSetAttribute(wfwd_generic_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
-    wfwd_generic_kernel<RT><<<grid, block, smem, st>>>(x, out, pl->t_wl, rows, wp, m2, act, wc);          \
+    launch_k(wfwd_generic_kernel<RT>, dim3(grid), dim3(block), smem, st, x, out, pl->t_wl, rows, wp, m2, act, wc);          \
   }
   if (rt == 4) BDN_WFWD(4) else if (rt == 2) BDN_WFWD(2) else BDN_WFWD(1)
 #undef BDN_WFWD
@@ -137,12 +139,18 @@ __global__ void __launch_bounds__(256) wfwd_pipe_kernel(const WfwdParams p) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int wp = p.wp, m2 = p.m2, m2p = p.m2p;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init_fence();
   }
+  for (int i = tid; i < wp * m2p; i += nt) {      // constant plan data: staged before the dependency wait
+    const int w = i / m2p, l = i - w * m2p;
+    ts[i] = l < m2 ? __ldg(p.t_wl + (size_t)w * m2 + l) : make_float2(0.f, 0.f);
+  }
   __syncthreads();
+  pdl_wait();
 
   const uint32_t row_bytes = (uint32_t)wp * 4u;
   auto issue = [&](int tile, int stage) {   // called by all lanes of warp 0
@@ -160,13 +168,7 @@ __global__ void __launch_bounds__(256) wfwd_pipe_kernel(const WfwdParams p) {
       for (int r = lane; r < nrows; r += 32)
         bulk_g2s(dst + r * p.pitch, p.x + (size_t)(row0 + r) * wp, row_bytes, &bars[stage]);
   };
-  if (warp == 0 && (int)blockIdx.x < p.ntiles) issue(blockIdx.x, 0);   // in flight while the table loads
-
-  for (int i = tid; i < wp * m2p; i += nt) {
-    const int w = i / m2p, l = i - w * m2p;
-    ts[i] = l < m2 ? __ldg(p.t_wl + (size_t)w * m2 + l) : make_float2(0.f, 0.f);
-  }
-  __syncthreads();
+  if (warp == 0 && (int)blockIdx.x < p.ntiles) issue(blockIdx.x, 0);
 
   const int rg = warp % p.nrg, mg0 = warp / p.nrg, mgstep = (nt >> 5) / p.nrg;
   int it = 0;
@@ -274,7 +276,7 @@ void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act,
 #define BDN_WFWD(RT)                                                                                   \
   {                                                                                                    \
     cudaFuncSetAttribute(wfwd_pipe_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-    wfwd_pipe_kernel<RT><<<grid, 32 * nwarps, smem, st>>>(p);                                          \
+    launch_k(wfwd_pipe_kernel<RT>, dim3(grid), dim3(32 * nwarps), smem, st, p);                                          \
   }
   if (rt == 4) BDN_WFWD(4) else if (rt == 2) BDN_WFWD(2) else BDN_WFWD(1)
 #undef BDN_WFWD
@@ -339,6 +341,7 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
   // item; from L1/L2 the inner loops were latency-bound: ncu long-scoreboard 20 cycles per issue).
   // Both are contiguous in HBM: two bulk async copies, in flight while phase 0 stages the image.
   uint64_t* tbar = reinterpret_cast<uint64_t*>(s_kh + K * p.hp8);
+  pdl_launch_dependents();
   if (tid == 0) {
     mbar_init(tbar, 1);
     mbar_init_fence();
@@ -347,6 +350,7 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
     bulk_g2s(s_hk, p.t_hk, b1, tbar);
     bulk_g2s(s_kh, p.t_kh, b2, tbar);
   }
+  pdl_wait();      // the tables above are constant plan data; everything below reads the previous kernel's output
   // phase 0: stage the image's TL columns, all channels: bufA[h][a*TL + lt]
   for (int idx = tid; idx < p.ca * hp * TL; idx += nt) {
     const int lt = idx % TL, h = (idx / TL) % hp, a = idx / (TL * hp);
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
 template <bool BWD, int G1, int G3>
 static void launch_core2d_t(const CoreParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
   cudaFuncSetAttribute(core2d_kernel<BWD, G1, G3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  core2d_kernel<BWD, G1, G3><<<grid, threads, smem, st>>>(p);
+  launch_k(core2d_kernel<BWD, G1, G3>, dim3(grid), dim3(threads), smem, st, p);
 }
 
 // Mode-major copy of the spectral weights of up to BDN_MAX_LAYERS layers: wt[layer][l][k][i][o] (k over
@@ -475,6 +479,8 @@ struct WtParams {
 };
 
 __global__ void spec_weights_mode_major_kernel(const WtParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int K = 2 * p.m1;
   const long per_layer = (long)p.m2 * K * p.ci * p.co;
   const int layer = blockIdx.y;
@@ -500,7 +506,7 @@ void launch_spec_weights_mode_major(const Plan* pl, const float* const* w1, cons
   p.wt = wt; p.ci = ci; p.co = co; p.m1 = pl->m1; p.m2 = pl->m2; p.n_layers = n_layers;
   const long per_layer = (long)pl->m2 * pl->K * ci * co;
   dim3 grid((unsigned)((per_layer + 255) / 256 < 148 * 8 ? (per_layer + 255) / 256 : 148 * 8), n_layers);
-  spec_weights_mode_major_kernel<<<grid, 256, 0, st>>>(p);
+  launch_k(spec_weights_mode_major_kernel, dim3(grid), dim3(256), 0, st, p);
 }
 
 void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_out, const float2* w1,
@@ -572,6 +578,8 @@ template <bool BWD>
 __global__ void mix1d_kernel(const float2* __restrict__ in, float2* __restrict__ out, float2* __restrict__ spec_out,
                              const float2* __restrict__ w, const float* __restrict__ pre,
                              const float* __restrict__ post, int images, int ca, int cb, int co_layer, int m2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cmax = ca > cb ? ca : cb;
   const long total = (long)images * cmax * m2;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -611,10 +619,10 @@ void launch_mix1d(const Plan* pl, const float2* in, float2* out, float2* spec_ou
   const int block = 256;
   const int grid = (int)((total + block - 1) / block);
   if (bwd)
-    mix1d_kernel<true><<<grid, block, 0, st>>>(in, out, spec_out, w, pl->col_fwd, pl->col_dc, images, ca, cb,
+    launch_k(mix1d_kernel<true>, dim3(grid), dim3(block), 0, st, in, out, spec_out, w, pl->col_fwd, pl->col_dc, images, ca, cb,
                                                co_layer, pl->m2);
   else
-    mix1d_kernel<false><<<grid, block, 0, st>>>(in, out, spec_out, w, pl->col_dc, pl->col_fwd, images, ca, cb,
+    launch_k(mix1d_kernel<false>, dim3(grid), dim3(block), 0, st, in, out, spec_out, w, pl->col_dc, pl->col_fwd, images, ca, cb,
                                                 co_layer, pl->m2);
 }
 
@@ -623,6 +631,8 @@ void launch_mix1d(const Plan* pl, const float2* in, float2* out, float2* spec_ou
 // ===========================================================================
 __global__ void gw_reduce_kernel(const float2* __restrict__ xs, const float2* __restrict__ gys, float2* gw1,
                                  float2* gw2, int images, int ci, int co, int K, int m1, int m2, int bchunk) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)ci * co * K * m2;
   const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -660,7 +670,7 @@ void launch_gw_reduce(const Plan* pl, const float2* xs, const float2* gys, float
   while (chunks < images && (long)gx * chunks < 4 * 148 && images / (chunks * 2) >= 8) chunks *= 2;
   const int bchunk = ceil_div(images, chunks);
   dim3 grid(gx, ceil_div(images, bchunk));
-  gw_reduce_kernel<<<grid, block, 0, st>>>(xs, gys, gw1, gw2, images, ci, co, pl->K, pl->m1, pl->m2, bchunk);
+  launch_k(gw_reduce_kernel, dim3(grid), dim3(block), 0, st, xs, gys, gw1, gw2, images, ci, co, pl->K, pl->m1, pl->m2, bchunk);
 }
 
 // ===========================================================================
@@ -700,7 +710,8 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
   const float inv_nwq = 1.0f / (float)nwq, inv_ht = 1.0f / (float)HT, inv_hp = 1.0f / (float)hp,
               inv_m2 = 1.0f / (float)m2;
   auto fdiv = [](int n, float inv) { return __float2int_rz(((float)n + 0.5f) * inv); };
-  for (int idx = tid; idx < m2 * nwq; idx += nt) {
+  pdl_launch_dependents();
+  for (int idx = tid; idx < m2 * nwq; idx += nt) {      // constant plan data: staged before the dependency wait
     const int l = fdiv(idx, inv_nwq), q = idx - l * nwq;
     const int w = wc0 + 4 * q;     // wp4 is a multiple of 4: a float4 is inside the table row or fully outside
     float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), sv = cv;
@@ -711,6 +722,7 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
     reinterpret_cast<float4*>(tc)[idx] = cv;
     reinterpret_cast<float4*>(tsn)[idx] = sv;
   }
+  pdl_wait();
   for (int idx = tid; idx < cpad * HT * m2; idx += nt) {
     const int row = fdiv(idx, inv_m2), l = idx - row * m2;
     const int ch = fdiv(row, inv_ht), hh = row - ch * HT;
@@ -898,7 +910,7 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
 template <int MODE, int CG>
 static void launch_winv_t(const WinvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   cudaFuncSetAttribute(winv_kernel<MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  winv_kernel<MODE, CG><<<grid, 256, smem, st>>>(p);
+  launch_k(winv_kernel<MODE, CG>, dim3(grid), dim3(256), smem, st, p);
 }
 
 void launch_winv(const Plan* pl, int mode, const WinvArgs& a, cudaStream_t st) {

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(192, 1) tc_wfwd_kernel(const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(192, 1) tc_wfwd_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // barriers, tensor memory and the (constant) DFT operand are set up; x is the previous kernel's output
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -296,7 +298,7 @@ bool launch_wfwd_tc(const Plan* pl, const float* x, float2* out, int rows, cudaS
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.ntiles < sms ? p.ntiles : sms;
   cudaFuncSetAttribute(tc_wfwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tc_wfwd_kernel<<<grid, 192, smem, st>>>(tmap, p);
+  launch_k(tc_wfwd_kernel, dim3(grid), dim3(192), smem, st, tmap, p);
   return true;
 }
 
