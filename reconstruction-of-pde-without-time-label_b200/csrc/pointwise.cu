@@ -42,15 +42,29 @@ __global__ void __launch_bounds__(256) lift_kernel(const LiftParams p, float* __
   for (int i = threadIdx.x; i < p.width * p.c_in; i += blockDim.x) ws[i] = __ldg(p.w0 + i);
   for (int i = threadIdx.x; i < p.width; i += blockDim.x) bs[i] = __ldg(p.b0 + i);
   __syncthreads();
+  // blockIdx.y = image (block-uniform: the bag / snapshot lookup is scalar work), x = tiles of the padded plane
   const int plane = p.hp * p.wp;
-  const long total = (long)p.images * plane;
-  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const int img = t / plane, q = t - (long)img * plane;
-    const int hh = q / p.wp, ww = q - hh * p.wp;
+  const float inv_wp = 1.0f / (float)p.wp;
+  for (int img = blockIdx.y; img < p.images; img += gridDim.y) {
+  const float* src0 = nullptr;             // bags form: the snapshot's plane
+  if (p.x_cl == nullptr) {
+    const int b = img / p.n_keep, l = img - b * p.n_keep;
+    const int snap = p.idx != nullptr ? __ldg(p.idx + l) : l;
+    src0 = p.bags + ((size_t)b * p.bag_len + snap) * p.h * p.w;
+  }
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < plane; q += gridDim.x * blockDim.x) {
+    const int hh = __float2int_rz(((float)q + 0.5f) * inv_wp), ww = q - hh * p.wp;
     float* dst = z0 + (size_t)img * p.width * plane + q;
     if (hh < p.h && ww < p.w) {
+      const int pix = hh * p.w + ww;
       float in[LIFT_MAX_CIN];
-      lift_fetch(p, img, hh * p.w + ww, in);
+      if (p.x_cl != nullptr) {
+        const float* src = p.x_cl + ((size_t)img * p.h * p.w + pix) * p.c_in;
+        for (int i = 0; i < p.c_in; ++i) in[i] = __ldg(src + i);
+      } else {
+        in[0] = __ldg(src0 + pix);
+        for (int d = 0; d < p.grid_dim; ++d) in[1 + d] = __ldg(p.grid + (size_t)pix * p.grid_dim + d);
+      }
       for (int c = 0; c < p.width; ++c) {
         float acc = bs[c];
         for (int i = 0; i < p.c_in; ++i) acc = fmaf(ws[c * p.c_in + i], in[i], acc);
@@ -59,6 +73,7 @@ __global__ void __launch_bounds__(256) lift_kernel(const LiftParams p, float* __
     } else {
       for (int c = 0; c < p.width; ++c) dst[(size_t)c * plane] = 0.f;
     }
+  }
   }
 }
 
@@ -74,11 +89,13 @@ static LiftParams make_lift_params(const LiftArgs& a) {
 void launch_lift(const LiftArgs& a, float* z0, cudaStream_t st) {
   LaunchScope scope("lift", st, a.width);
   const LiftParams p = make_lift_params(a);
-  const long total = (long)a.images * a.hp * a.wp;
+  const int plane = a.hp * a.wp;
   const int block = 256;
-  const int grid = (int)((total + block - 1) / block);
+  int gx = (plane + block - 1) / block;
+  // 1-D nets have tiny planes and many images: fold several images' worth of blocks only through grid.y
+  dim3 grid(gx, a.images < 65535 ? a.images : 65535);
   const size_t smem = (size_t)(a.width * a.c_in + a.width) * sizeof(float);
-  launch_k(lift_kernel, dim3(grid), dim3(block), smem, st, p, z0);
+  launch_k(lift_kernel, grid, dim3(block), smem, st, p, z0);
 }
 
 // lift backward: g_w0[c][i] += sum gz0[c] * in_i, g_b0[c] += sum gz0[c], gx_cl[.., i] = sum_c W0[c][i] gz0[c]

@@ -465,6 +465,137 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// 2-D middle stage, streaming variant for the many-image regime (the per-snapshot net).  Persistent
+// blocks; a block owns whole images: the W-transformed image [ca][hp][m2] is ONE contiguous span of HBM,
+// brought in by a single bulk async copy into a double-buffered shared tile (the copy of image i+1 is
+// in flight while image i is transformed); the two DFT tables and nothing else are staged once per
+// block.  Phases as in core2d_kernel.
+// ---------------------------------------------------------------------------
+template <bool BWD, int G1, int G3>
+__global__ void __launch_bounds__(1024) core2d_stream_kernel(const CoreParams p, int images) {
+  extern __shared__ __align__(16) float smem[];
+  const int K = p.K, hp = p.hp, m2 = p.m2, Pa = p.ca * m2, Pb = p.cb * m2;
+  const int in_elems = p.ca * hp * m2;                      // float2 per image (even: m2*hp*ca*... padded below)
+  const int in_pad = (in_elems + 1) & ~1;
+  float2* in0 = reinterpret_cast<float2*>(smem);
+  float2* in1 = in0 + in_pad;
+  float2* bufX = in1 + in_pad;                              // [K][Pa]
+  float2* bufY = bufX + ((K * Pa + 1) & ~1);                // [K][Pb]
+  float2* s_hk = bufY + ((K * Pb + 1) & ~1);                // [hp][Kp]
+  float2* s_kh = s_hk + hp * p.Kp;                          // [K][hp8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kh + K * p.hp8);   // [0],[1]: image stages, [2]: tables
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t img_bytes = (uint32_t)in_elems * 8u;
+
+  pdl_launch_dependents();
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_init_fence();
+    const uint32_t b1 = (uint32_t)(hp * p.Kp) * 8u, b2 = (uint32_t)(K * p.hp8) * 8u;
+    mbar_expect_tx(&bars[2], b1 + b2);
+    bulk_g2s(s_hk, p.t_hk, b1, &bars[2]);
+    bulk_g2s(s_kh, p.t_kh, b2, &bars[2]);
+  }
+  pdl_wait();
+  __syncthreads();
+  auto issue = [&](int img, int stage) {     // thread 0 only
+    fence_proxy_async();
+    mbar_expect_tx(&bars[stage], img_bytes);
+    bulk_g2s(stage ? in1 : in0, p.in + (size_t)img * in_elems, img_bytes, &bars[stage]);
+  };
+  if (tid == 0 && (int)blockIdx.x < images) issue(blockIdx.x, 0);
+  mbar_wait(&bars[2], 0);
+
+  int it = 0;
+  for (int b = blockIdx.x; b < images; b += gridDim.x, ++it) {
+    const int stage = it & 1;
+    if (tid == 0 && b + (int)gridDim.x < images) issue(b + gridDim.x, stage ^ 1);
+    mbar_wait(&bars[stage], (it >> 1) & 1);
+    const float2* xin = stage ? in1 : in0;                  // [a][h][l]
+
+    // phase 1: X[k][(a,l)] = pre[l] * sum_h x[a][h][l] * e^{-i phi_kh}
+    const int nkg = (K + G1 - 1) / G1;
+    for (int idx = tid; idx < Pa * nkg; idx += nt) {
+      const int pa = idx % Pa, kg = idx / Pa;
+      const int a = pa / m2, l = pa - a * m2;
+      float re[G1], im[G1];
+#pragma unroll
+      for (int j = 0; j < G1; ++j) re[j] = im[j] = 0.f;
+      const float2* trow = s_hk + kg * G1;
+      const float2* xcol = xin + (size_t)a * hp * m2 + l;
+#pragma unroll 4
+      for (int h = 0; h < hp; ++h) cacc_rows<G1>(xcol[h * m2], trow + (size_t)h * p.Kp, re, im, true);
+      const float sc = __ldg(p.pre + l);
+#pragma unroll
+      for (int j = 0; j < G1; ++j) {
+        const int k = kg * G1 + j;
+        if (k < K) {
+          const float2 v = make_float2(re[j] * sc, im[j] * sc);
+          bufX[k * Pa + pa] = v;
+          if (p.spec_out != nullptr) p.spec_out[((size_t)(b * p.ca + a) * K + k) * m2 + l] = v;
+        }
+      }
+    }
+    __syncthreads();
+
+    // phase 2: per-mode channel mix
+    for (int idx = tid; idx < K * Pb; idx += nt) {
+      const int l = idx % m2, k = (idx / m2) % K, bc = idx / (m2 * K);
+      const bool lo = k < p.m1;
+      const float2* wsel = lo ? p.w1 : p.w2;
+      const int kk = lo ? k : k - p.m1;
+      const size_t mode_off = (size_t)kk * m2 + l;
+      const size_t cstride = (size_t)p.m1 * m2;
+      float yr = 0.f, yi = 0.f;
+#pragma unroll 4
+      for (int a = 0; a < p.ca; ++a) {
+        const float2 x = bufX[k * Pa + a * m2 + l];
+        if (!BWD) {
+          const float2 w = __ldg(wsel + (size_t)(a * p.co_layer + bc) * cstride + mode_off);
+          yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
+          yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
+        } else {
+          const float2 w = __ldg(wsel + (size_t)(bc * p.co_layer + a) * cstride + mode_off);
+          yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
+          yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
+        }
+      }
+      bufY[k * Pb + bc * m2 + l] = make_float2(yr, yi);
+    }
+    __syncthreads();
+
+    // phase 3: Z[(bc)][h][l] = post[l] * sum_k y[k][(bc,l)] * e^{+i phi_kh}
+    const int nhg = (hp + G3 - 1) / G3;
+    for (int idx = tid; idx < Pb * nhg; idx += nt) {
+      const int pb = idx % Pb, hg = idx / Pb;
+      float re[G3], im[G3];
+#pragma unroll
+      for (int j = 0; j < G3; ++j) re[j] = im[j] = 0.f;
+      const float2* trow = s_kh + hg * G3;
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) cacc_rows<G3>(bufY[k * Pb + pb], trow + (size_t)k * p.hp8, re, im, false);
+      const int bc = pb / m2, l = pb - bc * m2;
+      const float sc = __ldg(p.post + l);
+#pragma unroll
+      for (int j = 0; j < G3; ++j) {
+        const int h = hg * G3 + j;
+        if (h < hp) p.out[((size_t)(b * p.cb + bc) * hp + h) * m2 + l] = make_float2(re[j] * sc, im[j] * sc);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();          // bufX / bufY and this image stage are free again
+  }
+}
+
+template <bool BWD, int G1, int G3>
+static void launch_core2d_stream_t(const CoreParams& p, int images, int grid, int threads, size_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(core2d_stream_kernel<BWD, G1, G3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  launch_k(core2d_stream_kernel<BWD, G1, G3>, dim3(grid), dim3(threads), smem, st, p, images);
+}
+
 template <bool BWD, int G1, int G3>
 static void launch_core2d_t(const CoreParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
   cudaFuncSetAttribute(core2d_kernel<BWD, G1, G3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -522,6 +653,28 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
   p.cb = bwd ? ci_layer : co_layer;
   p.co_layer = co_layer;
   p.hp = pl->hp; p.hp8 = pl->hp8; p.m1 = pl->m1; p.m2 = pl->m2; p.K = pl->K; p.Kp = pl->Kp;
+  // many images: persistent streaming kernel, whole images per block (G1 = 2 kept rows, G3 = 8 rows per item)
+  {
+    const size_t in_pad = ((size_t)p.ca * pl->hp * pl->m2 + 1) & ~(size_t)1;
+    const size_t nX = ((size_t)pl->K * p.ca * pl->m2 + 1) & ~(size_t)1, nY = ((size_t)pl->K * p.cb * pl->m2 + 1) & ~(size_t)1;
+    const size_t smem_s = (2 * in_pad + nX + nY + (size_t)pl->hp * pl->Kp + (size_t)pl->K * pl->hp8) * sizeof(float2) + 32;
+    const bool aligned = (((size_t)p.ca * pl->hp * pl->m2 * 8) & 15) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    if (images >= 148 && smem_s <= 110 * 1024 && aligned) {
+      p.TL = pl->m2;
+      const int Pa_s = p.ca * pl->m2, Pb_s = p.cb * pl->m2;
+      const int items1 = Pa_s * ceil_div(pl->K, 2), items3 = Pb_s * ceil_div(pl->hp, 8);
+      int threads = items1 > items3 ? items1 : items3;
+      threads = ceil_div(threads, ceil_div(threads, 1024));
+      threads = (threads + 31) & ~31;
+      if (threads < 128) threads = 128;
+      const int per_sm = (int)((220 * 1024) / (smem_s + 1024)) < 2048 / threads ? (int)((220 * 1024) / (smem_s + 1024)) : 2048 / threads;
+      const int cap = 148 * (per_sm < 1 ? 1 : per_sm);
+      const int grid_s = images < cap ? images : cap;
+      if (bwd) launch_core2d_stream_t<true, 2, 8>(p, images, grid_s, threads, smem_s, st);
+      else launch_core2d_stream_t<false, 2, 8>(p, images, grid_s, threads, smem_s, st);
+      return;
+    }
+  }
   // TL mode columns per block: the widest column tile that still leaves >= 2 blocks per SM and fits
   // shared memory (wide tiles read the W-transformed image with full 32-byte sectors)
   auto smem_of = [&](int t) {
