@@ -218,6 +218,8 @@ def run_b200(args, wl, rank, world, local_rank):
     if args.prec == "tf32":
         ops.set_precision(model, ops.PREC_TF32)     # tcgen05 tensor-core kernels where a stage has one
     trainer = FlatTrainer(model, lr=wl["lr"])
+    if args.no_split_backward:
+        trainer.split_backward = False
     grid = make_grid(wl).to(dev)
     batch = args.batch_per_gpu or wl["batch"]
     use_graphs = not args.no_graphs
@@ -355,7 +357,10 @@ def run_b200(args, wl, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.prec == "fp32" else "tf32", "data": "synthetic",
         "config": {"workload": args.workload, "model": f"{wl['cls']}{wl['args']}", "batch_per_gpu": batch,
-                   "global_batch": batch * world, "bag": wl["bag"], "bag_subsample": "U[50,99] per step (reference)",
+                   "global_batch": batch * world, "bag": wl["bag"],
+                   "allreduce": ("none (1 GPU)" if world == 1 else
+                                 ("heads' region overlapped with the encoder backward + encoder region at the end"
+                                  if trainer.split_backward else "one flat all-reduce after backward")), "bag_subsample": "U[50,99] per step (reference)",
                    "grid": wl["n"], "parallelism": f"dp{world}", "precision_mode": "fp32 (1e-5 parity mode)" if args.prec == "fp32" else
                    "tf32: tcgen05 tensor-core W-forward DFT GEMM, fp32 accumulate (bound 2e-3 outputs / 1e-2 grads)",
                    "cuda_graphs": f"{n_graphs} graphs (one per bag size), captured before timing" if use_graphs else "off",
@@ -388,6 +393,8 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=0)
     ap.add_argument("--pool", type=int, default=8, help="distinct batches rotated through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-split-backward", action="store_true",
+                    help="one all-reduce after backward instead of overlapping the heads' all-reduce with the encoder backward")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--prec", default="fp32", choices=["fp32", "tf32"],
                     help="fp32 = CUDA-core FFMA DFT GEMMs (1e-5 parity mode, the headline); tf32 = tcgen05 mode (2e-3)")

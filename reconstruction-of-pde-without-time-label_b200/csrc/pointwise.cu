@@ -19,61 +19,73 @@ struct LiftParams {
   int images, c_in, width, h, w, hp, wp;
 };
 
-__device__ __forceinline__ void lift_fetch(const LiftParams& p, int img, int pix, float* in) {
-  if (p.x_cl != nullptr) {
-    const float* src = p.x_cl + ((size_t)img * p.h * p.w + pix) * p.c_in;
-    for (int i = 0; i < p.c_in; ++i) in[i] = __ldg(src + i);
-  } else {
-    const int b = img / p.n_keep, l = img - b * p.n_keep;
-    const int snap = p.idx != nullptr ? __ldg(p.idx + l) : l;
-    in[0] = __ldg(p.bags + ((size_t)b * p.bag_len + snap) * p.h * p.w + pix);
-    for (int d = 0; d < p.grid_dim; ++d) in[1 + d] = __ldg(p.grid + (size_t)pix * p.grid_dim + d);
-  }
-}
 
-constexpr int LIFT_MAX_CIN = 32;
-
+template <int CP, int PX>   // CP = width rounded up to 4 (accumulators live in registers), PX = pixels per thread
 __global__ void __launch_bounds__(256) lift_kernel(const LiftParams p, float* __restrict__ z0) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float smem[];
-  float* ws = smem;                        // [width][c_in]
-  float* bs = smem + p.width * p.c_in;     // [width]
-  for (int i = threadIdx.x; i < p.width * p.c_in; i += blockDim.x) ws[i] = __ldg(p.w0 + i);
-  for (int i = threadIdx.x; i < p.width; i += blockDim.x) bs[i] = __ldg(p.b0 + i);
+  float* ws = smem;                        // [c_in][CP]  (transposed: one input feature's column of W0)
+  float* bs = smem + p.c_in * CP;          // [CP]
+  for (int i = threadIdx.x; i < p.c_in * CP; i += blockDim.x) {
+    const int ci = i / CP, c = i - ci * CP;
+    ws[i] = c < p.width ? __ldg(p.w0 + c * p.c_in + ci) : 0.f;
+  }
+  for (int i = threadIdx.x; i < CP; i += blockDim.x) bs[i] = i < p.width ? __ldg(p.b0 + i) : 0.f;
   __syncthreads();
   // blockIdx.y = image (block-uniform: the bag / snapshot lookup is scalar work), x = tiles of the padded plane
   const int plane = p.hp * p.wp;
   const float inv_wp = 1.0f / (float)p.wp;
   for (int img = blockIdx.y; img < p.images; img += gridDim.y) {
-  const float* src0 = nullptr;             // bags form: the snapshot's plane
-  if (p.x_cl == nullptr) {
-    const int b = img / p.n_keep, l = img - b * p.n_keep;
-    const int snap = p.idx != nullptr ? __ldg(p.idx + l) : l;
-    src0 = p.bags + ((size_t)b * p.bag_len + snap) * p.h * p.w;
-  }
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < plane; q += gridDim.x * blockDim.x) {
-    const int hh = __float2int_rz(((float)q + 0.5f) * inv_wp), ww = q - hh * p.wp;
-    float* dst = z0 + (size_t)img * p.width * plane + q;
-    if (hh < p.h && ww < p.w) {
-      const int pix = hh * p.w + ww;
-      float in[LIFT_MAX_CIN];
-      if (p.x_cl != nullptr) {
-        const float* src = p.x_cl + ((size_t)img * p.h * p.w + pix) * p.c_in;
-        for (int i = 0; i < p.c_in; ++i) in[i] = __ldg(src + i);
-      } else {
-        in[0] = __ldg(src0 + pix);
-        for (int d = 0; d < p.grid_dim; ++d) in[1 + d] = __ldg(p.grid + (size_t)pix * p.grid_dim + d);
-      }
-      for (int c = 0; c < p.width; ++c) {
-        float acc = bs[c];
-        for (int i = 0; i < p.c_in; ++i) acc = fmaf(ws[c * p.c_in + i], in[i], acc);
-        dst[(size_t)c * plane] = acc;
-      }
-    } else {
-      for (int c = 0; c < p.width; ++c) dst[(size_t)c * plane] = 0.f;
+    const float* src0 = nullptr;           // bags form: the snapshot's plane
+    if (p.x_cl == nullptr) {
+      const int b = img / p.n_keep, l = img - b * p.n_keep;
+      const int snap = p.idx != nullptr ? __ldg(p.idx + l) : l;
+      src0 = p.bags + ((size_t)b * p.bag_len + snap) * p.h * p.w;
     }
-  }
+    for (int q0 = blockIdx.x * blockDim.x * PX + threadIdx.x; q0 < plane; q0 += gridDim.x * blockDim.x * PX) {
+      float acc[PX][CP];
+      int pix[PX];
+#pragma unroll
+      for (int u = 0; u < PX; ++u) {
+        const int q = q0 + u * blockDim.x;
+        const int hh = __float2int_rz(((float)q + 0.5f) * inv_wp), ww = q - hh * p.wp;
+        pix[u] = (q < plane && hh < p.h && ww < p.w) ? hh * p.w + ww : -1;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) acc[u][c] = pix[u] >= 0 ? bs[c] : 0.f;
+      }
+      for (int i = 0; i < p.c_in; ++i) {
+        float v[PX];
+#pragma unroll
+        for (int u = 0; u < PX; ++u) {
+          v[u] = 0.f;
+          if (pix[u] >= 0) {
+            if (p.x_cl != nullptr) v[u] = __ldg(p.x_cl + ((size_t)img * p.h * p.w + pix[u]) * p.c_in + i);
+            else v[u] = i == 0 ? __ldg(src0 + pix[u]) : __ldg(p.grid + (size_t)pix[u] * p.grid_dim + (i - 1));
+          }
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < CP; c4 += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(ws + i * CP + c4);
+#pragma unroll
+          for (int u = 0; u < PX; ++u) {
+            acc[u][c4] = fmaf(w.x, v[u], acc[u][c4]);
+            acc[u][c4 + 1] = fmaf(w.y, v[u], acc[u][c4 + 1]);
+            acc[u][c4 + 2] = fmaf(w.z, v[u], acc[u][c4 + 2]);
+            acc[u][c4 + 3] = fmaf(w.w, v[u], acc[u][c4 + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PX; ++u) {
+        const int q = q0 + u * blockDim.x;
+        if (q >= plane) continue;
+        float* dst = z0 + (size_t)img * p.width * plane + q;
+#pragma unroll
+        for (int c = 0; c < CP; ++c)
+          if (c < p.width) dst[(size_t)c * plane] = acc[u][c];
+      }
+    }
   }
 }
 
@@ -91,11 +103,23 @@ void launch_lift(const LiftArgs& a, float* z0, cudaStream_t st) {
   const LiftParams p = make_lift_params(a);
   const int plane = a.hp * a.wp;
   const int block = 256;
-  int gx = (plane + block - 1) / block;
+  int gx = (plane + 4 * block - 1) / (4 * block);
   // 1-D nets have tiny planes and many images: fold several images' worth of blocks only through grid.y
   dim3 grid(gx, a.images < 65535 ? a.images : 65535);
-  const size_t smem = (size_t)(a.width * a.c_in + a.width) * sizeof(float);
-  launch_k(lift_kernel, grid, dim3(block), smem, st, p, z0);
+  const int cp = (a.width + 3) & ~3;
+  const size_t smem = (size_t)(a.c_in * cp + cp) * sizeof(float);
+#define BDN_LIFT(CPV, PXV) launch_k(lift_kernel<CPV, PXV>, grid, dim3(block), smem, st, p, z0)
+  switch (cp) {
+    case 4: BDN_LIFT(4, 4); break;
+    case 8: BDN_LIFT(8, 4); break;
+    case 12: BDN_LIFT(12, 4); break;
+    case 16: BDN_LIFT(16, 4); break;
+    case 20: BDN_LIFT(20, 4); break;
+    case 24: BDN_LIFT(24, 4); break;
+    case 28: BDN_LIFT(28, 4); break;
+    default: BDN_LIFT(32, 4); break;
+  }
+#undef BDN_LIFT
 }
 
 // lift backward: g_w0[c][i] += sum gz0[c] * in_i, g_b0[c] += sum gz0[c], gx_cl[.., i] = sum_c W0[c][i] gz0[c]
@@ -116,6 +140,8 @@ __global__ void __launch_bounds__(256) lift_bwd_kernel(const LiftParams p, const
   float* ws = xs + CI * PT;          // [C][CI]
   float* acc = ws + ((C * CI + 3) & ~3);   // [C*CI + C] (+ pad)
   long* s_goff = reinterpret_cast<long*>(acc + ((C * CI + C + 3) & ~3) + 4);   // [TP] offset of the pixel in a gz plane, -1 = dead
+  int* s_img = reinterpret_cast<int*>(s_goff + TP);   // [TP] image of the pixel
+  int* s_pix = s_img + TP;                            // [TP] pixel index inside the unpadded image
   const int npair = C * CI + C;
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < C * CI; i += nt) ws[i] = __ldg(p.w0 + i);
@@ -132,12 +158,15 @@ __global__ void __launch_bounds__(256) lift_bwd_kernel(const LiftParams p, const
     if (tid < TP) {
       const long t = t0 + tid;
       long off = -1;
+      int img = 0, pix = 0;
       if (t < total) {
-        const int img = t / hw, pix = t - (long)img * hw;
+        img = t / hw; pix = t - (long)img * hw;
         const int hh = pix / p.w, ww = pix - hh * p.w;
         off = (long)img * C * plane + hh * p.wp + ww;
       }
       s_goff[tid] = off;
+      s_img[tid] = img;
+      s_pix[tid] = pix;
     }
     __syncthreads();
     for (int idx = tid; idx < C * TP; idx += nt) {
@@ -153,7 +182,7 @@ __global__ void __launch_bounds__(256) lift_bwd_kernel(const LiftParams p, const
         if (p.x_cl != nullptr) {
           v = __ldg(p.x_cl + (size_t)t * CI + i);
         } else {
-          const int img = t / hw, pix = t - (long)img * hw;
+          const int img = s_img[tp], pix = s_pix[tp];
           if (i == 0) {
             const int b = img / p.n_keep, l = img - b * p.n_keep;
             const int snap = p.idx != nullptr ? __ldg(p.idx + l) : l;
@@ -222,7 +251,8 @@ void launch_lift_bwd(const LiftArgs& a, const float* gz0, float* g_w0, float* g_
   while (ceil_div(tiles, tpb) > 4 * 148) ++tpb;
   const int grid = ceil_div(tiles, tpb);
   const size_t smem = (size_t)((a.width + a.c_in) * (tp + 4) + ((a.width * a.c_in + 3) & ~3) +
-                               ((a.width * a.c_in + a.width + 3) & ~3) + 4) * sizeof(float) + (size_t)tp * sizeof(long) + 16;
+                               ((a.width * a.c_in + a.width + 3) & ~3) + 4) * sizeof(float) +
+                      (size_t)tp * (sizeof(long) + 2 * sizeof(int)) + 16;
   if (few) {
     cudaFuncSetAttribute(lift_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     launch_k(lift_bwd_kernel<64>, dim3(grid), dim3(256), smem, st, p, gz0, g_w0, g_b0, gx_cl, tpb);
@@ -627,15 +657,25 @@ __global__ void pool_lift_kernel(const float* __restrict__ s, const float* __res
                                  float* __restrict__ out, int n_bags, int n_keep, int npix, int gd, int width) {
   pdl_launch_dependents();
   pdl_wait();
+  // 8 lanes share one pixel and split the bag; 4 pixels per warp (each lane group reads 4 consecutive pixels' worth
+  // of 32-byte sectors together)
   const long total = (long)n_bags * npix;
-  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int b = t / npix, pix = t - (long)b * npix;
-  const float* sp = s + (size_t)b * n_keep * npix + pix;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane >> 2, pl = lane & 3;          // sub: bag slice 0..7, pl: pixel within the warp's group of 4
+  const long t = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + pl;
   float acc = 0.f;
-  for (int l = 0; l < n_keep; ++l) acc += __ldg(sp + (size_t)l * npix);
+  int b = 0, pix = 0;
+  if (t < total) {
+    b = t / npix; pix = t - (long)b * npix;
+    const float* sp = s + (size_t)b * n_keep * npix + pix;
+    for (int l = sub; l < n_keep; l += 8) acc += __ldg(sp + (size_t)l * npix);
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+  if (t >= total) return;
   const float mean = acc / (float)n_keep;
-  for (int j = 0; j < width; ++j) {
+  for (int j = sub; j < width; j += 8) {
     float v = __ldg(b0 + j);
     for (int d = 0; d < gd; ++d) v = fmaf(__ldg(w0 + j * (gd + 1) + d), __ldg(grid + (size_t)pix * gd + d), v);
     out[(size_t)t * width + j] = fmaf(__ldg(w0 + j * (gd + 1) + gd), mean, v);
@@ -646,9 +686,10 @@ void launch_pool_lift(const float* s, const float* grid, const float* w0, const 
                       int n_keep, int npix, int grid_dim, int width, cudaStream_t st) {
   LaunchScope scope("pool_lift", st);
   const long total = (long)n_bags * npix;
-  const int block = 64;
-  launch_k(pool_lift_kernel, dim3((int)((total + block - 1) / block)), dim3(block), 0, st, s, grid, w0, b0, out, n_bags, n_keep, npix,
-                                                                         grid_dim, width);
+  const int block = 128;                              // 4 warps x 4 pixels
+  const long pix_per_block = (block / 32) * 4;
+  launch_k(pool_lift_kernel, dim3((unsigned)((total + pix_per_block - 1) / pix_per_block)), dim3(block), 0, st, s, grid, w0,
+           b0, out, n_bags, n_keep, npix, grid_dim, width);
 }
 
 __global__ void pool_lift_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w0,

@@ -58,6 +58,12 @@ class FlatTrainer:
         self._graphs = {}
         self._graph_pool = None
         self.replayed_launches = 0
+        # Backward split (NIO-FNO): the heads' gradients (94 % of the buffer) are complete before the
+        # per-snapshot net starts back-propagating, so their all-reduce runs on a side stream under that
+        # backward; only the small FNO_input region is reduced at the end.  On by default when world > 1.
+        self.split_backward = self.world > 1 and hasattr(model, "FNO_input") and hasattr(model, "_expose_lifted")
+        self._comm_stream = None
+        self._late_span = None
 
         named = live_parameters(model)
         if not named:
@@ -108,6 +114,8 @@ class FlatTrainer:
                 self.n_live += p.numel() * (2 if p.is_complex() else 1)
             if mod is not None:
                 mod._grad_sink = self.flat_grad[base: base + n]
+                if mod is getattr(model, "FNO_input", None):
+                    self._late_span = (base, base + n)
 
     # -- pieces of a step ----------------------------------------------------------------
     def zero_grad(self):
@@ -117,6 +125,30 @@ class FlatTrainer:
         """Sum over ranks in one collective; the 1/world of DDP's mean is folded into the Adam kernel."""
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _early_spans(self):
+        a, b = self._late_span
+        return [(lo, hi) for lo, hi in ((0, a), (b, self.numel)) if hi > lo]
+
+    def reduce_early(self):
+        """All-reduce everything but the FNO_input region on the communication stream (non-blocking for the
+        compute stream)."""
+        if self.world == 1:
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        self._comm_stream.wait_stream(main)
+        with torch.cuda.stream(self._comm_stream):
+            for lo, hi in self._early_spans():
+                dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+
+    def reduce_late(self):
+        if self.world == 1:
+            return
+        a, b = self._late_span
+        dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.group)
+        torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
 
     def optimizer_step(self):
         self.step_count += 1
@@ -176,13 +208,30 @@ class FlatTrainer:
         ent["target"].copy_(target)
         torch.cuda.synchronize(dev)
 
-        def body():
+        split = self.split_backward and self._late_span is not None
+
+        def body_a():
             self.flat_grad.zero_()
+            self.model._expose_lifted = split
             pred = self.model(ent["x"], ent["grid"], idx=ent["idx"]) if ent["idx"] is not None else \
                 self.model(ent["x"], ent["grid"])
             loss = self.loss_fn(pred, ent["target"])
-            loss.backward()
-            return loss.detach()
+            if not split:
+                loss.backward()
+                return loss.detach(), None, None
+            lifted = self.model._lifted
+            self.model._lifted = None
+            (g_lifted,) = torch.autograd.grad(loss, [lifted])     # runs the heads' backward (gradients -> flat buffer)
+            return loss.detach(), lifted, g_lifted
+
+        def body_b(lifted, g_lifted):
+            torch.autograd.backward([lifted], [g_lifted])          # the per-snapshot net's backward
+
+        def body():
+            loss, lifted, g_lifted = body_a()
+            if split:
+                body_b(lifted, g_lifted)
+            return loss
 
         # warm-up on a side stream (plans, lazy module loads, autograd buffers), then capture
         side = torch.cuda.Stream(device=dev)
@@ -199,9 +248,18 @@ class FlatTrainer:
             self._graph_pool = torch.cuda.graph_pool_handle()
         graph = torch.cuda.CUDAGraph()
         launches0 = ops.kernel_launches()
-        with torch.cuda.graph(graph, pool=self._graph_pool):
-            ent["loss"] = body()
-        ent["launches"] = ops.kernel_launches() - launches0      # kernels of this library inside the graph
+        ent["graph_b"] = None
+        if not split:
+            with torch.cuda.graph(graph, pool=self._graph_pool):
+                ent["loss"] = body()
+        else:
+            with torch.cuda.graph(graph, pool=self._graph_pool):
+                ent["loss"], lifted, g_lifted = body_a()
+            graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_b, pool=self._graph_pool):
+                body_b(lifted, g_lifted)
+            ent["graph_b"] = graph_b
+        ent["launches"] = ops.kernel_launches() - launches0      # kernels of this library inside the graph(s)
         ent["graph"] = graph
         self._graphs[key] = ent
         return ent
@@ -216,8 +274,13 @@ class FlatTrainer:
             # pageable source: the runtime stages it before returning, so the host array may be reused
             ent["idx"].copy_(torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int32)))
         ent["graph"].replay()
+        if ent["graph_b"] is not None:
+            self.reduce_early()            # heads' gradients travel while the per-snapshot net back-propagates
+            ent["graph_b"].replay()
+            self.reduce_late()
+        else:
+            self.reduce_gradients()
         self.replayed_launches += ent["launches"]
-        self.reduce_gradients()
         self.optimizer_step()
         return ent["loss"]
 

@@ -79,6 +79,8 @@ class _BagModel(nn.Module):
 
 class _NioFnoMixin(_BagModel):
     """FNO_input on every snapshot -> mean over the bag folded into the detached fc0 -> FNO heads."""
+    _expose_lifted = False
+    _lifted = None
 
     def forward(self, x, grid, idx=None):
         """``idx`` (optional int32 device tensor): the kept snapshots, when the caller has already drawn
@@ -87,6 +89,10 @@ class _NioFnoMixin(_BagModel):
         if idx is None:
             idx = _idx_tensor(draw_bag(x.shape[1], self.training), x.device)
         lifted = self.FNO_input.encode_bags(x, grid, idx=idx, pool=(self.fc0.weight.data, self.fc0.bias.data))
+        if self._expose_lifted:
+            # the data-parallel trainer splits backward at this tensor: once the heads' gradients are complete
+            # their all-reduce runs while the per-snapshot net is still back-propagating
+            self._lifted = lifted
         return self._heads(lifted)
 
 
