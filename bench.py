@@ -45,6 +45,27 @@ WORKLOADS = {
 }
 METRIC = "nio_fno_train_samples_per_sec"
 
+# stdout carries exactly ONE line (the JSON result): libraries that write to fd 1 (NCCL prints its version
+# banner there) are sent to stderr for the life of the process, and emit() writes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
 
 def make_grid(wl):
     if wl["ndim"] == 2:
@@ -195,7 +216,7 @@ def run_reference(args, wl, rank, world):
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -380,7 +401,7 @@ def run_b200(args, wl, rank, world, local_rank):
         "kernel_time_us_per_step": total_ms * 1e3 / prof_steps,
         "final_loss": losses[-1] if losses else None,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -400,6 +421,7 @@ def main():
                     help="fp32 = CUDA-core FFMA DFT GEMMs (1e-5 parity mode, the headline); tf32 = tcgen05 mode (2e-3)")
     ap.add_argument("--top", type=int, default=8, help="how many kernels the top_kernels table lists")
     args = ap.parse_args()
+    _protect_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
 
