@@ -46,7 +46,12 @@ typedef enum BdnStatus {
 /* Arithmetic of the DFT GEMMs.  FP32 = CUDA-core FFMA (the 1e-5 parity mode);
  * TF32 = tcgen05 tensor cores with TF32 operands, fp32 accumulation in TMEM
  * (bound stated in DESIGN.md).  */
-typedef enum BdnPrecision { BDN_PREC_FP32 = 0, BDN_PREC_TF32 = 1 } BdnPrecision;
+typedef enum BdnPrecision {
+  BDN_PREC_FP32 = 0,     /* CUDA-core FFMA everywhere                                             */
+  BDN_PREC_TF32 = 1,     /* tcgen05 TF32 where a stage has a tensor-core kernel (bound 2e-3)      */
+  BDN_PREC_TF32X3 = 2    /* tcgen05 with operands split into TF32 high + low parts, 3 MMAs per K
+                            step: fp32-level accuracy (meets the 1e-5 bound)                      */
+} BdnPrecision;
 
 /* ---------------------------------------------------------------------------
  * Shape of one spectral convolution.

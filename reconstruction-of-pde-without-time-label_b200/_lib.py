@@ -10,7 +10,7 @@ import os
 import threading
 
 MAX_LAYERS = 8
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libblindno_b200.so")

@@ -426,7 +426,8 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
   if (s->images == 0) return BDN_OK;
   if (!p || !out || !ws) return set_error(BDN_ERR_INVALID, "null pointer argument");
   if ((rc = check_lift_input(s, in)) != BDN_OK) return rc;
-  if (s->prec != BDN_PREC_FP32 && s->prec != BDN_PREC_TF32) return set_error(BDN_ERR_INVALID, "bad precision");
+  if (s->prec != BDN_PREC_FP32 && s->prec != BDN_PREC_TF32 && s->prec != BDN_PREC_TF32X3)
+    return set_error(BDN_ERR_INVALID, "bad precision");
   const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
   if (!pl) return BDN_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;

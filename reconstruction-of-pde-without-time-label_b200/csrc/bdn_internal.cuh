@@ -79,8 +79,9 @@ namespace bdn {
 int tc_n_pad(int m2);
 int tc_kch(int wp);
 void tc_build_b_image(int wp, int m2, std::vector<float>& img);     // host image of the swizzled DFT operand
-bool tc_wfwd_supported(const Plan* pl, const float* x);
-bool launch_wfwd_tc(const Plan* pl, const float* x, float2* out, int rows, cudaStream_t st);
+bool tc_wfwd_supported(const Plan* pl, const float* x, bool split);
+// act: exact GELU on load; split: 3xTF32 (hi/lo operands, fp32-level accuracy) instead of plain TF32
+bool launch_wfwd_tc(const Plan* pl, const float* x, float2* out, int rows, int act, bool split, cudaStream_t st);
 
 enum WinvMode { WINV_PLAIN = 0, WINV_LAYER_FWD = 1, WINV_LAYER_BWD = 2 };
 struct WinvArgs {

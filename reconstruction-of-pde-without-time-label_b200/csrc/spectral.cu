@@ -244,7 +244,12 @@ __global__ void __launch_bounds__(256) wfwd_pipe_kernel(const WfwdParams p) {
 }
 
 void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st, int prec) {
-  if (prec == 1 && !act && rows >= 128 && tc_wfwd_supported(pl, x) && launch_wfwd_tc(pl, x, out, rows, st)) return;
+  // prec 1 = TF32 tensor cores (2e-3 mode); prec 2 = 3xTF32 tensor cores (operands split into TF32 high and
+  // low parts, three MMAs per K step: fp32-level accuracy).  Either falls back to the FFMA kernel below when
+  // the shape does not fit the tensor-core kernel's shared memory budget.
+  if ((prec == 1 || prec == 2) && rows >= 128 && tc_wfwd_supported(pl, x, prec == 2) &&
+      launch_wfwd_tc(pl, x, out, rows, act, prec == 2, st))
+    return;
   LaunchScope scope(act ? "wfwd_gelu" : "wfwd", st, pl->m2);
   const int m2 = pl->m2, wp = pl->wp;
   if ((wp & 3) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) {   // bulk copies need 16-byte rows

@@ -22,6 +22,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -109,7 +110,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 struct TcWfwdParams {
   float* out;             // [rows][nreal]
   const float* b_image;   // [kch][n_pad][32] fp32, already in the 128-byte-swizzled smem image
+                          // (split mode: the TF32-truncated high part, followed by the low part)
   int rows, nreal, n_pad, kch, ntiles;
+  int act;                // exact GELU applied to the tile in shared memory before the MMAs
+  int split;              // 3xTF32: x = hi + lo, B = hi + lo, D = lo*hi + hi*lo + hi*hi (fp32-level accuracy)
   uint32_t tmem_cols;     // power of two >= 2 * n_pad
 };
 
@@ -118,27 +122,31 @@ __host__ __device__ inline uint32_t tc_idesc(int n_pad) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(192, 1) tc_wfwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcWfwdParams p) {
+__global__ void __launch_bounds__(320, 1) tc_wfwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcWfwdParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve: [A stages][B image][barriers][tmem slot]
+  // carve: [A stages (hi | lo)][B image (hi | lo)][barriers][tmem slot]
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int a_stage_bytes = p.kch * TC_ATILE;
+  const int a_tile_bytes = p.kch * TC_ATILE;                   // one copy of the x tile
+  const int a_stage_bytes = a_tile_bytes * (p.split ? 2 : 1);  // split: low parts behind the high parts
   unsigned char* a_smem = base;
   unsigned char* b_smem = a_smem + TC_STAGES * a_stage_bytes;               // multiple of 1024
-  const int b_bytes = p.kch * p.n_pad * 128;
+  const int b_part_bytes = p.kch * p.n_pad * 128;
+  const int b_bytes = b_part_bytes * (p.split ? 2 : 1);
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + ((b_bytes + 1023) & ~1023));
   uint64_t* full = bars;                 // [TC_STAGES]  TMA -> MMA
   uint64_t* empty = bars + TC_STAGES;    // [TC_STAGES]  MMA -> TMA
   uint64_t* tfull = bars + 2 * TC_STAGES;       // [2] MMA -> epilogue
   uint64_t* tempty = bars + 2 * TC_STAGES + 2;  // [2] epilogue -> MMA
   uint64_t* bbar = bars + 2 * TC_STAGES + 4;    // B image landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 5);
+  uint64_t* xfull = bars + 2 * TC_STAGES + 5;   // [TC_STAGES] transform warps -> MMA (GELU / hi-lo split done)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 5);
+  const bool transform = p.act || p.split;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&xfull[s], 128); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
     mbar_init(bbar, 1);
     mbar_init_fence();
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(192, 1) tc_wfwd_kernel(const __grid_constant__
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], (uint32_t)a_stage_bytes);
+        mbar_expect_tx(&full[s], (uint32_t)a_tile_bytes);
         for (int kc = 0; kc < p.kch; ++kc)
           tma_load_2d(a_smem + s * a_stage_bytes + kc * TC_ATILE, &tmap_x, &full[s], kc * TC_KC, tile * TC_BM);
       }
@@ -179,18 +187,52 @@ __global__ void __launch_bounds__(192, 1) tc_wfwd_kernel(const __grid_constant__
         const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
         const int acc = it & 1, aph = (it >> 1) & 1;
         mbar_wait(&tempty[acc], aph ^ 1);
-        mbar_wait(&full[s], ph);
+        mbar_wait(transform ? &xfull[s] : &full[s], ph);
         tc_fence_after();
         const uint32_t a0 = smem_u32(a_smem + s * a_stage_bytes), b0 = smem_u32(b_smem);
         const uint32_t d = tmem_base + (uint32_t)(acc * p.n_pad);
         for (int kc = 0; kc < p.kch; ++kc)
 #pragma unroll
-          for (int k = 0; k < TC_KC / 8; ++k)
-            umma_tf32(d, umma_desc_sw128(a0 + kc * TC_ATILE + k * 32), umma_desc_sw128(b0 + kc * p.n_pad * 128 + k * 32),
-                      idesc, (uint32_t)((kc | k) != 0));
+          for (int k = 0; k < TC_KC / 8; ++k) {
+            const uint32_t ao = a0 + kc * TC_ATILE + k * 32, bo = b0 + kc * p.n_pad * 128 + k * 32;
+            if (p.split) {     // small cross terms first, then the main term
+              umma_tf32(d, umma_desc_sw128(ao + a_tile_bytes), umma_desc_sw128(bo), idesc, (uint32_t)((kc | k) != 0));
+              umma_tf32(d, umma_desc_sw128(ao), umma_desc_sw128(bo + b_part_bytes), idesc, 1u);
+              umma_tf32(d, umma_desc_sw128(ao), umma_desc_sw128(bo), idesc, 1u);
+            } else {
+              umma_tf32(d, umma_desc_sw128(ao), umma_desc_sw128(bo), idesc, (uint32_t)((kc | k) != 0));
+            }
+          }
         tc_commit(&empty[s]);      // the x stage may be refilled once these MMAs have read it
         tc_commit(&tfull[acc]);    // ... and the accumulator is complete
       }
+    }
+  } else if (warp >= 6) {
+    // ---------------- transform warps 6..9: exact GELU and / or the hi-lo split, in place in shared memory ----------------
+    const int t = threadIdx.x - 192;
+    const int n4 = a_tile_bytes >> 4;                      // float4 per tile copy
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      float4* hi = reinterpret_cast<float4*>(a_smem + s * a_stage_bytes);
+      float4* lo = reinterpret_cast<float4*>(a_smem + s * a_stage_bytes + a_tile_bytes);
+      for (int i = t; i < n4; i += 128) {
+        float4 v = hi[i];
+        if (p.act) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
+        if (p.split) {
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          v = h;
+        }
+        hi[i] = v;
+      }
+      fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      mbar_arrive(&xfull[s]);
     }
   } else {
     // ---------------- epilogue: warps 2..5, TMEM lane quadrant = warp % 4 ----------------
@@ -243,8 +285,11 @@ int tc_kch(int wp) { return (wp + TC_KC - 1) / TC_KC; }
 
 // The B operand image for one plan: [kch][n_pad rows][128 bytes], 16-byte chunks XOR-swizzled by (row % 8).
 void tc_build_b_image(int wp, int m2, std::vector<float>& img) {
+  // [hi part | lo part]: hi = value truncated to TF32 (13 low mantissa bits cleared), lo = value - hi.
+  // The plain TF32 mode reads only the first part (the tensor core ignores the low bits anyway).
   const int n_pad = tc_n_pad(m2), kch = tc_kch(wp);
-  img.assign((size_t)kch * n_pad * 32, 0.f);
+  const size_t part = (size_t)kch * n_pad * 32;
+  img.assign(2 * part, 0.f);
   const double two_pi = 6.283185307179586476925286766559;
   for (int n = 0; n < 2 * m2; ++n) {
     const int l = n >> 1;
@@ -253,24 +298,30 @@ void tc_build_b_image(int wp, int m2, std::vector<float>& img) {
       const float v = (n & 1) ? (float)(-std::sin(th)) : (float)std::cos(th);
       const int kc = w / TC_KC, k = w % TC_KC;
       const size_t off = (size_t)kc * n_pad * 32 + (size_t)n * 32 + (size_t)((((k >> 2) ^ (n & 7)) << 2) + (k & 3));
-      img[off] = v;
+      uint32_t bits;
+      memcpy(&bits, &v, 4);
+      bits &= 0xFFFFE000u;
+      float hi;
+      memcpy(&hi, &bits, 4);
+      img[off] = hi;
+      img[part + off] = v - hi;
     }
   }
 }
 
-static size_t tc_smem_bytes(int wp, int m2) {
-  const int kch = tc_kch(wp), n_pad = tc_n_pad(m2);
-  return 1024 + (size_t)TC_STAGES * kch * TC_ATILE + (((size_t)kch * n_pad * 128 + 1023) & ~(size_t)1023) + 256;
+static size_t tc_smem_bytes(int wp, int m2, bool split) {
+  const int kch = tc_kch(wp), n_pad = tc_n_pad(m2), f = split ? 2 : 1;
+  return 1024 + (size_t)TC_STAGES * kch * TC_ATILE * f + (((size_t)kch * n_pad * 128 * f + 1023) & ~(size_t)1023) + 256;
 }
 
-bool tc_wfwd_supported(const Plan* pl, const float* x) {
+bool tc_wfwd_supported(const Plan* pl, const float* x, bool split) {
   return pl->tc_fwd_b != nullptr && (pl->wp & 3) == 0 && tc_n_pad(pl->m2) <= 256 &&
-         tc_smem_bytes(pl->wp, pl->m2) <= 200 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+         tc_smem_bytes(pl->wp, pl->m2, split) <= 224 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
          encode_fn() != nullptr;
 }
 
 // returns false if the tensor map could not be encoded (caller falls back to the fp32 kernel)
-bool launch_wfwd_tc(const Plan* pl, const float* x, float2* out, int rows, cudaStream_t st) {
+bool launch_wfwd_tc(const Plan* pl, const float* x, float2* out, int rows, int act, bool split, cudaStream_t st) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return false;
   CUtensorMap tmap;
@@ -283,22 +334,23 @@ bool launch_wfwd_tc(const Plan* pl, const float* x, float2* out, int rows, cudaS
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) return false;
 
-  LaunchScope scope("wfwd_tc", st, pl->m2);
+  LaunchScope scope(split ? (act ? "wfwd_tc3x_gelu" : "wfwd_tc3x") : (act ? "wfwd_tc_gelu" : "wfwd_tc"), st, pl->m2);
   TcWfwdParams p;
   p.out = reinterpret_cast<float*>(out);
   p.b_image = pl->tc_fwd_b;
   p.rows = rows; p.nreal = 2 * pl->m2; p.n_pad = tc_n_pad(pl->m2); p.kch = tc_kch(pl->wp);
   p.ntiles = ceil_div(rows, TC_BM);
+  p.act = act; p.split = split ? 1 : 0;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * p.n_pad)) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = tc_smem_bytes(pl->wp, pl->m2);
+  const size_t smem = tc_smem_bytes(pl->wp, pl->m2, split);
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.ntiles < sms ? p.ntiles : sms;
   cudaFuncSetAttribute(tc_wfwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  launch_k(tc_wfwd_kernel, dim3(grid), dim3(192), smem, st, tmap, p);
+  launch_k(tc_wfwd_kernel, dim3(grid), dim3((act || split) ? 320 : 192), smem, st, tmap, p);
   return true;
 }
 

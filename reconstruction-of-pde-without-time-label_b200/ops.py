@@ -12,11 +12,11 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (FnoGrads, FnoParams, FnoShape, LiftInput, MAX_LAYERS, PREC_FP32, PREC_TF32, SpectralShape,
+from ._lib import (FnoGrads, FnoParams, FnoShape, LiftInput, MAX_LAYERS, PREC_FP32, PREC_TF32, PREC_TF32X3, SpectralShape,
                    check, pad_amount)
 
 __all__ = ["FnoSpec", "set_precision", "stage_wfwd", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat", "kernel_launches",
-           "PREC_FP32", "PREC_TF32"]
+           "PREC_FP32", "PREC_TF32", "PREC_TF32X3"]
 
 
 def _ptr(t: Optional[torch.Tensor]) -> int:
@@ -49,7 +49,7 @@ def set_precision(module, prec: int):
     """Select the arithmetic of the DFT GEMMs for every FNO net under ``module``: PREC_FP32 (CUDA-core FFMA,
     the 1e-5 parity mode, default) or PREC_TF32 (tcgen05 tensor cores where a stage has a tensor-core
     kernel, TF32 operands / fp32 accumulation; bound 2e-3, tests/test_gpu_parity.py)."""
-    if prec not in (PREC_FP32, PREC_TF32):
+    if prec not in (PREC_FP32, PREC_TF32, PREC_TF32X3):
         raise ValueError(f"unknown precision {prec}")
     for m in module.modules():
         if hasattr(m, "_spec") and hasattr(m, "spectral_list"):

@@ -340,6 +340,15 @@ def test_stage_wfwd_fp32_and_tf32_tensor_core(rows, wp, m2, hp, m1):
     err = rel_err(got_tc, want)
     assert err < TF32_TOL, f"tcgen05 TF32 W-forward: rel err {err:.3e}"
     assert err > 1e-7           # it really ran in TF32 (the fp32 kernel would be ~1e-7)
+    # GELU applied to the tile in shared memory by the transform warps
+    want_act = torch.from_numpy(dft64.wfwd(torch.nn.functional.gelu(x.double()).numpy(), m2))
+    assert rel_err(ops.stage_wfwd(x.to(DEV), m2, hp=hp, m1=m1, act=True), want_act) < TOL
+    assert rel_err(ops.stage_wfwd(x.to(DEV), m2, hp=hp, m1=m1, act=True, prec=ops.PREC_TF32), want_act) < TF32_TOL
+    # 3xTF32: operands split into TF32 high and low parts, three MMAs per K step -> the fp32 bound
+    for act, ref in ((False, want), (True, want_act)):
+        got3 = ops.stage_wfwd(x.to(DEV), m2, hp=hp, m1=m1, act=act, prec=ops.PREC_TF32X3)
+        e3 = rel_err(got3, ref)
+        assert e3 < TOL, f"tcgen05 3xTF32 W-forward (act={act}): rel err {e3:.3e}"
 
 
 def test_tf32_mode_whole_model_within_stated_bound():

@@ -33,7 +33,8 @@ def bench(rows, wp, m2, prec, iters=20, act=False):
     us = times[len(times) // 2]
     nbytes = rows * (4 * wp + 8 * m2)
     flops = 2.0 * rows * wp * 2 * m2
-    return {"rows": rows, "wp": wp, "m2": m2, "prec": "tf32_tcgen05" if prec else "fp32_ffma", "us": us,
+    return {"rows": rows, "wp": wp, "m2": m2, "act": bool(act),
+            "prec": {0: "fp32_ffma", 1: "tf32_tcgen05", 2: "3xtf32_tcgen05"}[prec], "us": us,
             "GBps": nbytes / us / 1e3, "TFLOPs": flops / us / 1e6}
 
 
@@ -42,10 +43,10 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--shapes", default="default")
     a = ap.parse_args()
-    shapes = [(300 * 4 * 76, 76, 12), (8 * 12 * 76, 76, 32), (300 * 4 * 100, 100, 12), (1600 * 4 * 76, 76, 12),
-              (400 * 12 * 160, 160, 32)]
+    shapes = [(300 * 4 * 76, 76, 12), (1600 * 4 * 76, 76, 12), (300 * 4 * 100, 100, 12)]
     if a.shapes == "one":
         shapes = shapes[:1]
     for rows, wp, m2 in shapes:
-        for prec in (0, 1):
-            print(json.dumps(bench(rows, wp, m2, prec, a.iters)), flush=True)
+        for act in (False, True):
+            for prec in (0, 1, 2):
+                print(json.dumps(bench(rows, wp, m2, prec, a.iters, act=act)), flush=True)
