@@ -122,7 +122,9 @@ __host__ __device__ inline uint32_t tc_idesc(int n_pad) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(320, 1) tc_wfwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcWfwdParams p) {
+constexpr int TC_XFORM_THREADS = 384;   // 12 transform warps (GELU / hi-lo split of a 48 KB tile per ~1 us)
+
+__global__ void __launch_bounds__(192 + TC_XFORM_THREADS, 1) tc_wfwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcWfwdParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [A stages (hi | lo)][B image (hi | lo)][barriers][tmem slot]
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(320, 1) tc_wfwd_kernel(const __grid_constant__
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&xfull[s], 128); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&xfull[s], TC_XFORM_THREADS); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
     mbar_init(bbar, 1);
     mbar_init_fence();
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(320, 1) tc_wfwd_kernel(const __grid_constant__
       }
     }
   } else if (warp >= 6) {
-    // ---------------- transform warps 6..9: exact GELU and / or the hi-lo split, in place in shared memory ----------------
+    // ---------------- transform warps 6..17: exact GELU and / or the hi-lo split, in place in shared memory ----------------
     const int t = threadIdx.x - 192;
     const int n4 = a_tile_bytes >> 4;                      // float4 per tile copy
     int it = 0;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(320, 1) tc_wfwd_kernel(const __grid_constant__
       mbar_wait(&full[s], ph);
       float4* hi = reinterpret_cast<float4*>(a_smem + s * a_stage_bytes);
       float4* lo = reinterpret_cast<float4*>(a_smem + s * a_stage_bytes + a_tile_bytes);
-      for (int i = t; i < n4; i += 128) {
+      for (int i = t; i < n4; i += TC_XFORM_THREADS) {
         float4 v = hi[i];
         if (p.act) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
         if (p.split) {
@@ -350,7 +352,7 @@ bool launch_wfwd_tc(const Plan* pl, const float* x, float2* out, int rows, int a
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.ntiles < sms ? p.ntiles : sms;
   cudaFuncSetAttribute(tc_wfwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  launch_k(tc_wfwd_kernel, dim3(grid), dim3((act || split) ? 320 : 192), smem, st, tmap, p);
+  launch_k(tc_wfwd_kernel, dim3(grid), dim3((act || split) ? 192 + TC_XFORM_THREADS : 192), smem, st, tmap, p);
   return true;
 }
 
