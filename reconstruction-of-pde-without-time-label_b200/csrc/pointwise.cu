@@ -239,11 +239,87 @@ __global__ void __launch_bounds__(256) lift_bwd_kernel(const LiftParams p, const
   }
 }
 
+// lift backward, narrow nets without an input gradient (the per-snapshot net: width 4, 2-3 input features):
+// the C*(CI+1) sums live in registers, one thread walks pixels of one image (grid.y = image, so the bag /
+// snapshot lookup is block-uniform), then warp shuffle -> shared -> one atomic per sum per block.
+template <int C, int CI>
+__global__ void __launch_bounds__(256) lift_bwd_small_kernel(const LiftParams p, const float* __restrict__ gz0,
+                                                             float* g_w0, float* g_b0) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8][C * (CI + 1)];
+  const int plane = p.hp * p.wp, hw = p.h * p.w;
+  const float inv_w = 1.0f / (float)p.w;
+  float acc[C][CI + 1];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int i = 0; i <= CI; ++i) acc[c][i] = 0.f;
+  for (int img = blockIdx.y; img < p.images; img += gridDim.y) {
+    const float* src0 = nullptr;
+    if (p.x_cl == nullptr) {
+      const int b = img / p.n_keep, l = img - b * p.n_keep;
+      const int snap = p.idx != nullptr ? __ldg(p.idx + l) : l;
+      src0 = p.bags + ((size_t)b * p.bag_len + snap) * hw;
+    }
+    const float* g = gz0 + (size_t)img * C * plane;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += gridDim.x * blockDim.x) {
+      const int hh = __float2int_rz(((float)pix + 0.5f) * inv_w), ww = pix - hh * p.w;
+      float in[CI];
+      if (p.x_cl != nullptr) {
+#pragma unroll
+        for (int i = 0; i < CI; ++i) in[i] = __ldg(p.x_cl + ((size_t)img * hw + pix) * CI + i);
+      } else {
+        in[0] = __ldg(src0 + pix);
+#pragma unroll
+        for (int d = 1; d < CI; ++d) in[d] = __ldg(p.grid + (size_t)pix * (CI - 1) + (d - 1));
+      }
+      const int off = hh * p.wp + ww;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float gv = __ldg(g + (size_t)c * plane + off);
+#pragma unroll
+        for (int i = 0; i < CI; ++i) acc[c][i] = fmaf(gv, in[i], acc[c][i]);
+        acc[c][CI] += gv;
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int i = 0; i <= CI; ++i) {
+      const float v = warp_sum(acc[c][i]);
+      if (lane == 0) red[warp][c * (CI + 1) + i] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < C * (CI + 1)) {
+    float v = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+    const int c = threadIdx.x / (CI + 1), i = threadIdx.x - c * (CI + 1);
+    if (c < p.width) {
+      if (i < CI) atomicAdd(g_w0 + c * CI + i, v);
+      else atomicAdd(g_b0 + c, v);
+    }
+  }
+}
+
 void launch_lift_bwd(const LiftArgs& a, const float* gz0, float* g_w0, float* g_b0, float* gx_cl,
                      cudaStream_t st) {
   LaunchScope scope("lift_bwd", st, a.width);
   const LiftParams p = make_lift_params(a);
   const long total = (long)a.images * a.h * a.w;
+  if (gx_cl == nullptr && a.width == 4 && (a.c_in == 2 || a.c_in == 3) && (a.x_cl != nullptr || a.grid_dim == a.c_in - 1)) {
+    const int hw = a.h * a.w;
+    int gx = ceil_div(hw, 256 * 4);                     // >= 4 pixels per thread per image
+    if (gx < 1) gx = 1;
+    int gy = a.images;
+    while ((long)gx * gy > 148L * 16 && gy > 1) gy = (gy + 1) / 2;   // a few blocks per SM, several images per block
+    dim3 grid(gx, gy);
+    if (a.c_in == 3) launch_k(lift_bwd_small_kernel<4, 3>, grid, dim3(256), 0, st, p, gz0, g_w0, g_b0);
+    else launch_k(lift_bwd_small_kernel<4, 2>, grid, dim3(256), 0, st, p, gz0, g_w0, g_b0);
+    return;
+  }
   const bool few = total < 148L * 256 * 2;
   const int tp = few ? 64 : 256;
   const int tiles = (int)((total + tp - 1) / tp);
