@@ -172,6 +172,45 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
                      void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Single stages of an FNO net (what the torch custom ops fno_lift_pad / fno_layer{1,2}d /
+ * fno_project bind).  They take the BdnFnoShape of the net they belong to (n_layers is only
+ * range-checked) and run the same kernels bdn_fno_forward / bdn_fno_backward chain.
+ * Activations are PRE-activation tensors z_k [images, width, hp, wp]; a layer applies the
+ * exact GELU to its input on load when act_in != 0, so the reference's
+ *   x_{k+1} = gelu(spectral(x_k) + conv1x1(x_k))        2d_FPE/FNOModules.py:226-232
+ *                                                        1d_FPE/FNOModules.py:108-114
+ * is  z_{k+1} = layer(z_k, act_in = (k > 0)),  x_k = gelu(z_k) for k > 0,  x_0 = z_0.
+ * All g_* gradient pointers are ACCUMULATED into (+=): the caller zeroes them.
+ * ------------------------------------------------------------------------- */
+/* lift: fc0 + channels-first + zero pad   FNOModules.py:103-106 (1-D), :219-224 (2-D) */
+int bdn_stage_lift_forward(const BdnFnoShape* s, const float* fc0_w, const float* fc0_b,
+                           const BdnLiftInput* in, float* z0, void* stream);
+int bdn_stage_lift_backward(const BdnFnoShape* s, const float* fc0_w, const float* fc0_b,
+                            const BdnLiftInput* in, const float* gz0,
+                            float* g_fc0_w, float* g_fc0_b, float* gx_cl /* may be NULL */, void* stream);
+/* one layer body.  xs_saved (may be NULL in forward): [images, width, K, m2] complex. */
+size_t bdn_stage_layer_workspace_bytes(const BdnFnoShape* s);
+int bdn_stage_layer_forward(const BdnFnoShape* s, const float* z_in, int32_t act_in,
+                            const float* spec_w1, const float* spec_w2 /* NULL in 1-D */,
+                            const float* conv_w, const float* conv_b, float* z_out, float* xs_saved,
+                            void* ws, size_t ws_bytes, void* stream);
+int bdn_stage_layer_backward(const BdnFnoShape* s, const float* gz_out, const float* z_in, int32_t act_in,
+                             const float* xs_saved, const float* spec_w1, const float* spec_w2,
+                             const float* conv_w, float* gz_in /* overwritten */,
+                             float* g_spec_w1, float* g_spec_w2, float* g_conv_w, float* g_conv_b,
+                             void* ws, size_t ws_bytes, void* stream);
+/* crop + fc1 + exact GELU + fc2   FNOModules.py:116-121 (1-D), :234-239 (2-D).
+ * z: the last layer's output [images, width, hp, wp]; out: [images, out_h, out_w, c_out].
+ * backward: gz [images, width, hp, wp] is overwritten (zero outside the crop); pooled_g as in
+ * bdn_fno_backward. */
+int bdn_stage_project_forward(const BdnFnoShape* s, const float* z, const float* fc1_w, const float* fc1_b,
+                              const float* fc2_w, const float* fc2_b, float* out, void* stream);
+int bdn_stage_project_backward(const BdnFnoShape* s, const float* z, const float* fc1_w, const float* fc1_b,
+                               const float* fc2_w, const float* fc2_b, const float* g_out,
+                               int32_t pooled_g, int32_t n_keep, float* gz,
+                               float* g_fc1_w, float* g_fc1_b, float* g_fc2_w, float* g_fc2_b, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Bag mean + lift: fc0([grid, mean_l s_l]) with fc0 detached
  *   2d_FPE/NIOModules.py:564-575, 1d_FPE/NIOModules.py:139-149,
  *   1d_GPE/NIOModules.py:209-219.

@@ -65,6 +65,15 @@ EXPORTS = {
                                   _fp, C.c_size_t, _fp]),
     "bdn_fno_backward": (C.c_int, [C.POINTER(FnoShape), C.POINTER(FnoParams), C.POINTER(LiftInput), _fp, C.c_int32,
                                    C.c_int32, _fp, _fp, C.POINTER(FnoGrads), _fp, _fp, C.c_size_t, _fp]),
+    "bdn_stage_lift_forward": (C.c_int, [C.POINTER(FnoShape), _fp, _fp, C.POINTER(LiftInput), _fp, _fp]),
+    "bdn_stage_lift_backward": (C.c_int, [C.POINTER(FnoShape), _fp, _fp, C.POINTER(LiftInput), _fp, _fp, _fp, _fp, _fp]),
+    "bdn_stage_layer_workspace_bytes": (C.c_size_t, [C.POINTER(FnoShape)]),
+    "bdn_stage_layer_forward": (C.c_int, [C.POINTER(FnoShape), _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                                          C.c_size_t, _fp]),
+    "bdn_stage_layer_backward": (C.c_int, [C.POINTER(FnoShape), _fp, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                                           _fp, _fp, _fp, C.c_size_t, _fp]),
+    "bdn_stage_project_forward": (C.c_int, [C.POINTER(FnoShape)] + [_fp] * 7),
+    "bdn_stage_project_backward": (C.c_int, [C.POINTER(FnoShape)] + [_fp] * 6 + [C.c_int32, C.c_int32] + [_fp] * 6),
     "bdn_bag_pool_lift_forward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_int32, _fp]),
     "bdn_bag_pool_lift_backward": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp]),

@@ -522,6 +522,140 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
 }
 
 // ---------------------------------------------------------------------------
+// single stages of an FNO net (the custom-op layer exposes them one by one; the whole-net calls
+// above run exactly these launches back to back)
+// ---------------------------------------------------------------------------
+static BdnFnoParams lift_only_params(const float* fc0_w, const float* fc0_b) {
+  BdnFnoParams p{};
+  p.fc0_w = fc0_w; p.fc0_b = fc0_b;
+  return p;
+}
+
+int bdn_stage_lift_forward(const BdnFnoShape* s, const float* fc0_w, const float* fc0_b, const BdnLiftInput* in,
+                           float* z0, void* stream) {
+  int rc = check_fno(s);
+  if (rc != BDN_OK) return rc;
+  if (s->images == 0) return BDN_OK;
+  if (!fc0_w || !fc0_b || !z0) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  if ((rc = check_lift_input(s, in)) != BDN_OK) return rc;
+  const BdnFnoParams p = lift_only_params(fc0_w, fc0_b);
+  launch_lift(make_lift(s, &p, in), z0, (cudaStream_t)stream);
+  return check_cuda("bdn_stage_lift_forward");
+}
+
+int bdn_stage_lift_backward(const BdnFnoShape* s, const float* fc0_w, const float* fc0_b, const BdnLiftInput* in,
+                            const float* gz0, float* g_fc0_w, float* g_fc0_b, float* gx_cl, void* stream) {
+  int rc = check_fno(s);
+  if (rc != BDN_OK) return rc;
+  if (s->images == 0) return BDN_OK;
+  if (!fc0_w || !fc0_b || !gz0 || !g_fc0_w || !g_fc0_b) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  if ((rc = check_lift_input(s, in)) != BDN_OK) return rc;
+  const BdnFnoParams p = lift_only_params(fc0_w, fc0_b);
+  launch_lift_bwd(make_lift(s, &p, in), gz0, g_fc0_w, g_fc0_b, gx_cl, (cudaStream_t)stream);
+  return check_cuda("bdn_stage_lift_backward");
+}
+
+size_t bdn_stage_layer_workspace_bytes(const BdnFnoShape* s) {
+  if (check_fno(s) != BDN_OK) return 0;
+  return 2 * align_up(spec1_bytes(s->images, s->width, s->hp, s->m2)) + align_up(kspec_floats1(s) * sizeof(float)) + 256;
+}
+
+int bdn_stage_layer_forward(const BdnFnoShape* s, const float* z_in, int32_t act_in, const float* spec_w1,
+                            const float* spec_w2, const float* conv_w, const float* conv_b, float* z_out,
+                            float* xs_saved, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_fno(s);
+  if (rc != BDN_OK) return rc;
+  if (s->images == 0) return BDN_OK;
+  if (!z_in || !spec_w1 || (s->ndim == 2 && !spec_w2) || !conv_w || !conv_b || !z_out || !ws)
+    return set_error(BDN_ERR_INVALID, "null pointer argument");
+  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  if (!pl) return BDN_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv{(char*)ws, ws_bytes};
+  float2* X1 = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
+  float2* Z = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
+  if (!X1 || !Z) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+  launch_wfwd(pl, z_in, X1, s->images * s->width * s->hp, act_in != 0, st, s->prec);
+  if (s->ndim == 2)
+    launch_core2d(pl, X1, Z, (float2*)xs_saved, (const float2*)spec_w1, (const float2*)spec_w2, s->images, s->width,
+                  s->width, false, st);
+  else
+    launch_mix1d(pl, X1, Z, (float2*)xs_saved, (const float2*)spec_w1, s->images, s->width, s->width, false, st);
+  WinvArgs wa{};
+  wa.z = Z; wa.y = z_out; wa.a = z_in; wa.pw_w = conv_w; wa.pw_b = conv_b;
+  wa.images = s->images; wa.c = s->width; wa.act_in = act_in != 0;
+  launch_winv(pl, WINV_LAYER_FWD, wa, st);
+  return check_cuda("bdn_stage_layer_forward");
+}
+
+int bdn_stage_layer_backward(const BdnFnoShape* s, const float* gz_out, const float* z_in, int32_t act_in,
+                             const float* xs_saved, const float* spec_w1, const float* spec_w2, const float* conv_w,
+                             float* gz_in, float* g_spec_w1, float* g_spec_w2, float* g_conv_w, float* g_conv_b,
+                             void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_fno(s);
+  if (rc != BDN_OK) return rc;
+  if (s->images == 0) return BDN_OK;
+  if (!gz_out || !z_in || !xs_saved || !spec_w1 || (s->ndim == 2 && (!spec_w2 || !g_spec_w2)) || !conv_w || !gz_in ||
+      !g_spec_w1 || !g_conv_w || !g_conv_b || !ws)
+    return set_error(BDN_ERR_INVALID, "null pointer argument");
+  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  if (!pl) return BDN_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv{(char*)ws, ws_bytes};
+  float2* G1 = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
+  float2* GZ = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
+  float2* GY = (float2*)cv.take(kspec_floats1(s) * sizeof(float));
+  if (!G1 || !GZ || !GY) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+  launch_wfwd(pl, gz_out, G1, s->images * s->width * s->hp, 0, st, s->prec);
+  if (s->ndim == 2)
+    launch_core2d(pl, G1, GZ, GY, (const float2*)spec_w1, (const float2*)spec_w2, s->images, s->width, s->width, true, st);
+  else
+    launch_mix1d(pl, G1, GZ, GY, (const float2*)spec_w1, s->images, s->width, s->width, true, st);
+  launch_gw_reduce(pl, (const float2*)xs_saved, GY, (float2*)g_spec_w1, (float2*)g_spec_w2, s->images, s->width,
+                   s->width, st);
+  WinvArgs wa{};
+  wa.z = GZ; wa.y = gz_in; wa.a = gz_out; wa.zin = z_in;
+  wa.pw_w = conv_w; wa.g_pw_w = g_conv_w; wa.g_pw_b = g_conv_b;
+  wa.images = s->images; wa.c = s->width; wa.act_in = act_in != 0;
+  launch_winv(pl, WINV_LAYER_BWD, wa, st);
+  return check_cuda("bdn_stage_layer_backward");
+}
+
+static BdnFnoParams proj_only_params(const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b) {
+  BdnFnoParams p{};
+  p.fc1_w = fc1_w; p.fc1_b = fc1_b; p.fc2_w = fc2_w; p.fc2_b = fc2_b;
+  return p;
+}
+
+int bdn_stage_project_forward(const BdnFnoShape* s, const float* z, const float* fc1_w, const float* fc1_b,
+                              const float* fc2_w, const float* fc2_b, float* out, void* stream) {
+  int rc = check_fno(s);
+  if (rc != BDN_OK) return rc;
+  if (s->images == 0) return BDN_OK;
+  if (!z || !fc1_w || !fc1_b || !fc2_w || !fc2_b || !out) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  const BdnFnoParams p = proj_only_params(fc1_w, fc1_b, fc2_w, fc2_b);
+  launch_project(make_proj(s, &p, z), out, (cudaStream_t)stream);
+  return check_cuda("bdn_stage_project_forward");
+}
+
+int bdn_stage_project_backward(const BdnFnoShape* s, const float* z, const float* fc1_w, const float* fc1_b,
+                               const float* fc2_w, const float* fc2_b, const float* g_out, int32_t pooled_g,
+                               int32_t n_keep, float* gz, float* g_fc1_w, float* g_fc1_b, float* g_fc2_w,
+                               float* g_fc2_b, void* stream) {
+  int rc = check_fno(s);
+  if (rc != BDN_OK) return rc;
+  if (s->images == 0) return BDN_OK;
+  if (!z || !fc1_w || !fc1_b || !fc2_w || !fc2_b || !g_out || !gz || !g_fc1_w || !g_fc1_b || !g_fc2_w || !g_fc2_b)
+    return set_error(BDN_ERR_INVALID, "null pointer argument");
+  if (pooled_g && (n_keep < 1 || s->images % n_keep != 0))
+    return set_error(BDN_ERR_INVALID, "pooled gradient: images=%d not a multiple of n_keep=%d", s->images, n_keep);
+  const BdnFnoParams p = proj_only_params(fc1_w, fc1_b, fc2_w, fc2_b);
+  launch_project_bwd(make_proj(s, &p, z), g_out, pooled_g, n_keep, gz, g_fc1_w, g_fc1_b, g_fc2_w, g_fc2_b,
+                     (cudaStream_t)stream);
+  return check_cuda("bdn_stage_project_backward");
+}
+
+// ---------------------------------------------------------------------------
 // bag pool, optimiser
 // ---------------------------------------------------------------------------
 int bdn_bag_pool_lift_forward(const float* s, const float* grid, const float* w0, const float* b0, float* out,

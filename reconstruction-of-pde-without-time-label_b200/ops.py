@@ -1,13 +1,34 @@
-"""Autograd-aware Python entry points over the C ABI (include/blindno_b200.h).
+"""PyTorch custom ops (``torch.ops.blindno_b200.*``) over the C ABI (include/blindno_b200.h).
 
-torch is used for device memory, streams and autograd bookkeeping only; every FLOP of these
-ops runs in libblindno_b200.so.  CPU tensors are rejected -- there is no fallback path.
+The reference has no operator registry of its own: its interface for this path is the ``forward`` of a
+few nn.Modules.  This module registers one custom op per fused stage with
+``torch.library`` -- schema, CUDA implementation (a ctypes call into libblindno_b200.so), a shape-only
+fake/meta implementation and an autograd formula -- and the drop-in modules in ``surface/`` call those
+ops.  torch provides device memory, the current stream, the dispatcher and autograd bookkeeping; every
+FLOP runs in libblindno_b200.so.  There is no CPU implementation: the CPU dispatch key raises.
+
+    differentiable ops (what a model calls)                  reference code it replaces
+    ---------------------------------------------------------------------------------------------------
+    spectral_conv2d(x, w1, w2, m1, m2, prec)                 SpectralConv2d.forward   2d_FPE/FNOModules.py:156-178
+    spectral_conv1d(x, w, m, halve_dc, prec)                 SpectralConv1d.forward   1d_FPE/FNOModules.py:47-59
+    fno_lift_pad(x_cl, fc0_w, fc0_b, ndim)                   fc0 + permute + F.pad    FNOModules.py:103-106, :219-224
+    fno_layer2d / fno_layer1d(z, w.., conv_w, conv_b, gelu_in, prec)
+                                                             layer body               FNOModules.py:226-232, :108-114
+    fno_project(z, fc1_w, fc1_b, fc2_w, fc2_b, out_h, out_w) crop + fc1 + GELU + fc2  FNOModules.py:116-121, :234-239
+    fno_net(...)                                             FNO1d/FNO2d.forward (+ bag gather / grid concat / bag
+                                                             mean + detached lift)    2d_FPE/NIOModules.py:548-575
+    bag_pool_lift(s, grid, fc0_w, fc0_b)                     bag mean + detached fc0  2d_FPE/NIOModules.py:564-575
+    bag_project_pool_lift(z, n_keep, fc1.., grid, fc0..)     projection of every snapshot, then the above
+    deeponet_pool_contract_lift(w, basis, b0, grid, fc0..)   DeepOnetNoBiasOrg.forward + bag mean + lift
+                                                             DeepONetModules.py:142-151, 1d_GPE/NIOModules.py:209-219
+
+    *_forward / *_backward ops are the non-differentiable primitives the formulas above are made of.
 """
 from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 
@@ -15,8 +36,13 @@ from . import _lib
 from ._lib import (FnoGrads, FnoParams, FnoShape, LiftInput, MAX_LAYERS, PREC_FP32, PREC_TF32, PREC_TF32X3, SpectralShape,
                    check, pad_amount)
 
-__all__ = ["FnoSpec", "set_precision", "stage_wfwd", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat", "kernel_launches",
+__all__ = ["FnoSpec", "set_precision", "stage_wfwd", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat",
+           "kernel_launches", "fno_lift_pad", "fno_layer", "fno_project", "OP_NAMES",
            "PREC_FP32", "PREC_TF32", "PREC_TF32X3"]
+
+NS = "blindno_b200"
+_LIB = torch.library.Library(NS, "DEF")
+_OPS = torch.ops.blindno_b200
 
 
 def _ptr(t: Optional[torch.Tensor]) -> int:
@@ -43,6 +69,40 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise RuntimeError(f"blindno_b200 ops are fp32, got {t.dtype}")
     return t.contiguous()
+
+
+def _like_param(flat: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    """A gradient computed as fp32 (pairs) in the layout of parameter ``ref``."""
+    if ref.is_complex():
+        return torch.view_as_complex(flat.view(*ref.shape, 2))
+    return flat.view(ref.shape)
+
+
+def _empty(dev):
+    return torch.empty(0, dtype=torch.float32, device=dev)
+
+
+OP_NAMES: List[str] = []
+
+
+def _define(name: str, schema: str, cuda_impl, fake_impl=None):
+    """Schema + CUDA kernel + loud CPU key (+ shape-only fake kernel, also used on the meta device)."""
+    _LIB.define(f"{name}{schema}")
+    _LIB.impl(name, cuda_impl, "CUDA")
+
+    def _no_cpu(*args, **kwargs):
+        raise RuntimeError(f"blindno_b200::{name} runs on CUDA tensors only (there is no CPU fallback by design)")
+
+    _LIB.impl(name, _no_cpu, "CPU")
+    if fake_impl is not None:
+        torch.library.register_fake(f"{NS}::{name}", fake_impl, lib=_LIB)
+    OP_NAMES.append(name)
+
+
+def _define_composite(name: str, schema: str, fn):
+    _LIB.define(f"{name}{schema}")
+    _LIB.impl(name, fn, "CompositeImplicitAutograd")
+    OP_NAMES.append(name)
 
 
 def set_precision(module, prec: int):
@@ -83,9 +143,10 @@ def profile_end() -> dict:
     return json.loads(buf.value.decode() or "{}")
 
 
-def stage_wfwd(x: torch.Tensor, m2: int, *, hp: int = 1, m1: int = 0, act: bool = False, prec: int = PREC_FP32):
-    """One stage on its own (tests, kernel benchmarks): pruned forward DFT along the last axis of
-    x [rows, wp] -> complex64 [rows, m2].  ``prec=PREC_TF32`` runs the tcgen05 tensor-core kernel."""
+# ---------------------------------------------------------------------------------------------
+# stage_wfwd: one pruned forward DFT (tests, kernel benchmarks)
+# ---------------------------------------------------------------------------------------------
+def _stage_wfwd_cuda(x, m2, hp, m1, act, prec):
     _need_cuda(x)
     xc = _f32c(x)
     rows, wp = xc.shape
@@ -94,6 +155,150 @@ def stage_wfwd(x: torch.Tensor, m2: int, *, hp: int = 1, m1: int = 0, act: bool 
         check(_lib.lib().bdn_stage_wfwd(hp, wp, m1, m2, rows, _ptr(xc), _ptr(out), int(act), prec, _stream()),
               "bdn_stage_wfwd")
     return torch.view_as_complex(out)
+
+
+_define("stage_wfwd", "(Tensor x, int m2, int hp=1, int m1=0, bool act=False, int prec=0) -> Tensor", _stage_wfwd_cuda,
+        lambda x, m2, hp=1, m1=0, act=False, prec=0: x.new_empty(x.shape[0], m2, dtype=torch.complex64))
+
+
+def stage_wfwd(x: torch.Tensor, m2: int, *, hp: int = 1, m1: int = 0, act: bool = False, prec: int = PREC_FP32):
+    """One stage on its own (tests, kernel benchmarks): pruned forward DFT along the last axis of
+    x [rows, wp] -> complex64 [rows, m2].  ``prec=PREC_TF32`` runs the tcgen05 tensor-core kernel."""
+    return _OPS.stage_wfwd(x, m2, hp, m1, act, prec)
+
+
+# ---------------------------------------------------------------------------------------------
+# one spectral convolution
+# ---------------------------------------------------------------------------------------------
+def _spectral_shape(x_shape, w1_shape, ndim: int, prec: int) -> SpectralShape:
+    s = SpectralShape()
+    s.ndim, s.prec = ndim, prec
+    if ndim == 2:
+        s.images, s.c_in, s.hp, s.wp = x_shape
+        ci, s.c_out, s.m1, s.m2 = w1_shape[:4]
+    else:
+        (s.images, s.c_in, s.wp), s.hp, s.m1 = x_shape, 1, 0
+        ci, s.c_out, s.m2 = w1_shape[:3]
+    if ci != s.c_in:
+        raise RuntimeError(f"weights expect {ci} input channels, x has {s.c_in}")
+    return s
+
+
+def _spectral_forward_cuda(x, w1, w2, prec, save):
+    L = _lib.lib()
+    _need_cuda(x, w1, w2)
+    ndim = 2 if w2 is not None else 1
+    xc, w1c = _f32c(x), _f32c(w1)
+    w2c = _f32c(w2) if w2 is not None else None
+    if xc.dim() != ndim + 2:
+        raise RuntimeError(f"spectral conv {ndim}-D expects x with {ndim + 2} dims, got {tuple(xc.shape)}")
+    s = _spectral_shape(tuple(xc.shape), tuple(w1c.shape), ndim, prec)
+    dev = xc.device
+    with torch.cuda.device(dev):
+        ws_bytes = L.bdn_spectral_workspace_bytes(C.byref(s))
+        if ws_bytes == 0:
+            check(-1, "bdn_spectral_workspace_bytes")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        K = 2 * s.m1 if ndim == 2 else 1
+        xs = torch.empty(s.images * s.c_in * K * s.m2 * 2, dtype=torch.float32, device=dev) if save else None
+        y = torch.empty((s.images, s.c_out) + tuple(xc.shape[2:]), dtype=torch.float32, device=dev)
+        check(L.bdn_spectral_forward(C.byref(s), _ptr(xc), _ptr(w1c), _ptr(w2c), _ptr(y), _ptr(xs), _ptr(ws),
+                                     ws_bytes, _stream()), "bdn_spectral_forward")
+    return y, (xs if xs is not None else _empty(dev))
+
+
+def _spectral_forward_fake(x, w1, w2, prec, save):
+    ndim = 2 if w2 is not None else 1
+    c_in, c_out = w1.shape[0], w1.shape[1]
+    K = 2 * w1.shape[2] if ndim == 2 else 1
+    m2 = w1.shape[3] if ndim == 2 else w1.shape[2]
+    y = x.new_empty((x.shape[0], c_out) + tuple(x.shape[2:]), dtype=torch.float32)
+    return y, x.new_empty(x.shape[0] * c_in * K * m2 * 2 if save else 0, dtype=torch.float32)
+
+
+def _spectral_backward_cuda(gy, xs, w1, w2, need_gx, prec):
+    L = _lib.lib()
+    _need_cuda(gy, xs, w1, w2)
+    ndim = 2 if w2 is not None else 1
+    gyc, w1c = _f32c(gy), _f32c(w1)
+    w2c = _f32c(w2) if w2 is not None else None
+    c_in = w1c.shape[0]
+    s = _spectral_shape((gyc.shape[0], c_in) + tuple(gyc.shape[2:]), tuple(w1c.shape), ndim, prec)
+    dev = gyc.device
+    with torch.cuda.device(dev):
+        ws_bytes = L.bdn_spectral_workspace_bytes(C.byref(s))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        gx = torch.empty((s.images, c_in) + tuple(gyc.shape[2:]), dtype=torch.float32, device=dev) if need_gx else None
+        gw1 = torch.empty_like(w1c)
+        gw2 = torch.empty_like(w2c) if w2c is not None else None
+        check(L.bdn_spectral_backward(C.byref(s), _ptr(gyc), _ptr(xs), _ptr(w1c), _ptr(w2c), _ptr(gx), _ptr(gw1),
+                                      _ptr(gw2), _ptr(ws), ws_bytes, _stream()), "bdn_spectral_backward")
+    return (gx if gx is not None else _empty(dev), _like_param(gw1, w1),
+            _like_param(gw2, w2) if w2 is not None else _empty(dev))
+
+
+def _spectral_backward_fake(gy, xs, w1, w2, need_gx, prec):
+    gx = gy.new_empty((gy.shape[0], w1.shape[0]) + tuple(gy.shape[2:]) if need_gx else (0,), dtype=torch.float32)
+    return gx, torch.empty_like(w1), (torch.empty_like(w2) if w2 is not None else gy.new_empty(0))
+
+
+_define("spectral_conv_forward", "(Tensor x, Tensor w1, Tensor? w2, int prec, bool save) -> (Tensor, Tensor)",
+        _spectral_forward_cuda, _spectral_forward_fake)
+_define("spectral_conv_backward",
+        "(Tensor gy, Tensor xs, Tensor w1, Tensor? w2, bool need_gx, int prec) -> (Tensor, Tensor, Tensor)",
+        _spectral_backward_cuda, _spectral_backward_fake)
+
+
+def _spectral_setup(ctx, inputs, output):
+    x, w1, w2, prec, save = inputs
+    ctx.set_materialize_grads(False)
+    ctx.mark_non_differentiable(output[1])
+    ctx.save_for_backward(output[1], w1, w2)
+    ctx.prec, ctx.saved_spectrum = prec, save
+
+
+def _spectral_bwd(ctx, gy, _gxs):
+    xs, w1, w2 = ctx.saved_tensors
+    if gy is None:
+        return None, None, None, None, None
+    if not ctx.saved_spectrum:
+        raise RuntimeError("spectral_conv_forward was called with save=False; it cannot be differentiated")
+    gx, gw1, gw2 = _OPS.spectral_conv_backward(gy, xs, w1, w2, ctx.needs_input_grad[0], ctx.prec)
+    return (gx if ctx.needs_input_grad[0] else None, gw1 if ctx.needs_input_grad[1] else None,
+            gw2 if (w2 is not None and ctx.needs_input_grad[2]) else None, None, None)
+
+
+torch.library.register_autograd(f"{NS}::spectral_conv_forward", _spectral_bwd, setup_context=_spectral_setup, lib=_LIB)
+
+
+def _wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _spectral_conv2d(x, w1, w2, m1, m2, prec=0):
+    if tuple(w1.shape[2:4]) != (m1, m2) or tuple(w2.shape[2:4]) != (m1, m2):
+        raise RuntimeError(f"weights keep {tuple(w1.shape[2:4])} modes, the call says ({m1}, {m2})")
+    return _OPS.spectral_conv_forward(x, w1, w2, prec, _wants_grad(x, w1, w2))[0]
+
+
+def _spectral_conv1d(x, w, m, halve_dc=True, prec=0):
+    if w.shape[2] != m:
+        raise RuntimeError(f"weights keep {w.shape[2]} modes, the call says {m}")
+    if not halve_dc:
+        raise RuntimeError("the reference's SpectralConv1d halves the DC bin (FNOModules.py:51-52); halve_dc=False is not built")
+    return _OPS.spectral_conv_forward(x, w, None, prec, _wants_grad(x, w))[0]
+
+
+_define_composite("spectral_conv2d", "(Tensor x, Tensor w1, Tensor w2, int m1, int m2, int prec=0) -> Tensor", _spectral_conv2d)
+_define_composite("spectral_conv1d", "(Tensor x, Tensor w, int m, bool halve_dc=True, int prec=0) -> Tensor", _spectral_conv1d)
+
+
+def spectral_conv(x: torch.Tensor, w1: torch.Tensor, w2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """SpectralConv2d.forward (x [B,C,H,W], w1/w2 real pairs [...,2] or complex64) or, with ``w2=None``,
+    SpectralConv1d.forward (x [B,C,N], w1 complex64 [Ci,Co,m]; DC bin halved as in the reference)."""
+    if w2 is not None:
+        return _OPS.spectral_conv2d(x, w1, w2, w1.shape[2], w1.shape[3])
+    return _OPS.spectral_conv1d(x, w1, w1.shape[2])
 
 
 # ---------------------------------------------------------------------------------------------
@@ -128,6 +333,16 @@ class FnoSpec:
         fc1_w, fc1_b, fc2_w, fc2_b = next(it), next(it), next(it), next(it)
         return fc0_w, fc0_b, conv_w, conv_b, w1, w2, fc1_w, fc1_b, fc2_w, fc2_b
 
+    def as_ints(self) -> List[int]:
+        """The ``int[] spec`` argument of the fno_net ops."""
+        return [self.ndim, self.c_in, self.width, self.c_out, self.n_layers, self.modes1, self.modes2, self.hidden, self.prec]
+
+    @staticmethod
+    def from_ints(v: Sequence[int]) -> "FnoSpec":
+        if len(v) != 9:
+            raise RuntimeError("spec must be [ndim, c_in, width, c_out, n_layers, modes1, modes2, hidden, prec]")
+        return FnoSpec(*[int(k) for k in v])
+
 
 def _fill_params(spec: FnoSpec, tensors) -> FnoParams:
     fc0_w, fc0_b, conv_w, conv_b, w1, w2, fc1_w, fc1_b, fc2_w, fc2_b = spec.split(tensors)
@@ -155,137 +370,209 @@ def _make_shape(spec: FnoSpec, images: int, h: int, w: int) -> FnoShape:
     return s
 
 
-class _FnoFn(torch.autograd.Function):
-    """FNO1d/FNO2d.forward (+ optionally the bag mean and detached lift on its output)."""
-
-    @staticmethod
-    def forward(ctx, spec: FnoSpec, x_cl, bags, idx, grid, pool_w0, pool_b0, sink, *params):
-        L = _lib.lib()
-        _need_cuda(x_cl, bags, grid, *params)
-        flat = [_f32c(p.detach()) for p in params]
-        if len(flat) != spec.n_params:
-            raise RuntimeError(f"expected {spec.n_params} parameter tensors, got {len(flat)}")
-        lift = LiftInput()
-        if x_cl is not None:
-            x_cl = _f32c(x_cl.detach())
-            if spec.ndim == 2:
-                images, h, w, cin = x_cl.shape
-            else:
-                (images, w, cin), h = x_cl.shape, 1
-            if cin != spec.c_in:
-                raise RuntimeError(f"input has {cin} features, fc0 expects {spec.c_in}")
-            lift.x_cl = _ptr(x_cl)
-            n_bags = n_keep = 0
-            dev = x_cl.device
+def _lift_input(spec: FnoSpec, x_cl, bags, idx, grid):
+    """-> (LiftInput, keep-alive tensors, images, h, w, n_bags, n_keep, grid_dim, device)"""
+    lift = LiftInput()
+    if x_cl is not None:
+        x_cl = _f32c(x_cl)
+        if x_cl.dim() != spec.ndim + 2:
+            raise RuntimeError(f"FNO{spec.ndim}d expects a channels-last input with {spec.ndim + 2} dims, got {tuple(x_cl.shape)}")
+        if spec.ndim == 2:
+            images, h, w, cin = x_cl.shape
         else:
-            bags, grid = _f32c(bags.detach()), _f32c(grid.detach())
-            if spec.ndim == 2:
-                n_bags, bag_len, h, w = bags.shape
-            else:
-                (n_bags, bag_len, w), h = bags.shape, 1
-            if idx is not None:
-                idx = idx.to(device=bags.device, dtype=torch.int32).contiguous()
-                n_keep = idx.numel()
-            else:
-                n_keep = bag_len
-            gd = grid.shape[-1]
-            if grid.numel() != h * w * gd or 1 + gd != spec.c_in:
-                raise RuntimeError(f"grid shape {tuple(grid.shape)} does not match bags {tuple(bags.shape)}")
-            images = n_bags * n_keep
-            lift.bags, lift.idx, lift.grid = _ptr(bags), _ptr(idx), _ptr(grid)
-            lift.n_bags, lift.bag_len, lift.n_keep, lift.grid_dim = n_bags, bag_len, n_keep, gd
-            dev = bags.device
-        shape = _make_shape(spec, images, h, w)
-        pooled = pool_w0 is not None
+            (images, w, cin), h = x_cl.shape, 1
+        if cin != spec.c_in:
+            raise RuntimeError(f"input has {cin} features, fc0 expects {spec.c_in}")
+        lift.x_cl = _ptr(x_cl)
+        return lift, (x_cl,), images, h, w, 0, 0, 0, x_cl.device
+    if bags is None or grid is None:
+        raise RuntimeError("an FNO net needs x_cl, or bags + grid")
+    bags, grid = _f32c(bags), _f32c(grid)
+    if spec.ndim == 2:
+        n_bags, bag_len, h, w = bags.shape
+    else:
+        (n_bags, bag_len, w), h = bags.shape, 1
+    if idx is not None:
+        idx = idx.to(device=bags.device, dtype=torch.int32).contiguous()
+        n_keep = idx.numel()
+    else:
+        n_keep = bag_len
+    gd = grid.shape[-1]
+    if grid.numel() != h * w * gd or 1 + gd != spec.c_in:
+        raise RuntimeError(f"grid shape {tuple(grid.shape)} does not match bags {tuple(bags.shape)}")
+    lift.bags, lift.idx, lift.grid = _ptr(bags), _ptr(idx), _ptr(grid)
+    lift.n_bags, lift.bag_len, lift.n_keep, lift.grid_dim = n_bags, bag_len, n_keep, gd
+    return lift, (bags, idx, grid), n_bags * n_keep, h, w, n_bags, n_keep, gd, bags.device
+
+
+def _fno_forward_cuda(x_cl, bags, idx, grid, pool_w0, pool_b0, params, spec, save, grad_sink):
+    L = _lib.lib()
+    spec = FnoSpec.from_ints(spec)
+    _need_cuda(x_cl, bags, grid, pool_w0, pool_b0, *params)
+    if len(params) != spec.n_params:
+        raise RuntimeError(f"expected {spec.n_params} parameter tensors, got {len(params)}")
+    flat = [_f32c(p) for p in params]
+    lift, keep, images, h, w, n_bags, n_keep, gd, dev = _lift_input(spec, x_cl, bags, idx, grid)
+    shape = _make_shape(spec, images, h, w)
+    pooled = pool_w0 is not None
+    if pooled:
+        if x_cl is not None or spec.c_out != 1:
+            raise RuntimeError("bag pooling needs the bag input form and a scalar FNO output")
+        pool_w0, pool_b0 = _f32c(pool_w0), _f32c(pool_b0)
+    with torch.cuda.device(dev):
+        ws_bytes = L.bdn_fno_workspace_bytes(C.byref(shape))
+        if ws_bytes == 0 and images > 0:
+            check(-1, "bdn_fno_workspace_bytes")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        z_saved = xs_saved = None
+        if save:
+            z_saved = torch.empty(L.bdn_fno_act_floats(C.byref(shape)), dtype=torch.float32, device=dev)
+            xs_saved = torch.empty(L.bdn_fno_spec_floats(C.byref(shape)), dtype=torch.float32, device=dev)
+        out_shape = (images, shape.out_h, shape.out_w, spec.c_out) if spec.ndim == 2 else (images, shape.out_w, spec.c_out)
+        out = torch.empty(out_shape, dtype=torch.float32, device=dev)
+        cparams = _fill_params(spec, flat)
+        check(L.bdn_fno_forward(C.byref(shape), C.byref(cparams), C.byref(lift), _ptr(out), _ptr(z_saved),
+                                _ptr(xs_saved), _ptr(ws), ws_bytes, _stream()), "bdn_fno_forward")
+        result = out
         if pooled:
-            if x_cl is not None or spec.c_out != 1:
-                raise RuntimeError("bag pooling needs the bag input form and a scalar FNO output")
-            pool_w0, pool_b0 = _f32c(pool_w0.detach()), _f32c(pool_b0.detach())
+            npix = shape.out_h * shape.out_w
+            if npix != h * w:
+                raise RuntimeError("bag pooling needs the FNO output on the input grid (square 2-D grids)")
+            width0 = pool_w0.shape[0]
+            lifted_shape = (n_bags, h, w, width0) if spec.ndim == 2 else (n_bags, w, width0)
+            result = torch.empty(lifted_shape, dtype=torch.float32, device=dev)
+            check(L.bdn_bag_pool_lift_forward(_ptr(out), _ptr(keep[2]), _ptr(pool_w0), _ptr(pool_b0), _ptr(result),
+                                              n_bags, n_keep, npix, gd, width0, _stream()),
+                  "bdn_bag_pool_lift_forward")
+    return result, (z_saved if save else _empty(dev)), (xs_saved if save else _empty(dev))
 
-        need_grad = any(ctx.needs_input_grad)
-        with torch.cuda.device(dev):
-            ws_bytes = L.bdn_fno_workspace_bytes(C.byref(shape))
-            if ws_bytes == 0 and images > 0:
-                check(-1, "bdn_fno_workspace_bytes")
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            z_saved = xs_saved = None
-            if need_grad:
-                z_saved = torch.empty(L.bdn_fno_act_floats(C.byref(shape)), dtype=torch.float32, device=dev)
-                xs_saved = torch.empty(L.bdn_fno_spec_floats(C.byref(shape)), dtype=torch.float32, device=dev)
-            out_shape = (images, shape.out_h, shape.out_w, spec.c_out) if spec.ndim == 2 else (images, shape.out_w, spec.c_out)
-            out = torch.empty(out_shape, dtype=torch.float32, device=dev)
-            cparams = _fill_params(spec, flat)
-            check(L.bdn_fno_forward(C.byref(shape), C.byref(cparams), C.byref(lift), _ptr(out), _ptr(z_saved),
-                                    _ptr(xs_saved), _ptr(ws), ws_bytes, _stream()), "bdn_fno_forward")
-            if pooled:
-                npix = shape.out_h * shape.out_w
-                if npix != h * w:
-                    raise RuntimeError("bag pooling needs the FNO output on the input grid (square 2-D grids)")
-                width0 = pool_w0.shape[0]
-                lifted_shape = (n_bags, h, w, width0) if spec.ndim == 2 else (n_bags, w, width0)
-                lifted = torch.empty(lifted_shape, dtype=torch.float32, device=dev)
-                check(L.bdn_bag_pool_lift_forward(_ptr(out), _ptr(grid), _ptr(pool_w0), _ptr(pool_b0), _ptr(lifted),
-                                                  n_bags, n_keep, npix, gd, width0, _stream()),
-                      "bdn_bag_pool_lift_forward")
-                result = lifted
-            else:
-                result = out
-        ctx.spec, ctx.shape, ctx.lift = spec, shape, lift
-        ctx.keep = (x_cl, bags, idx, grid, pool_w0, flat, z_saved, xs_saved)   # keeps the raw pointers alive
-        ctx.pooled, ctx.n_bags, ctx.n_keep = pooled, n_bags, n_keep
-        ctx.sink = sink
-        ctx.param_meta = [(p.shape, p.is_complex()) for p in params]
-        return result
 
-    @staticmethod
-    def backward(ctx, g):
-        L = _lib.lib()
-        spec, shape, lift = ctx.spec, ctx.shape, ctx.lift
-        x_cl, bags, idx, grid, pool_w0, flat, z_saved, xs_saved = ctx.keep
-        dev = z_saved.device
-        g = _f32c(g)
-        with torch.cuda.device(dev):
-            if ctx.pooled:
-                npix = shape.out_h * shape.out_w
-                gpool = torch.empty(ctx.n_bags * npix, dtype=torch.float32, device=dev)
-                check(L.bdn_bag_pool_lift_backward(_ptr(g), _ptr(pool_w0), _ptr(gpool), ctx.n_bags, npix,
-                                                   lift.grid_dim, pool_w0.shape[0], _stream()),
-                      "bdn_bag_pool_lift_backward")
-                g = gpool
-            sizes = [t.numel() for t in flat]
-            offs, total = slot_layout(sizes)
-            if ctx.sink is not None:
-                # the trainer's flat gradient buffer: kernels accumulate into it, autograd sees no grads
-                if ctx.sink.numel() != total or ctx.sink.dtype != torch.float32 or not ctx.sink.is_contiguous():
-                    raise RuntimeError("gradient sink does not match this net's slot layout")
-                gflat = ctx.sink
-            else:
-                gflat = torch.zeros(total, dtype=torch.float32, device=dev)
-            gviews = [gflat[o:o + n] for o, n in zip(offs, sizes)]
-            cgrads = _fill_params(spec, gviews)
-            gx = None
-            if x_cl is not None and ctx.needs_input_grad[1]:
-                gx = torch.empty_like(x_cl)
-            ws_bytes = L.bdn_fno_workspace_bytes(C.byref(shape))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            cparams = _fill_params(spec, flat)
-            check(L.bdn_fno_backward(C.byref(shape), C.byref(cparams), C.byref(lift), _ptr(g), int(ctx.pooled),
-                                     max(ctx.n_keep, 1), _ptr(z_saved), _ptr(xs_saved), C.byref(cgrads), _ptr(gx),
-                                     _ptr(ws), ws_bytes, _stream()), "bdn_fno_backward")
-        grads = []
-        for view, (shp, is_c), need in zip(gviews, ctx.param_meta, ctx.needs_input_grad[8:]):
-            if not need or ctx.sink is not None:
-                grads.append(None)
-            elif is_c:
-                grads.append(torch.view_as_complex(view.view(*shp, 2)))
-            else:
-                grads.append(view.view(shp))
-        return (None, gx, None, None, None, None, None, None, *grads)
+def _fno_dims(x_cl, bags, idx, spec: FnoSpec):
+    if x_cl is not None:
+        images = x_cl.shape[0]
+        h, w = (x_cl.shape[1], x_cl.shape[2]) if spec.ndim == 2 else (1, x_cl.shape[1])
+        return images, h, w, 0
+    n_keep = idx.numel() if idx is not None else bags.shape[1]
+    h, w = (bags.shape[2], bags.shape[3]) if spec.ndim == 2 else (1, bags.shape[2])
+    return bags.shape[0] * n_keep, h, w, bags.shape[0]
+
+
+def _fno_forward_fake(x_cl, bags, idx, grid, pool_w0, pool_b0, params, spec, save, grad_sink):
+    spec = FnoSpec.from_ints(spec)
+    images, h, w, n_bags = _fno_dims(x_cl, bags, idx, spec)
+    s = _make_shape(spec, images, h, w)
+    ref = x_cl if x_cl is not None else bags
+    if pool_w0 is not None:
+        shp = (n_bags, h, w, pool_w0.shape[0]) if spec.ndim == 2 else (n_bags, w, pool_w0.shape[0])
+    else:
+        shp = (images, s.out_h, s.out_w, spec.c_out) if spec.ndim == 2 else (images, s.out_w, spec.c_out)
+    L = _lib.lib()          # the size queries are host-only
+    nz = L.bdn_fno_act_floats(C.byref(s)) if save else 0
+    nx = L.bdn_fno_spec_floats(C.byref(s)) if save else 0
+    return (ref.new_empty(shp, dtype=torch.float32), ref.new_empty(nz, dtype=torch.float32),
+            ref.new_empty(nx, dtype=torch.float32))
+
+
+def _fno_backward_cuda(g, x_cl, bags, idx, grid, pool_w0, params, z_saved, xs_saved, spec, need_gx, grad_sink):
+    L = _lib.lib()
+    spec = FnoSpec.from_ints(spec)
+    _need_cuda(g, z_saved, xs_saved, *params)
+    flat = [_f32c(p) for p in params]
+    lift, keep, images, h, w, n_bags, n_keep, gd, dev = _lift_input(spec, x_cl, bags, idx, grid)
+    shape = _make_shape(spec, images, h, w)
+    pooled = pool_w0 is not None
+    g = _f32c(g)
+    with torch.cuda.device(dev):
+        if pooled:
+            pool_w0 = _f32c(pool_w0)
+            npix = shape.out_h * shape.out_w
+            gpool = torch.empty(n_bags * npix, dtype=torch.float32, device=dev)
+            check(L.bdn_bag_pool_lift_backward(_ptr(g), _ptr(pool_w0), _ptr(gpool), n_bags, npix, gd,
+                                               pool_w0.shape[0], _stream()), "bdn_bag_pool_lift_backward")
+            g = gpool
+        sizes = [t.numel() for t in flat]
+        offs, total = slot_layout(sizes)
+        if grad_sink is not None:
+            # the trainer's flat gradient buffer: kernels accumulate into it, autograd sees no grads
+            if grad_sink.numel() != total or grad_sink.dtype != torch.float32 or not grad_sink.is_contiguous():
+                raise RuntimeError("gradient sink does not match this net's slot layout")
+            gflat = grad_sink
+        else:
+            gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+        gviews = [gflat[o:o + n] for o, n in zip(offs, sizes)]
+        cgrads = _fill_params(spec, gviews)
+        gx = torch.empty_like(keep[0]) if (x_cl is not None and need_gx) else None
+        ws_bytes = L.bdn_fno_workspace_bytes(C.byref(shape))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        cparams = _fill_params(spec, flat)
+        check(L.bdn_fno_backward(C.byref(shape), C.byref(cparams), C.byref(lift), _ptr(g), int(pooled),
+                                 max(n_keep, 1), _ptr(z_saved), _ptr(xs_saved), C.byref(cgrads), _ptr(gx),
+                                 _ptr(ws), ws_bytes, _stream()), "bdn_fno_backward")
+    return (gx if gx is not None else _empty(dev)), (gflat if grad_sink is None else _empty(dev))
+
+
+def _fno_backward_fake(g, x_cl, bags, idx, grid, pool_w0, params, z_saved, xs_saved, spec, need_gx, grad_sink):
+    sizes = [p.numel() * (2 if p.is_complex() else 1) for p in params]
+    _, total = slot_layout(sizes)
+    gx = torch.empty_like(x_cl, dtype=torch.float32) if (x_cl is not None and need_gx) else g.new_empty(0)
+    return gx, g.new_empty(total if grad_sink is None else 0, dtype=torch.float32)
+
+
+_define("fno_net_forward",
+        "(Tensor? x_cl, Tensor? bags, Tensor? idx, Tensor? grid, Tensor? pool_w0, Tensor? pool_b0, Tensor[] params, "
+        "int[] spec, bool save, Tensor? grad_sink) -> (Tensor, Tensor, Tensor)", _fno_forward_cuda, _fno_forward_fake)
+_define("fno_net_backward",
+        "(Tensor g, Tensor? x_cl, Tensor? bags, Tensor? idx, Tensor? grid, Tensor? pool_w0, Tensor[] params, "
+        "Tensor z_saved, Tensor xs_saved, int[] spec, bool need_gx, Tensor(a!)? grad_sink) -> (Tensor, Tensor)",
+        _fno_backward_cuda, _fno_backward_fake)
+
+
+def _fno_setup(ctx, inputs, output):
+    x_cl, bags, idx, grid, pool_w0, pool_b0, params, spec, save, grad_sink = inputs
+    ctx.set_materialize_grads(False)
+    ctx.mark_non_differentiable(output[1], output[2])
+    ctx.n_params = len(params)
+    ctx.save_for_backward(output[1], output[2], x_cl, bags, idx, grid, pool_w0, *params)
+    ctx.spec, ctx.saved_acts = list(spec), save
+    ctx.sink = grad_sink      # mutated by the backward kernels: deliberately not a saved (version-checked) tensor
+
+
+def _fno_bwd(ctx, g, _gz, _gxs):
+    none = (None, None, None, None, None, None, [None] * ctx.n_params, None, None, None)
+    if g is None:
+        return none
+    if not ctx.saved_acts:
+        raise RuntimeError("fno_net_forward was called with save=False; it cannot be differentiated")
+    z_saved, xs_saved, x_cl, bags, idx, grid, pool_w0, *params = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    need_gx = bool(x_cl is not None and need[0])
+    gx, gflat = _OPS.fno_net_backward(g, x_cl, bags, idx, grid, pool_w0, params, z_saved, xs_saved, ctx.spec, need_gx, ctx.sink)
+    grads: List[Optional[torch.Tensor]] = [None] * ctx.n_params
+    if ctx.sink is None:
+        sizes = [p.numel() * (2 if p.is_complex() else 1) for p in params]
+        offs, _ = slot_layout(sizes)
+        for k, (p, o, n) in enumerate(zip(params, offs, sizes)):
+            if need[6][k]:
+                grads[k] = _like_param(gflat[o:o + n], p)
+    return (gx if need_gx else None, None, None, None, None, None, grads, None, None, None)
+
+
+torch.library.register_autograd(f"{NS}::fno_net_forward", _fno_bwd, setup_context=_fno_setup, lib=_LIB)
+
+
+def _fno_net(x_cl, bags, idx, grid, pool_w0, pool_b0, params, spec, grad_sink=None):
+    save = _wants_grad(x_cl, *params)
+    return _OPS.fno_net_forward(x_cl, bags, idx, grid, pool_w0, pool_b0, params, spec, save, grad_sink)[0]
+
+
+_define_composite("fno_net",
+                  "(Tensor? x_cl, Tensor? bags, Tensor? idx, Tensor? grid, Tensor? pool_w0, Tensor? pool_b0, "
+                  "Tensor[] params, int[] spec, Tensor? grad_sink=None) -> Tensor", _fno_net)
 
 
 def fno_apply(spec: FnoSpec, params: Sequence[torch.Tensor], *, x_cl=None, bags=None, idx=None, grid=None,
               pool=None, grad_sink=None) -> torch.Tensor:
-    """Run one FNO net.
+    """Run one FNO net (``torch.ops.blindno_b200.fno_net``).
 
     ``x_cl``: channels-last input [images, (h,) w, c_in]; or ``bags`` [B, L0, (h,) w] + ``grid`` [(h,) w, d]
     (+ optional int ``idx`` of kept snapshots) for the per-snapshot NIO-FNO encoder, whose input
@@ -296,118 +583,393 @@ def fno_apply(spec: FnoSpec, params: Sequence[torch.Tensor], *, x_cl=None, bags=
     buffer in one call) and autograd receives no parameter gradients.
     """
     pw, pb = pool if pool is not None else (None, None)
-    return _FnoFn.apply(spec, x_cl, bags, idx, grid, pw, pb, grad_sink, *params)
+    return _OPS.fno_net(x_cl, bags, idx, grid, pw, pb, list(params), spec.as_ints(), grad_sink)
 
 
 # ---------------------------------------------------------------------------------------------
-# one spectral convolution
+# single stages: lift, layer body, projection
 # ---------------------------------------------------------------------------------------------
-class _SpectralFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, w1, w2, ndim):
-        L = _lib.lib()
-        _need_cuda(x, w1, w2)
-        xc, w1c = _f32c(x.detach()), _f32c(w1.detach())
-        w2c = _f32c(w2.detach()) if w2 is not None else None
-        s = SpectralShape()
-        s.ndim, s.prec = ndim, PREC_FP32
-        if ndim == 2:
-            s.images, s.c_in, s.hp, s.wp = xc.shape
-            ci, s.c_out, s.m1, s.m2 = w1c.shape[:4]
-        else:
-            (s.images, s.c_in, s.wp), s.hp, s.m1 = xc.shape, 1, 0
-            ci, s.c_out, s.m2 = w1c.shape[:3]
-        if ci != s.c_in:
-            raise RuntimeError(f"weights expect {ci} input channels, x has {s.c_in}")
-        dev = xc.device
-        with torch.cuda.device(dev):
-            ws_bytes = L.bdn_spectral_workspace_bytes(C.byref(s))
-            if ws_bytes == 0:
-                check(-1, "bdn_spectral_workspace_bytes")
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            K = 2 * s.m1 if ndim == 2 else 1
-            xs = torch.empty(s.images * s.c_in * K * s.m2 * 2, dtype=torch.float32, device=dev) \
-                if any(ctx.needs_input_grad) else None
-            y = torch.empty((s.images, s.c_out) + tuple(xc.shape[2:]), dtype=torch.float32, device=dev)
-            check(L.bdn_spectral_forward(C.byref(s), _ptr(xc), _ptr(w1c), _ptr(w2c), _ptr(y), _ptr(xs), _ptr(ws),
-                                         ws_bytes, _stream()), "bdn_spectral_forward")
-        ctx.s, ctx.keep = s, (w1c, w2c, xs)
-        ctx.meta = (w1.shape, w1.is_complex())
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        L = _lib.lib()
-        s = ctx.s
-        w1c, w2c, xs = ctx.keep
-        gy = _f32c(gy)
-        dev = gy.device
-        with torch.cuda.device(dev):
-            ws_bytes = L.bdn_spectral_workspace_bytes(C.byref(s))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            gx = torch.empty((s.images, s.c_in) + tuple(gy.shape[2:]), dtype=torch.float32, device=dev) \
-                if ctx.needs_input_grad[0] else None
-            gw1 = torch.empty_like(w1c)
-            gw2 = torch.empty_like(w2c) if w2c is not None else None
-            check(L.bdn_spectral_backward(C.byref(s), _ptr(gy), _ptr(xs), _ptr(w1c), _ptr(w2c), _ptr(gx), _ptr(gw1),
-                                          _ptr(gw2), _ptr(ws), ws_bytes, _stream()), "bdn_spectral_backward")
-        shp, is_c = ctx.meta
-        if is_c:
-            gw1 = torch.view_as_complex(gw1)
-            gw2 = torch.view_as_complex(gw2) if gw2 is not None else None
-        return gx, gw1, gw2, None
+def _stage_shape(ndim, images, *, c_in=1, width=1, c_out=1, hidden=1, h=1, w=1, hp=1, wp=1, out_h=1, out_w=1, m1=None,
+                 m2=1, prec=0) -> FnoShape:
+    s = FnoShape()
+    s.ndim, s.images, s.c_in, s.width, s.c_out, s.hidden, s.n_layers = ndim, images, c_in, width, c_out, hidden, 1
+    s.h, s.w, s.hp, s.wp, s.out_h, s.out_w = h, w, hp, wp, out_h, out_w
+    s.m1 = (1 if ndim == 2 else 0) if m1 is None else m1
+    s.m2, s.prec = m2, prec
+    return s
 
 
-def spectral_conv(x: torch.Tensor, w1: torch.Tensor, w2: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """SpectralConv2d.forward (x [B,C,H,W], w1/w2 real pairs [...,2] or complex64) or, with ``w2=None``,
-    SpectralConv1d.forward (x [B,C,N], w1 complex64 [Ci,Co,m]; DC bin halved as in the reference)."""
-    return _SpectralFn.apply(x, w1, w2, 2 if w2 is not None else 1)
+def _lift_shape(x_cl, fc0_w, ndim):
+    if ndim not in (1, 2) or x_cl.dim() != ndim + 2:
+        raise RuntimeError(f"fno_lift_pad: ndim={ndim} needs a channels-last input with {ndim + 2} dims, got {tuple(x_cl.shape)}")
+    if ndim == 2:
+        images, h, w, cin = x_cl.shape
+        hp = h + pad_amount(h)
+    else:
+        (images, w, cin), h, hp = x_cl.shape, 1, 1
+    width = fc0_w.shape[0]
+    if fc0_w.shape[1] != cin:
+        raise RuntimeError(f"input has {cin} features, fc0 expects {fc0_w.shape[1]}")
+    wp = w + pad_amount(w)
+    return images, h, w, hp, wp, cin, width
+
+
+def _lift_cuda(x_cl, fc0_w, fc0_b, ndim):
+    _need_cuda(x_cl, fc0_w, fc0_b)
+    x, w0, b0 = _f32c(x_cl), _f32c(fc0_w), _f32c(fc0_b)
+    images, h, w, hp, wp, cin, width = _lift_shape(x, w0, ndim)
+    s = _stage_shape(ndim, images, c_in=cin, width=width, h=h, w=w, hp=hp, wp=wp, out_h=hp, out_w=wp)
+    lift = LiftInput()
+    lift.x_cl = _ptr(x)
+    z0 = torch.empty((images, width, hp, wp) if ndim == 2 else (images, width, wp), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().bdn_stage_lift_forward(C.byref(s), _ptr(w0), _ptr(b0), C.byref(lift), _ptr(z0), _stream()),
+              "bdn_stage_lift_forward")
+    return z0
+
+
+def _lift_fake(x_cl, fc0_w, fc0_b, ndim):
+    images, h, w, hp, wp, cin, width = _lift_shape(x_cl, fc0_w, ndim)
+    return x_cl.new_empty((images, width, hp, wp) if ndim == 2 else (images, width, wp), dtype=torch.float32)
+
+
+def _lift_backward_cuda(gz0, x_cl, fc0_w, fc0_b, ndim, need_gx):
+    _need_cuda(gz0, x_cl, fc0_w, fc0_b)
+    g, x, w0, b0 = _f32c(gz0), _f32c(x_cl), _f32c(fc0_w), _f32c(fc0_b)
+    images, h, w, hp, wp, cin, width = _lift_shape(x, w0, ndim)
+    s = _stage_shape(ndim, images, c_in=cin, width=width, h=h, w=w, hp=hp, wp=wp, out_h=hp, out_w=wp)
+    lift = LiftInput()
+    lift.x_cl = _ptr(x)
+    gw, gb = torch.zeros_like(w0), torch.zeros_like(b0)
+    gx = torch.empty_like(x) if need_gx else None
+    with torch.cuda.device(x.device):
+        check(_lib.lib().bdn_stage_lift_backward(C.byref(s), _ptr(w0), _ptr(b0), C.byref(lift), _ptr(g), _ptr(gw), _ptr(gb),
+                                                 _ptr(gx), _stream()), "bdn_stage_lift_backward")
+    return (gx if gx is not None else _empty(x.device)), gw, gb
+
+
+_define("fno_lift_pad", "(Tensor x_cl, Tensor fc0_w, Tensor fc0_b, int ndim) -> Tensor", _lift_cuda, _lift_fake)
+_define("fno_lift_pad_backward",
+        "(Tensor gz0, Tensor x_cl, Tensor fc0_w, Tensor fc0_b, int ndim, bool need_gx) -> (Tensor, Tensor, Tensor)",
+        _lift_backward_cuda,
+        lambda gz0, x_cl, fc0_w, fc0_b, ndim, need_gx: (torch.empty_like(x_cl) if need_gx else gz0.new_empty(0),
+                                                       torch.empty_like(fc0_w), torch.empty_like(fc0_b)))
+
+
+def _lift_setup(ctx, inputs, output):
+    x_cl, fc0_w, fc0_b, ndim = inputs
+    ctx.save_for_backward(x_cl, fc0_w, fc0_b)
+    ctx.ndim = ndim
+
+
+def _lift_bwd(ctx, gz0):
+    x_cl, fc0_w, fc0_b = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    gx, gw, gb = _OPS.fno_lift_pad_backward(gz0, x_cl, fc0_w, fc0_b, ctx.ndim, need[0])
+    return gx if need[0] else None, gw if need[1] else None, gb if need[2] else None, None
+
+
+torch.library.register_autograd(f"{NS}::fno_lift_pad", _lift_bwd, setup_context=_lift_setup, lib=_LIB)
+
+
+def fno_lift_pad(x_cl, fc0_w, fc0_b, ndim: int):
+    """fc0 + channels-first + zero pad round(n/4): x_cl [images,(h,)w,c_in] -> z0 [images,width,(hp,)wp]."""
+    return _OPS.fno_lift_pad(x_cl, fc0_w, fc0_b, ndim)
+
+
+def _layer_shape(z, w1, w2, prec):
+    ndim = 2 if w2 is not None else 1
+    if z.dim() != ndim + 2:
+        raise RuntimeError(f"fno_layer{ndim}d expects z with {ndim + 2} dims, got {tuple(z.shape)}")
+    images, width = z.shape[0], z.shape[1]
+    hp, wp = (z.shape[2], z.shape[3]) if ndim == 2 else (1, z.shape[2])
+    if w1.shape[0] != width or w1.shape[1] != width:
+        raise RuntimeError(f"spectral weights are {tuple(w1.shape[:2])}, z has {width} channels")
+    m1, m2 = (w1.shape[2], w1.shape[3]) if ndim == 2 else (0, w1.shape[2])
+    s = _stage_shape(ndim, images, c_in=width, width=width, h=hp, w=wp, hp=hp, wp=wp, out_h=hp, out_w=wp, m1=m1, m2=m2, prec=prec)
+    K = 2 * m1 if ndim == 2 else 1
+    return s, images * width * K * m2 * 2
+
+
+def _layer_forward_cuda(z, w1, w2, conv_w, conv_b, gelu_in, prec, save):
+    L = _lib.lib()
+    _need_cuda(z, w1, w2, conv_w, conv_b)
+    zc, w1c, cw, cb = _f32c(z), _f32c(w1), _f32c(conv_w), _f32c(conv_b)
+    w2c = _f32c(w2) if w2 is not None else None
+    s, nxs = _layer_shape(zc, w1c, w2c, prec)
+    dev = zc.device
+    with torch.cuda.device(dev):
+        ws_bytes = L.bdn_stage_layer_workspace_bytes(C.byref(s))
+        if ws_bytes == 0:
+            check(-1, "bdn_stage_layer_workspace_bytes")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        xs = torch.empty(nxs, dtype=torch.float32, device=dev) if save else None
+        out = torch.empty_like(zc)
+        check(L.bdn_stage_layer_forward(C.byref(s), _ptr(zc), int(gelu_in), _ptr(w1c), _ptr(w2c), _ptr(cw), _ptr(cb),
+                                        _ptr(out), _ptr(xs), _ptr(ws), ws_bytes, _stream()), "bdn_stage_layer_forward")
+    return out, (xs if save else _empty(dev))
+
+
+def _layer_forward_fake(z, w1, w2, conv_w, conv_b, gelu_in, prec, save):
+    _, nxs = _layer_shape(z, torch.view_as_real(w1) if w1.is_complex() else w1, w2, prec)
+    return torch.empty_like(z), z.new_empty(nxs if save else 0)
+
+
+def _layer_backward_cuda(gz_out, z, xs, w1, w2, conv_w, gelu_in, prec):
+    L = _lib.lib()
+    _need_cuda(gz_out, z, xs, w1, w2, conv_w)
+    g, zc, w1c, cw = _f32c(gz_out), _f32c(z), _f32c(w1), _f32c(conv_w)
+    w2c = _f32c(w2) if w2 is not None else None
+    s, _ = _layer_shape(zc, w1c, w2c, prec)
+    dev = zc.device
+    with torch.cuda.device(dev):
+        ws_bytes = L.bdn_stage_layer_workspace_bytes(C.byref(s))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        gz_in = torch.empty_like(zc)
+        gw1 = torch.zeros_like(w1c)
+        gw2 = torch.zeros_like(w2c) if w2c is not None else None
+        gcw = torch.zeros_like(cw)
+        gcb = torch.zeros(cw.shape[0], dtype=torch.float32, device=dev)
+        check(L.bdn_stage_layer_backward(C.byref(s), _ptr(g), _ptr(zc), int(gelu_in), _ptr(xs), _ptr(w1c), _ptr(w2c),
+                                         _ptr(cw), _ptr(gz_in), _ptr(gw1), _ptr(gw2), _ptr(gcw), _ptr(gcb), _ptr(ws),
+                                         ws_bytes, _stream()), "bdn_stage_layer_backward")
+    return (gz_in, _like_param(gw1, w1), _like_param(gw2, w2) if w2 is not None else _empty(dev),
+            gcw.view(conv_w.shape), gcb)
+
+
+_define("fno_layer_forward",
+        "(Tensor z, Tensor w1, Tensor? w2, Tensor conv_w, Tensor conv_b, bool gelu_in, int prec, bool save) -> (Tensor, Tensor)",
+        _layer_forward_cuda, _layer_forward_fake)
+_define("fno_layer_backward",
+        "(Tensor gz_out, Tensor z, Tensor xs, Tensor w1, Tensor? w2, Tensor conv_w, bool gelu_in, int prec) -> "
+        "(Tensor, Tensor, Tensor, Tensor, Tensor)", _layer_backward_cuda,
+        lambda gz_out, z, xs, w1, w2, conv_w, gelu_in, prec: (
+            torch.empty_like(z), torch.empty_like(w1), torch.empty_like(w2) if w2 is not None else z.new_empty(0),
+            torch.empty_like(conv_w), z.new_empty(conv_w.shape[0])))
+
+
+def _layer_setup(ctx, inputs, output):
+    z, w1, w2, conv_w, conv_b, gelu_in, prec, save = inputs
+    ctx.set_materialize_grads(False)
+    ctx.mark_non_differentiable(output[1])
+    ctx.save_for_backward(z, output[1], w1, w2, conv_w)
+    ctx.gelu_in, ctx.prec, ctx.saved_spectrum = gelu_in, prec, save
+
+
+def _layer_bwd(ctx, gz_out, _gxs):
+    if gz_out is None:
+        return (None,) * 8
+    if not ctx.saved_spectrum:
+        raise RuntimeError("fno_layer_forward was called with save=False; it cannot be differentiated")
+    z, xs, w1, w2, conv_w = ctx.saved_tensors
+    gz, gw1, gw2, gcw, gcb = _OPS.fno_layer_backward(gz_out, z, xs, w1, w2, conv_w, ctx.gelu_in, ctx.prec)
+    need = ctx.needs_input_grad
+    return (gz if need[0] else None, gw1 if need[1] else None, gw2 if (w2 is not None and need[2]) else None,
+            gcw if need[3] else None, gcb if need[4] else None, None, None, None)
+
+
+torch.library.register_autograd(f"{NS}::fno_layer_forward", _layer_bwd, setup_context=_layer_setup, lib=_LIB)
+
+
+def _fno_layer2d(z, w1, w2, conv_w, conv_b, gelu_in, prec=0):
+    return _OPS.fno_layer_forward(z, w1, w2, conv_w, conv_b, gelu_in, prec, _wants_grad(z, w1, w2, conv_w, conv_b))[0]
+
+
+def _fno_layer1d(z, w, conv_w, conv_b, gelu_in, prec=0):
+    return _OPS.fno_layer_forward(z, w, None, conv_w, conv_b, gelu_in, prec, _wants_grad(z, w, conv_w, conv_b))[0]
+
+
+_define_composite("fno_layer2d", "(Tensor z, Tensor w1, Tensor w2, Tensor conv_w, Tensor conv_b, bool gelu_in, int prec=0) -> Tensor",
+                  _fno_layer2d)
+_define_composite("fno_layer1d", "(Tensor z, Tensor w, Tensor conv_w, Tensor conv_b, bool gelu_in, int prec=0) -> Tensor",
+                  _fno_layer1d)
+
+
+def fno_layer(z, w1, w2, conv_w, conv_b, gelu_in: bool, prec: int = PREC_FP32):
+    """One layer body on pre-activation tensors: ``spectral(a) + conv1x1(a) + b`` with ``a = gelu(z)`` if
+    ``gelu_in`` else ``z`` (the reference's ``x = gelu(spectral(x) + conv(x))`` with the GELU moved to the
+    consumer; no GELU follows the last layer)."""
+    if w2 is not None:
+        return _OPS.fno_layer2d(z, w1, w2, conv_w, conv_b, gelu_in, prec)
+    return _OPS.fno_layer1d(z, w1, conv_w, conv_b, gelu_in, prec)
+
+
+def _project_shape(z, fc1_w, fc2_w, out_h, out_w):
+    ndim = z.dim() - 2
+    if ndim not in (1, 2):
+        raise RuntimeError(f"fno_project expects z [images, width, (hp,) wp], got {tuple(z.shape)}")
+    images, width = z.shape[0], z.shape[1]
+    hp, wp = (z.shape[2], z.shape[3]) if ndim == 2 else (1, z.shape[2])
+    if ndim == 1 and out_h != 1:
+        raise RuntimeError("1-D projection needs out_h = 1")
+    if fc1_w.shape[1] != width or fc2_w.shape[1] != fc1_w.shape[0]:
+        raise RuntimeError("fc1 / fc2 shapes do not match z")
+    s = _stage_shape(ndim, images, c_in=width, width=width, c_out=fc2_w.shape[0], hidden=fc1_w.shape[0], h=hp, w=wp, hp=hp,
+                     wp=wp, out_h=out_h, out_w=out_w)
+    out_shape = (images, out_h, out_w, fc2_w.shape[0]) if ndim == 2 else (images, out_w, fc2_w.shape[0])
+    return s, out_shape
+
+
+def _project_cuda(z, fc1_w, fc1_b, fc2_w, fc2_b, out_h, out_w):
+    _need_cuda(z, fc1_w, fc1_b, fc2_w, fc2_b)
+    zc, w1, b1, w2, b2 = (_f32c(t) for t in (z, fc1_w, fc1_b, fc2_w, fc2_b))
+    s, out_shape = _project_shape(zc, w1, w2, out_h, out_w)
+    out = torch.empty(out_shape, dtype=torch.float32, device=zc.device)
+    with torch.cuda.device(zc.device):
+        check(_lib.lib().bdn_stage_project_forward(C.byref(s), _ptr(zc), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(out),
+                                                   _stream()), "bdn_stage_project_forward")
+    return out
+
+
+def _project_backward_cuda(g, z, fc1_w, fc1_b, fc2_w, fc2_b, out_h, out_w, n_keep):
+    _need_cuda(g, z, fc1_w, fc1_b, fc2_w, fc2_b)
+    gc, zc, w1, b1, w2, b2 = (_f32c(t) for t in (g, z, fc1_w, fc1_b, fc2_w, fc2_b))
+    s, out_shape = _project_shape(zc, w1, w2, out_h, out_w)
+    pooled = n_keep > 0          # g is the gradient of the bag mean: [images / n_keep, ...]
+    gz = torch.empty_like(zc)
+    gw1, gb1, gw2, gb2 = (torch.zeros_like(t) for t in (w1, b1, w2, b2))
+    with torch.cuda.device(zc.device):
+        check(_lib.lib().bdn_stage_project_backward(C.byref(s), _ptr(zc), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(gc),
+                                                    int(pooled), max(n_keep, 1), _ptr(gz), _ptr(gw1), _ptr(gb1), _ptr(gw2),
+                                                    _ptr(gb2), _stream()), "bdn_stage_project_backward")
+    return gz, gw1, gb1, gw2, gb2
+
+
+_define("fno_project", "(Tensor z, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w, Tensor fc2_b, int out_h, int out_w) -> Tensor",
+        _project_cuda,
+        lambda z, fc1_w, fc1_b, fc2_w, fc2_b, out_h, out_w: z.new_empty(_project_shape(z, fc1_w, fc2_w, out_h, out_w)[1]))
+_define("fno_project_backward",
+        "(Tensor g, Tensor z, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w, Tensor fc2_b, int out_h, int out_w, int n_keep) -> "
+        "(Tensor, Tensor, Tensor, Tensor, Tensor)", _project_backward_cuda,
+        lambda g, z, fc1_w, fc1_b, fc2_w, fc2_b, out_h, out_w, n_keep: tuple(
+            torch.empty_like(t) for t in (z, fc1_w, fc1_b, fc2_w, fc2_b)))
+
+
+def _project_setup(ctx, inputs, output):
+    z, fc1_w, fc1_b, fc2_w, fc2_b, out_h, out_w = inputs
+    ctx.save_for_backward(z, fc1_w, fc1_b, fc2_w, fc2_b)
+    ctx.crop = (out_h, out_w)
+
+
+def _project_bwd(ctx, g):
+    z, fc1_w, fc1_b, fc2_w, fc2_b = ctx.saved_tensors
+    grads = _OPS.fno_project_backward(g, z, fc1_w, fc1_b, fc2_w, fc2_b, ctx.crop[0], ctx.crop[1], 0)
+    return (*[gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[:5])], None, None)
+
+
+torch.library.register_autograd(f"{NS}::fno_project", _project_bwd, setup_context=_project_setup, lib=_LIB)
+
+
+def fno_project(z, fc1_w, fc1_b, fc2_w, fc2_b, out_h: int, out_w: int):
+    """crop + fc1 + exact GELU + fc2: z [images,width,(hp,)wp] -> [images,(out_h,)out_w,c_out]."""
+    return _OPS.fno_project(z, fc1_w, fc1_b, fc2_w, fc2_b, out_h, out_w)
 
 
 # ---------------------------------------------------------------------------------------------
-# bag mean + detached lift on its own (the NIO models feed it DeepONet outputs)
+# bag mean + detached lift (the NIO models feed it DeepONet outputs), and the two pooled tails
 # ---------------------------------------------------------------------------------------------
-class _PoolLiftFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, s, grid, w0, b0):
-        L = _lib.lib()
-        _need_cuda(s, grid, w0, b0)
-        sc, gc, w0c, b0c = _f32c(s.detach()), _f32c(grid.detach()), _f32c(w0.detach()), _f32c(b0.detach())
-        n_bags, n_keep = sc.shape[:2]
-        gshape = tuple(sc.shape[2:])
-        npix = 1
-        for d in gshape:
-            npix *= d
-        gd, width = gc.shape[-1], w0c.shape[0]
-        out = torch.empty((n_bags,) + gshape + (width,), dtype=torch.float32, device=sc.device)
-        with torch.cuda.device(sc.device):
-            check(L.bdn_bag_pool_lift_forward(_ptr(sc), _ptr(gc), _ptr(w0c), _ptr(b0c), _ptr(out), n_bags, n_keep,
-                                              npix, gd, width, _stream()), "bdn_bag_pool_lift_forward")
-        ctx.keep, ctx.dims = (w0c,), (n_bags, n_keep, npix, gd, width, tuple(sc.shape))
-        return out
+def _pool_dims(s, grid, w0):
+    n_bags, n_keep = s.shape[:2]
+    gshape = tuple(s.shape[2:])
+    npix = 1
+    for d in gshape:
+        npix *= d
+    return n_bags, n_keep, gshape, npix, grid.shape[-1], w0.shape[0]
 
-    @staticmethod
-    def backward(ctx, g):
-        L = _lib.lib()
-        (w0c,) = ctx.keep
-        n_bags, n_keep, npix, gd, width, sshape = ctx.dims
-        g = _f32c(g)
-        gpool = torch.empty(n_bags * npix, dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
-            check(L.bdn_bag_pool_lift_backward(_ptr(g), _ptr(w0c), _ptr(gpool), n_bags, npix, gd, width, _stream()),
-                  "bdn_bag_pool_lift_backward")
-        gs = (gpool.view(n_bags, 1, npix) / n_keep).expand(n_bags, n_keep, npix).reshape(sshape)
-        return gs, None, None, None
+
+def _pool_lift_cuda(s, grid, w0, b0):
+    _need_cuda(s, grid, w0, b0)
+    sc, gc, w0c, b0c = _f32c(s), _f32c(grid), _f32c(w0), _f32c(b0)
+    n_bags, n_keep, gshape, npix, gd, width = _pool_dims(sc, gc, w0c)
+    out = torch.empty((n_bags,) + gshape + (width,), dtype=torch.float32, device=sc.device)
+    with torch.cuda.device(sc.device):
+        check(_lib.lib().bdn_bag_pool_lift_forward(_ptr(sc), _ptr(gc), _ptr(w0c), _ptr(b0c), _ptr(out), n_bags, n_keep,
+                                                   npix, gd, width, _stream()), "bdn_bag_pool_lift_forward")
+    return out
+
+
+def _pool_lift_backward_cuda(g, w0, grid_dim):
+    _need_cuda(g, w0)
+    gc, w0c = _f32c(g), _f32c(w0)
+    n_bags, width = gc.shape[0], w0c.shape[0]
+    npix = gc.numel() // max(n_bags * width, 1)
+    gpool = torch.empty(n_bags, npix, dtype=torch.float32, device=gc.device)
+    with torch.cuda.device(gc.device):
+        check(_lib.lib().bdn_bag_pool_lift_backward(_ptr(gc), _ptr(w0c), _ptr(gpool), n_bags, npix, grid_dim, width,
+                                                    _stream()), "bdn_bag_pool_lift_backward")
+    return gpool
+
+
+_define("bag_pool_lift", "(Tensor s, Tensor grid, Tensor fc0_w, Tensor fc0_b) -> Tensor", _pool_lift_cuda,
+        lambda s, grid, w0, b0: s.new_empty((s.shape[0],) + tuple(s.shape[2:]) + (w0.shape[0],)))
+_define("bag_pool_lift_backward", "(Tensor g, Tensor fc0_w, int grid_dim) -> Tensor", _pool_lift_backward_cuda,
+        lambda g, w0, grid_dim: g.new_empty(g.shape[0], g.numel() // max(g.shape[0] * w0.shape[0], 1)))
+
+
+def _pool_setup(ctx, inputs, output):
+    s, grid, w0, b0 = inputs
+    ctx.save_for_backward(w0)
+    ctx.s_shape, ctx.grid_dim = tuple(s.shape), grid.shape[-1]
+
+
+def _pool_bwd(ctx, g):
+    (w0,) = ctx.saved_tensors
+    if not ctx.needs_input_grad[0]:
+        return None, None, None, None
+    n_bags, n_keep = ctx.s_shape[:2]
+    gpool = _OPS.bag_pool_lift_backward(g, w0, ctx.grid_dim)
+    gs = (gpool.view(n_bags, 1, -1) / n_keep).expand(n_bags, n_keep, gpool.shape[1]).reshape(ctx.s_shape)
+    return gs, None, None, None       # fc0 is detached in the reference (.data): no gradient, by construction
+
+
+torch.library.register_autograd(f"{NS}::bag_pool_lift", _pool_bwd, setup_context=_pool_setup, lib=_LIB)
 
 
 def bag_pool_lift(s, grid, w0, b0):
     """fc0([grid, mean_l s_l]) with fc0 detached: s [B,L,*g], grid [*g,d] -> [B,*g,width]."""
-    return _PoolLiftFn.apply(s, grid, w0, b0)
+    return _OPS.bag_pool_lift(s, grid, w0, b0)
+
+
+def _bag_project_pool_lift(z, n_keep, fc1_w, fc1_b, fc2_w, fc2_b, grid, fc0_w, fc0_b):
+    """Projection of every snapshot's last activation, bag mean, detached lift (NIO-FNO tail)."""
+    gshape = tuple(grid.shape[:-1])
+    out_h, out_w = (gshape if len(gshape) == 2 else (1, gshape[0]))
+    s = _OPS.fno_project(z, fc1_w, fc1_b, fc2_w, fc2_b, out_h, out_w)          # [B*L, *g, 1]
+    return _OPS.bag_pool_lift(s.reshape(z.shape[0] // n_keep, n_keep, *gshape), grid, fc0_w.detach(), fc0_b.detach())
+
+
+def _deeponet_pool_contract_lift(w, basis, b0, grid, fc0_w, fc0_b):
+    """(mean_l w_l) @ basis^T + b0) / sqrt(p), then the detached lift: by linearity the bag mean is taken on the
+    [B, L, p] branch coefficients, so the [B, L, n_points] DeepONet output is never materialised (NIO tail)."""
+    p = w.shape[-1]
+    pooled = (w.mean(dim=1) @ basis.T + b0) / p ** 0.5                        # [B, n_points]  (library GEMM, K = p)
+    return _OPS.bag_pool_lift(pooled.reshape(w.shape[0], 1, *grid.shape[:-1]), grid, fc0_w.detach(), fc0_b.detach())
+
+
+_define_composite("bag_project_pool_lift",
+                  "(Tensor z, int n_keep, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w, Tensor fc2_b, Tensor grid, Tensor fc0_w, "
+                  "Tensor fc0_b) -> Tensor", _bag_project_pool_lift)
+_define_composite("deeponet_pool_contract_lift",
+                  "(Tensor w, Tensor basis, Tensor b0, Tensor grid, Tensor fc0_w, Tensor fc0_b) -> Tensor",
+                  _deeponet_pool_contract_lift)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused Adam over a flat buffer
+# ---------------------------------------------------------------------------------------------
+def _adam_cuda(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale):
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    with torch.cuda.device(param.device):
+        check(_lib.lib().bdn_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(),
+                                       lr, beta1, beta2, eps, step, grad_scale, _stream()), "bdn_adam_step")
+
+
+_define("adam_step_flat_",
+        "(Tensor(a!) param, Tensor grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, float lr, float beta1, float beta2, "
+        "float eps, int step, float grad_scale) -> ()", _adam_cuda,
+        lambda param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale: None)
 
 
 def adam_step_flat(param, grad, exp_avg, exp_avg_sq, *, lr, betas=(0.9, 0.999), eps=1e-8, step, grad_scale=1.0):
     """torch.optim.Adam's update over one flat fp32 buffer, in place, one kernel."""
-    _need_cuda(param, grad, exp_avg, exp_avg_sq)
-    with torch.cuda.device(param.device):
-        check(_lib.lib().bdn_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(),
-                                       lr, betas[0], betas[1], eps, step, grad_scale, _stream()), "bdn_adam_step")
+    _OPS.adam_step_flat_(param, grad, exp_avg, exp_avg_sq, lr, betas[0], betas[1], eps, step, grad_scale)

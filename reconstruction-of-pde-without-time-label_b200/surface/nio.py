@@ -111,9 +111,8 @@ class _NioMixin(_BagModel):
         u = x.unsqueeze(2) if grid.dim() == 3 else x
         coeff = self.branch(u)                                   # [B, L, p]  (cuDNN conv stack)
         basis = self.trunk(grid_flat)                            # [n_points, p]
-        pooled = (coeff.mean(dim=1) @ basis.T + self.deeponet.b0) / self.deeponet.p ** 0.5
-        lifted = ops.bag_pool_lift(pooled.unsqueeze(1).reshape(x.shape[0], 1, *grid.shape[:-1]), grid,
-                                   self.fc0.weight.data, self.fc0.bias.data)
+        lifted = torch.ops.blindno_b200.deeponet_pool_contract_lift(coeff, basis, self.deeponet.b0, grid,
+                                                                    self.fc0.weight.data, self.fc0.bias.data)
         return self._heads(lifted)
 
 
