@@ -232,5 +232,75 @@ def main():
                                                          "meta.x_seed": np.asarray(16)})
 
 
+def rel_l2(a, b, eps=1e-12):
+    """The metric the reference's eval scripts report (2d_FPE/eval_fno.py:124-128): ||a-b||_2 / (||b||_2 + eps)."""
+    return float(np.linalg.norm((a - b).ravel(), 2) / (np.linalg.norm(b.ravel(), 2) + eps))
+
+
+def end_metric():
+    """The reference's reported end metric on a fixed synthetic problem: drift / diffusion relative L2 error of
+    the de-normalised prediction (2d_FPE/eval_fno.py:72-97, :274-276) at the initial weights and after 6 steps
+    of the reference train loop (2d_FPE/train_fno.py:115-143: Adam 5e-4, MSE, a fresh bag subsample per step)."""
+    torch.set_num_threads(1)
+    g = torch.Generator()
+    N2 = load_reference("2d_FPE", "NIOModules")
+    torch.manual_seed(61)
+    ctor = (2, 3, 100, 25, 2, 6, 5, 2)
+    model = N2.NIOFP2D_FNO(*ctor)
+    n = 20
+    ax = np.linspace(-1, 1, n, dtype=np.float32)
+    grid = torch.tensor(np.stack(np.meshgrid(ax, ax, indexing="ij"), axis=2))
+    # smooth synthetic fields: the targets are fixed functions of the grid modulated per sample
+    xx, yy = grid[..., 0], grid[..., 1]
+    def fields(k):
+        a = torch.randn(k, 1, 1, generator=g)
+        b = torch.randn(k, 1, 1, generator=g)
+        drift = a * torch.sin(3.0 * xx) * torch.cos(2.0 * yy) + 0.5 * b * xx * yy
+        diff = 1.0 + 0.3 * b * torch.cos(2.0 * xx + yy) + 0.1 * a
+        return torch.stack([drift, diff], dim=-1)                      # [k, n, n, 2]
+    g.manual_seed(31)
+    y_train, y_eval = fields(4), fields(3)
+    x_train = torch.randn(4, 60, n, n, generator=g) + y_train[..., 0].unsqueeze(1)
+    x_eval = torch.randn(3, 60, n, n, generator=g) + y_eval[..., 0].unsqueeze(1)
+    stats = dict(drift_mean=np.float32(0.05), drift_std=np.float32(1.7), diff_mean=np.float32(1.0), diff_std=np.float32(0.4))
+
+    def evaluate():
+        model.eval()
+        rows = []
+        with torch.no_grad():
+            for k in range(x_eval.shape[0]):
+                pred = model(x_eval[k:k + 1], grid)
+                truth = y_eval[k].numpy()
+                row = []
+                for c, nm in enumerate(("drift", "diff")):
+                    p_raw = pred[0, ..., c].numpy() * stats[nm + "_std"] + stats[nm + "_mean"]
+                    t_raw = truth[..., c] * stats[nm + "_std"] + stats[nm + "_mean"]
+                    row.append(rel_l2(p_raw, t_raw))
+                rows.append(row)
+        return np.asarray(rows, dtype=np.float64)
+
+    state0 = [(k, v.clone()) for k, v in model.state_dict().items() if not k.startswith("branch.")]
+    metric0 = evaluate()
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    np.random.seed(9)
+    losses = []
+    for step in range(6):
+        opt.zero_grad()
+        loss = torch.nn.functional.mse_loss(model(x_train, grid), y_train)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    metric1 = evaluate()
+    _save("endmetric_2d_fpe", x_train=_np(x_train), y_train=_np(y_train), x_eval=_np(x_eval), y_eval=_np(y_eval),
+          grid=_np(grid), metric0=metric0, metric1=metric1, losses=np.asarray(losses, dtype=np.float64),
+          **{"meta.ctor": np.asarray(ctor), "meta.np_seed": np.asarray(9), "meta.lr": np.asarray(5e-4)},
+          **{"stats." + k: np.asarray(v) for k, v in stats.items()}, **_pack("p.", state0))
+
+
 if __name__ == "__main__":
-    main()
+    if "end_metric" in sys.argv[1:]:
+        end_metric()
+    else:
+        main()
+        end_metric()

@@ -67,3 +67,24 @@ def assert_grads_close(got, want, tol, floor=1e-2):
         err = (g.double() - w.double()).abs().max().item()
         scale = max(w.double().abs().max().item(), floor * gmax)
         assert err <= tol * scale, f"{k}: err {err:.3e} > {tol:.1e} * {scale:.3e}"
+
+
+def rel_l2(a, b, eps=1e-12):
+    """The reference's reported end metric (2d_FPE/eval_fno.py:124-128): ||a-b||_2 / (||b||_2 + eps)."""
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.linalg.norm((a - b).ravel(), 2) / (np.linalg.norm(b.ravel(), 2) + eps))
+
+
+def end_metric(fx, predict):
+    """Drift / diffusion relative L2 of the de-normalised predictions on the fixture's eval set
+    (2d_FPE/eval_fno.py:72-97, :274-276).  ``predict(x[1,L,n,n]) -> [1,n,n,2]`` CPU tensor."""
+    rows = []
+    for k in range(fx.arrays["x_eval"].shape[0]):
+        pred = predict(fx.t("x_eval")[k:k + 1]).detach().cpu().numpy()
+        truth = fx.arrays["y_eval"][k]
+        row = []
+        for c, nm in enumerate(("drift", "diff")):
+            std, mean = fx.arrays[f"stats.{nm}_std"], fx.arrays[f"stats.{nm}_mean"]
+            row.append(rel_l2(pred[0, ..., c] * std + mean, truth[..., c] * std + mean))
+        rows.append(row)
+    return np.asarray(rows)

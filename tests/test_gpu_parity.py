@@ -408,3 +408,51 @@ def test_nio_models_golden(name):
         assert rel_err(got[k].grad, g) < 2e-3, k     # gradients pass through train-mode BatchNorm of tiny batches
     for k in fx.nograd:
         assert got[k].grad is None, k
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's reported end metric (drift / diffusion relative L2, eval_fno.py) is unchanged
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("loop", ["torch_adam", "flat_trainer", "flat_trainer_graphs"])
+def test_end_metric_relative_l2_unchanged(loop):
+    """Fixed synthetic problem, fixture produced by the unmodified reference: the relative L2 errors the eval
+    script reports agree to 6 decimals at the given weights, and after 6 steps of the reference train loop
+    (Adam 5e-4, MSE, a fresh bag per step) -- run with stock torch.optim.Adam on the drop-in module exactly as
+    train_fno.py does, and through FlatTrainer (flat buffers + fused Adam, eager and CUDA-graph replay)."""
+    from blindno_b200.parallel import FlatTrainer
+    from tests.helpers import end_metric
+    fx = Fixture("endmetric_2d_fpe")
+    model = nio.make_models("2d_FPE")["NIOFP2D_FNO"](*[int(v) for v in fx.meta("ctor")])
+    model.load_state_dict(fx.params, strict=False)
+    model = model.to(DEV)
+    grid = fx.t("grid").to(DEV)
+
+    def metric():
+        model.eval()
+        with torch.no_grad():
+            return end_metric(fx, lambda x: model(x.to(DEV), grid))
+
+    m0 = metric()
+    assert np.abs(m0 - fx.arrays["metric0"]).max() < 5e-7
+    assert np.array_equal(np.round(m0, 6), np.round(fx.arrays["metric0"], 6)) or np.abs(m0 - fx.arrays["metric0"]).max() < 2e-7
+
+    model.train()
+    x, y = fx.t("x_train").to(DEV), fx.t("y_train").to(DEV)
+    np.random.seed(int(fx.meta("np_seed")))
+    losses = []
+    if loop == "torch_adam":
+        opt = torch.optim.Adam(model.parameters(), lr=float(fx.meta("lr")))
+        for _ in range(6):
+            opt.zero_grad()
+            loss = torch.nn.functional.mse_loss(model(x, grid), y)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+    else:
+        trainer = FlatTrainer(model, lr=float(fx.meta("lr")))
+        trainer.enable_graphs(loop == "flat_trainer_graphs")
+        for _ in range(6):
+            losses.append(trainer.step(x, grid, y).item())
+    assert np.allclose(losses, fx.arrays["losses"], rtol=2e-5), (losses, fx.arrays["losses"])
+    m1 = metric()
+    assert np.abs(m1 - fx.arrays["metric1"]).max() < 2e-5, (m1, fx.arrays["metric1"])
