@@ -297,6 +297,7 @@ struct CoreParams {
   const float2* t_hk; const float2* t_kh;
   const float* pre; const float* post;
   int ca, cb, co_layer, hp, hp8, m1, m2, K, Kp, TL;
+  int tables_global;     // large hp x K: the DFT tables do not fit shared memory and are read through L1/L2
 };
 
 // G = kept rows (phase 1) / spatial rows (phase 3) accumulated per work item.  Small G gives more
@@ -337,23 +338,25 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
   const int nA = (max(hp * Pa, K * Pb) + 1) & ~1;
   float2* bufA = reinterpret_cast<float2*>(smem);
   float2* bufX = bufA + nA;
-  float2* s_hk = bufX + K * Pa + ((K * Pa) & 1);   // [hp][Kp], 16-byte aligned rows
-  float2* s_kh = s_hk + hp * p.Kp;                 // [K][hp8]
+  float2* tab = bufX + K * Pa + ((K * Pa) & 1);
+  const bool tg = p.tables_global != 0;
+  const float2* s_hk = tg ? p.t_hk : tab;                  // [hp][Kp], 16-byte aligned rows
+  const float2* s_kh = tg ? p.t_kh : tab + hp * p.Kp;      // [K][hp8]
   const int l0 = blockIdx.x * TL, b = blockIdx.y;
   const int tid = threadIdx.x, nt = blockDim.x;
 
   // the two DFT tables live in shared memory for the block's lifetime (they are re-read by every
   // item; from L1/L2 the inner loops were latency-bound: ncu long-scoreboard 20 cycles per issue).
   // Both are contiguous in HBM: two bulk async copies, in flight while phase 0 stages the image.
-  uint64_t* tbar = reinterpret_cast<uint64_t*>(s_kh + K * p.hp8);
+  uint64_t* tbar = reinterpret_cast<uint64_t*>(tab + (tg ? 0 : hp * p.Kp + K * p.hp8));
   pdl_launch_dependents();
-  if (tid == 0) {
+  if (tid == 0 && !tg) {
     mbar_init(tbar, 1);
     mbar_init_fence();
     const uint32_t b1 = (uint32_t)(hp * p.Kp) * 8u, b2 = (uint32_t)(K * p.hp8) * 8u;
     mbar_expect_tx(tbar, b1 + b2);
-    bulk_g2s(s_hk, p.t_hk, b1, tbar);
-    bulk_g2s(s_kh, p.t_kh, b2, tbar);
+    bulk_g2s(tab, p.t_hk, b1, tbar);
+    bulk_g2s(tab + hp * p.Kp, p.t_kh, b2, tbar);
   }
   pdl_wait();      // the tables above are constant plan data; everything below reads the previous kernel's output
   // phase 0: stage the image's TL columns, all channels: bufA[h][a*TL + lt]
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
         l < m2 ? __ldg(p.in + ((size_t)(b * p.ca + a) * hp + h) * m2 + l) : make_float2(0.f, 0.f);
   }
   __syncthreads();          // also publishes the mbarrier init to the waiting threads
-  mbar_wait(tbar, 0);
+  if (!tg) mbar_wait(tbar, 0);
 
   // phase 1: X[k][pa] = pre[l] * sum_h x[h][pa] * e^{-i phi_kh}, G1 kept rows per item
   constexpr int G = G1;
@@ -658,6 +661,8 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
   p.cb = bwd ? ci_layer : co_layer;
   p.co_layer = co_layer;
   p.hp = pl->hp; p.hp8 = pl->hp8; p.m1 = pl->m1; p.m2 = pl->m2; p.K = pl->K; p.Kp = pl->Kp;
+  const size_t table_f2 = (size_t)pl->hp * pl->Kp + (size_t)pl->K * pl->hp8;
+  p.tables_global = table_f2 * sizeof(float2) > 150 * 1024;    // e.g. 160 x 128 or 320 x 64: 327 KB of tables
   // many images: persistent streaming kernel, whole images per block (G1 = 2 kept rows, G3 = 8 rows per item)
   {
     const size_t in_pad = ((size_t)p.ca * pl->hp * pl->m2 + 1) & ~(size_t)1;
@@ -686,7 +691,7 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
     size_t nA = (size_t)((pl->hp * p.ca > pl->K * p.cb) ? pl->hp * p.ca : pl->K * p.cb) * t;
     nA = (nA + 1) & ~(size_t)1;
     const size_t nX = (size_t)pl->K * p.ca * t;
-    return (nA + nX + (nX & 1) + (size_t)pl->hp * pl->Kp + (size_t)pl->K * pl->hp8) * sizeof(float2) + 16;
+    return (nA + nX + (nX & 1) + (p.tables_global ? 0 : table_f2)) * sizeof(float2) + 16;
   };
   int tl = 1;
   for (int parts = 1; parts <= pl->m2; ++parts) {

@@ -146,7 +146,7 @@ def profile_end() -> dict:
 # ---------------------------------------------------------------------------------------------
 # stage_wfwd: one pruned forward DFT (tests, kernel benchmarks)
 # ---------------------------------------------------------------------------------------------
-def _stage_wfwd_cuda(x, m2, hp, m1, act, prec):
+def _stage_wfwd_cuda(x, m2, hp=1, m1=0, act=False, prec=0):     # (the dispatcher drops trailing default arguments)
     _need_cuda(x)
     xc = _f32c(x)
     rows, wp = xc.shape

@@ -106,6 +106,26 @@ def test_spectral_default_head_shape_golden():
     assert rel_err(ops.spectral_conv(x, w1, w2), fx.t("y")) < TOL
 
 
+@pytest.mark.parametrize("hp,wp,m1,m2", [(160, 160, 64, 64), (320, 320, 32, 32), (320, 320, 64, 64), (100, 160, 50, 40)])
+def test_spectral_large_grids_of_the_sweep(hp, wp, m1, m2):
+    """BASELINE.json configs[4] sweeps the grid up to 256 (padded 320) and the modes up to 64: the H-transform
+    tables (hp x 2*m1 complex, twice) no longer fit shared memory there and are read through L1/L2."""
+    torch.manual_seed(hp + m2)
+    C = 3
+    x = torch.randn(2, C, hp, wp)
+    w1, w2 = torch.rand(C, C, m1, m2, 2) / C ** 2, torch.rand(C, C, m1, m2, 2) / C ** 2
+    gy = torch.randn(2, C, hp, wp)
+    xs, w1s, w2s = (t.to(DEV).requires_grad_(True) for t in (x, w1, w2))
+    y = ops.spectral_conv(xs, w1s, w2s)
+    y.backward(gy.to(DEV))
+    ref = [t.double().requires_grad_(True) for t in (x, w1, w2)]
+    want = O.spectral_conv2d(*ref)
+    want.backward(gy.double())
+    assert rel_err(y, want) < TOL
+    for got, r in zip((xs, w1s, w2s), ref):
+        assert rel_err(got.grad, r.grad) < 2e-5
+
+
 def test_spectral_empty_batch_and_bad_modes():
     w = torch.rand(3, 3, 2, 2, 2, device=DEV)
     y = ops.spectral_conv(torch.zeros(0, 3, 8, 8, device=DEV), w, w)
