@@ -11,8 +11,8 @@ to this package without touching the scripts:
   * ``blindno_b200.dropin.install("2d_FPE")`` -- registers the same modules in ``sys.modules``.
 
 Names on the accelerated path resolve to ``blindno_b200.surface`` classes.  Names the scripts import but
-never touch on this path (the BlinDNO U-Net / attention variants, 3-D and ODE leftovers: SURVEY.md
-section 2, out of scope) resolve to placeholders that raise on construction, so imports succeed and a wrong
+never touch on this path (Transolver / plain U-Net variants, 3-D and ODE leftovers: SURVEY.md section 2,
+out of scope) resolve to placeholders that raise on construction, so imports succeed and a wrong
 model choice fails loudly instead of silently running something else.
 """
 from __future__ import annotations
@@ -55,6 +55,8 @@ def exports(variant: str, module: str) -> dict:
         keep = ("NIOFP2D", "NIOFP2D_FNO") if two_d else (
             ("NIOFP", "NIOFP_FNO") if variant == "1d_FPE" else ("NIOFP_schrodinger", "NIOFP_FNO"))
         out = {k: models[k] for k in keep}
+        from ..surface.blindno import make_blindno_models
+        out.update(make_blindno_models(variant))      # BlinDNO family: FNO heads on the accelerated path (8f N1)
     elif module == "DeepONetModules":
         out = {"FFN": deeponet.FFN, "DeepOnetNoBiasOrg": deeponet.DeepOnetNoBiasOrg,
                "kaiming_init": deeponet.kaiming_init, "activation": deeponet.activation}

@@ -298,9 +298,50 @@ def end_metric():
           **{"stats." + k: np.asarray(v) for k, v in stats.items()}, **_pack("p.", state0))
 
 
+def blindno_cases():
+    """BlinDNO models: the reference's PermInvUNet_attn* classes, forward + backward.  The FNO
+    heads are hard-wired to 32 (2-D) / 15 (1-D) modes, so the fixtures store the construction seed and keyword
+    arguments instead of the state_dict, the full gradients of the small tensors and (norm, sum) of the others."""
+    torch.set_num_threads(1)
+    g = torch.Generator()
+
+    def case(name, variant, cls, kwargs, x, seed, train, np_seed=None):
+        mod = load_reference(variant, "NIOModules")
+        torch.manual_seed(seed)
+        model = getattr(mod, cls)(**kwargs)
+        model.train(train)
+        if np_seed is not None:
+            np.random.seed(np_seed)
+        out = model(x)
+        gy = torch.randn(out.shape, generator=torch.Generator().manual_seed(97))
+        out.backward(gy)
+        named = [(k, p) for k, p in model.named_parameters() if p.grad is not None]
+        small = [(k, p.grad) for k, p in named if p.numel() <= 4096]
+        real = lambda t: torch.view_as_real(t) if t.is_complex() else t
+        big = [(k, torch.stack([real(p.grad).double().norm(), real(p.grad).double().sum()])) for k, p in named if p.numel() > 4096]
+        nograd = [k for k, p in model.named_parameters() if p.grad is None]
+        kw = {k: np.asarray(v) for k, v in kwargs.items() if k != "device"}
+        _save(name, x=_np(x), y=_np(out), gy=_np(gy), nograd=np.array(nograd, dtype="U"),
+              **{"meta.variant": np.asarray(variant), "meta.cls": np.asarray(cls), "meta.seed": np.asarray(seed),
+                 "meta.train": np.asarray(train), "meta.np_seed": np.asarray(-1 if np_seed is None else np_seed)},
+              **{"kw." + k: v for k, v in kw.items()}, **_pack("g.", small), **_pack("gnorm.", big))
+
+    case("blindno2d_fpe_train", "2d_FPE", "PermInvUNet_attn", dict(base_ch=2, depth=2, input_size=(52, 52)),
+         torch.randn(1, 53, 52, 52, generator=g.manual_seed(41)), 71, True, np_seed=11)
+    case("blindno2d_nc_eval", "2d_Non_conservative_FPE", "PermInvUNet_attn", dict(base_ch=2, depth=2, input_size=(52, 53)),
+         torch.randn(2, 6, 52, 53, generator=g.manual_seed(42)), 72, False)
+    case("blindno1d_fpe_bag_train", "1d_FPE", "PermInvUNet_attn1D_bag", dict(base_ch=2, depth=3, input_size=45, device="cpu"),
+         torch.randn(2, 54, 45, generator=g.manual_seed(43)), 73, True, np_seed=12)
+    case("blindno1d_gpe_bag_eval", "1d_GPE", "PermInvUNet_attn1D_bag_GPE",
+         dict(base_ch=2, depth=2, input_size=64, device="cpu", width=8, modes=9),
+         torch.randn(2, 6, 64, generator=g.manual_seed(44)), 74, False)
+
+
 if __name__ == "__main__":
-    if "end_metric" in sys.argv[1:]:
-        end_metric()
-    else:
+    wanted = [a for a in sys.argv[1:] if a in ("end_metric", "blindno")]
+    if not wanted:
         main()
+    if not wanted or "end_metric" in wanted:
         end_metric()
+    if not wanted or "blindno" in wanted:
+        blindno_cases()

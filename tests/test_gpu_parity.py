@@ -476,3 +476,44 @@ def test_end_metric_relative_l2_unchanged(loop):
     assert np.allclose(losses, fx.arrays["losses"], rtol=2e-5), (losses, fx.arrays["losses"])
     m1 = metric()
     assert np.abs(m1 - fx.arrays["metric1"]).max() < 2e-5, (m1, fx.arrays["metric1"])
+
+
+# ---------------------------------------------------------------------------------------------
+# BlinDNO models: U-Net + bag attention on library kernels, FNO heads on this path
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["blindno2d_fpe_train", "blindno2d_nc_eval", "blindno1d_fpe_bag_train", "blindno1d_gpe_bag_eval"])
+def test_blindno_models_golden(name):
+    """Fixtures from the unmodified reference classes (seeded construction: the surface classes draw identical
+    initial weights, tests/test_surface_cpu.py).  cuDNN convs vs the reference's CPU convs: outputs 5e-5,
+    gradients 2e-3 of each tensor's scale (the tolerance of the NIO models)."""
+    from blindno_b200.surface import blindno
+    fx = Fixture(name)
+    variant, cls = str(fx.meta("variant")), str(fx.meta("cls"))
+    kwargs = {}
+    for k, v in fx.group("kw.").items():
+        kwargs[k] = tuple(int(t) for t in v) if v.dim() else int(v)
+    if variant.startswith("1d"):
+        kwargs["device"] = "cpu"
+    torch.manual_seed(int(fx.meta("seed")))
+    model = blindno.make_blindno_models(variant)[cls](**kwargs).to(DEV)
+    model.train(bool(fx.meta("train")))
+    if int(fx.meta("np_seed")) >= 0:
+        np.random.seed(int(fx.meta("np_seed")))
+    launches0 = ops.kernel_launches()
+    y = model(fx.t("x").to(DEV))
+    assert ops.kernel_launches() > launches0
+    assert y.shape == fx.t("y").shape
+    assert rel_err(y, fx.t("y")) < 5e-5
+    y.backward(fx.t("gy").to(DEV))
+    got = dict(model.named_parameters())
+    gmax = max(v.abs().max().item() for v in fx.grads.values())
+    for k, want in fx.grads.items():
+        g = got[k].grad.detach().cpu()
+        err = (g - want).abs().max().item()
+        assert err <= 2e-3 * max(want.abs().max().item(), 1e-2 * gmax), (k, err)
+    for k, want in fx.group("gnorm.").items():
+        g = got[k].grad.detach().cpu()
+        g = torch.view_as_real(g) if g.is_complex() else g
+        assert abs(g.double().norm().item() - want[0].item()) <= 2e-3 * want[0].item(), k
+    for k in fx.nograd:
+        assert got[k].grad is None, k

@@ -134,10 +134,68 @@ def test_dropin_modules_resolve_the_scripts_imports(variant, imports):
         for n in [n for n in imports["NIOModules"] if n in accelerated]:
             assert getattr(NIOModules, n).__name__ == n
         with pytest.raises(NotImplementedError):
-            dropin.exports(variant, "NIOModules")["PermInvUNet_attn"]()
+            dropin.exports(variant, "NIOModules")["PermInvUNet"]()          # plain U-Net: out of scope, fails loudly
     finally:
         for k, v in saved.items():
             if v is None:
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+# ---------------------------------------------------------------------------------------------
+# BlinDNO family: same state_dict, same seeded initial weights, same encoder
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not os.path.isdir("/root/reference/2d_FPE"), reason="reference tree not mounted")
+@pytest.mark.parametrize("variant,cls,kwargs,xshape", [
+    ("2d_FPE", "PermInvUNet_attn", dict(base_ch=2, depth=2, input_size=(21, 18)), (2, 55, 21, 18)),
+    ("2d_Non_conservative_FPE", "PermInvUNet_attn", dict(base_ch=2, depth=3, input_size=(21, 18)), (2, 55, 21, 18)),
+    ("1d_FPE", "PermInvUNet_attn1D_bag", dict(base_ch=2, depth=3, input_size=45, device="cpu"), (2, 55, 45)),
+    ("1d_FPE", "PermInvUNet_attn1D", dict(base_ch=1, depth=2, input_size=40, device="cpu"), (2, 7, 40)),
+    ("1d_GPE", "PermInvUNet_attn1D_bag", dict(base_ch=2, depth=2, input_size=64, device="cpu"), (2, 52, 64)),
+    ("1d_GPE", "PermInvUNet_attn1D_bag_GPE", dict(base_ch=2, depth=2, input_size=64, device="cpu", width=8, modes=9), (2, 52, 64)),
+])
+def test_blindno_surface_matches_live_reference(variant, cls, kwargs, xshape):
+    """Seeded construction gives bit-identical state_dicts (names, order, shapes, values); with the FNO heads
+    replaced by the same stub in both, the U-Net encoder + bag attention agree and the bag draw consumes the
+    NumPy stream identically (the heads themselves are CUDA-only: tests/test_gpu_parity.py)."""
+    from blindno_b200.surface import blindno
+    from tests.golden.make_golden import load_reference
+    ref_mod = load_reference(variant, "NIOModules")
+    torch.manual_seed(5)
+    ref = getattr(ref_mod, cls)(**kwargs)
+    torch.manual_seed(5)
+    ours = blindno.make_blindno_models(variant)[cls](**kwargs)
+    a, b = ref.state_dict(), ours.state_dict()
+    assert list(a) == list(b)
+    for k in a:
+        assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+
+    class Stub(torch.nn.Module):
+        def forward(self, x):
+            return x[..., :1] * 2.0
+
+    for m in (ref, ours):
+        for name in [n for n, _ in m.named_children() if n.startswith("fno_")]:
+            setattr(m, name, Stub())
+    x = torch.randn(*xshape, generator=torch.Generator().manual_seed(1))
+    for training in (False, True):
+        ref.train(training), ours.train(training)
+        np.random.seed(3)
+        want = ref(x)
+        after_ref = np.random.randint(0, 1 << 30)
+        np.random.seed(3)
+        got = ours(x)
+        assert np.random.randint(0, 1 << 30) == after_ref
+        assert got.shape == want.shape
+        assert (got - want).abs().max().item() <= 2e-5 * max(want.abs().max().item(), 1.0)
+
+
+def test_dropin_exports_blindno_models():
+    from blindno_b200 import dropin
+    for variant, names in (("2d_FPE", ["PermInvUNet_attn"]), ("2d_Non_conservative_FPE", ["PermInvUNet_attn"]),
+                           ("1d_FPE", ["PermInvUNet_attn1D", "PermInvUNet_attn1D_bag"]),
+                           ("1d_GPE", ["PermInvUNet_attn1D_bag", "PermInvUNet_attn1D_bag_GPE"])):
+        ex = dropin.exports(variant, "NIOModules")
+        for n in names:
+            assert isinstance(ex[n], type) and issubclass(ex[n], torch.nn.Module), (variant, n)
