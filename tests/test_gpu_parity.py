@@ -500,11 +500,16 @@ def test_blindno_models_golden(name):
     if int(fx.meta("np_seed")) >= 0:
         np.random.seed(int(fx.meta("np_seed")))
     launches0 = ops.kernel_launches()
-    y = model(fx.t("x").to(DEV))
-    assert ops.kernel_launches() > launches0
-    assert y.shape == fx.t("y").shape
-    assert rel_err(y, fx.t("y")) < 5e-5
-    y.backward(fx.t("gy").to(DEV))
+    prev = torch.backends.cudnn.allow_tf32      # the U-Net's cuDNN convs default to TF32: compare in fp32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = model(fx.t("x").to(DEV))
+        assert ops.kernel_launches() > launches0
+        assert y.shape == fx.t("y").shape
+        assert rel_err(y, fx.t("y")) < 5e-5
+        y.backward(fx.t("gy").to(DEV))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
     got = dict(model.named_parameters())
     gmax = max(v.abs().max().item() for v in fx.grads.values())
     for k, want in fx.grads.items():
