@@ -357,9 +357,10 @@ def run_b200(args, wl, rank, world, local_rank):
     if roof_all:
         roofline = dict(roof_all[0])
         if roofline["kernel"].startswith("project"):
-            roofline["note"] = ("dominant kernel is ALU/SFU-bound, not HBM-bound: 128 exact-GELU evaluations per "
-                                "pixel (ncu: issue slots 75% busy, DRAM 1%); the HBM fraction is reported as the "
-                                "contract asks, see roofline_hbm_kernels for the memory-bound kernels")
+            roofline["note"] = ("dominant kernel is instruction-issue bound, not HBM-bound: 128 exact-GELU evaluations per "
+                                "pixel, recomputed in backward (ncu --set full, profiles/r1n_ncu_full_eager_step_summary.txt: "
+                                "issue slots 74% busy, FMA pipe 59%, MUFU 30%, DRAM 1%); the HBM fraction is reported as the "
+                                "contract asks, see roofline_hbm_kernels for the memory-side kernels")
     top = [{"kernel": k, "launches_per_step": v["launches"] / prof_steps, "us_per_step": v["ms"] * 1e3 / prof_steps,
             "share": v["ms"] / total_ms} for k, v in kernels[:args.top]]
 
