@@ -174,25 +174,35 @@ def kernel_bytes(name, wl, images_by_width):
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU oracle's train step
 # ---------------------------------------------------------------------------------------------
-def cpu_reference(wl, steps, warmup, batch, threads):
+def cpu_reference(wl, steps, warmup, batch, threads, device="cpu"):
+    """The reference's algorithm (oracle restatement: torch.fft / einsum / conv / gelu) timed on the host CPU, or -- with
+    device="cuda", the GPU status-quo comparator of SURVEY.md 8(d) -- on stock PyTorch CUDA kernels (cuFFT / cuBLAS)."""
     from blindno_b200.surface import nio
     from oracle import blindno_oracle as O
     torch.set_num_threads(threads)
     torch.manual_seed(1)
     np.random.seed(1)
+    dev = torch.device(device)
     model = nio.make_models(wl["variant"])[wl["cls"]](*wl["args"], *(("cpu",) if wl["ndim"] == 1 else ()))
-    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()
+    params = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in model.state_dict().items()
               if not k.startswith("branch.")}
     opt = torch.optim.Adam(O.trainable(params), lr=wl["lr"])
     fwd = O.niofp2d_fno_forward if wl["ndim"] == 2 else O.niofp1d_fno_forward
     kw = {"heads": tuple(model.head_names)}
-    grid = make_grid(wl)
-    batches = make_batches(wl, 2, batch, seed=0)
+    grid = make_grid(wl).to(dev)
+    batches = [(x.to(dev), y.to(dev)) for x, y in make_batches(wl, 2, batch, seed=0)]
+
+    def sync():
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+
     for i in range(warmup):
         O.train_step(params, opt, fwd, *batches[i % 2][:1], grid, batches[i % 2][1], **kw)
+    sync()
     t0 = time.perf_counter()
     for i in range(steps):
-        O.train_step(params, opt, fwd, *batches[i % 2][:1], grid, batches[i % 2][1], **kw)
+        O.train_step(params, opt, fwd, *batches[i % 2][:1], grid, batches[i % 2][1], **kw).item()   # loss.item() as the scripts do
+    sync()
     dt = time.perf_counter() - t0
     return batch * steps / dt, dt / steps * 1e3
 
@@ -201,18 +211,23 @@ def run_reference(args, wl, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps = min(args.steps, 10)
-    warmup = min(args.warmup, 2)
-    sps, ms = cpu_reference(wl, steps, warmup, wl["batch"], threads)
+    on_gpu = args.ref_device == "cuda"
+    steps = args.steps if on_gpu else min(args.steps, 10)
+    warmup = args.warmup if on_gpu else min(args.warmup, 2)
+    sps, ms = cpu_reference(wl, steps, warmup, wl["batch"], threads, device=args.ref_device)
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "batch": wl["batch"], "bag": wl["bag"], "grid": wl["n"],
+                   "ref_device": args.ref_device,
                    "note": "the reference's algorithm (torch.fft path) restated in oracle/blindno_oracle.py, "
-                           "timed on the host CPU; the reference is pure Python and cannot travel to the GPU box"},
+                           + ("run on stock PyTorch CUDA kernels (cuFFT / cuBLAS / ATen, eager): the GPU status-quo comparator"
+                              if on_gpu else "timed on the host CPU")
+                           + "; the reference is pure Python and cannot travel to the GPU box"},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} full train steps of batch {wl['batch']} after {warmup} warm-up"},
+                         "sample": f"{steps} full train steps of batch {wl['batch']} after {warmup} warm-up"
+                                   + (" (on cuda:0 with stock PyTorch kernels, not on the CPU)" if on_gpu else "")},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -412,6 +427,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="2d_FPE", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu (the contract's arm) or cuda = the same algorithm on stock PyTorch CUDA kernels")
     ap.add_argument("--batch-per-gpu", type=int, default=0)
     ap.add_argument("--pool", type=int, default=8, help="distinct batches rotated through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
