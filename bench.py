@@ -42,6 +42,10 @@ WORKLOADS = {
                   cls="NIOFP2D_FNO", args=(2, 3, 100, 25, 3, 12, 32, 2)),
     "1d_FPE": dict(variant="1d_FPE", ndim=1, n=80, bag=100, batch=32, lr=1e-3,
                    cls="NIOFP_FNO", args=(3, 30, 15, 2)),
+    # BASELINE.json configs[1]: the NIO model (DeepONet branch CNN + trunk -> bag mean -> one FNO head) of
+    # 1d_GPE/train_nio_GPE.py; the conv encoder stays on cuDNN, the pooled tail and the head are ours
+    "1d_GPE": dict(variant="1d_GPE", ndim=1, n=128, bag=101, batch=32, lr=1e-3, n_out=1, metric="nio_train_samples_per_sec",
+                   cls="NIOFP_schrodinger", args=(1, 3, 100, 25, 3, 20, 40, 1), head_width=20, head_modes=40),
 }
 METRIC = "nio_fno_train_samples_per_sec"
 
@@ -77,7 +81,7 @@ def make_grid(wl):
 def make_batches(wl, count, batch, seed):
     g = torch.Generator().manual_seed(seed)
     dims = (wl["n"],) * wl["ndim"]
-    n_out = 2
+    n_out = wl.get("n_out", 2)
     return [(torch.randn(batch, wl["bag"], *dims, generator=g), torch.randn(batch, *dims, n_out, generator=g))
             for _ in range(count)]
 
@@ -143,8 +147,8 @@ def kernel_bytes(name, wl, images_by_width):
     hp = wp if wl["ndim"] == 2 else 1
     h = n if wl["ndim"] == 2 else 1
     width_in = 4
-    width_head = wl["args"][5] if wl["ndim"] == 2 else wl["args"][1]
-    m_in, m_head = 12, (wl["args"][6] if wl["ndim"] == 2 else wl["args"][2])
+    width_head = wl.get("head_width") or (wl["args"][5] if wl["ndim"] == 2 else wl["args"][1])
+    m_in, m_head = 12, wl.get("head_modes") or (wl["args"][6] if wl["ndim"] == 2 else wl["args"][2])
     if kind in ("wfwd", "wfwd_gelu"):                 # tag = m2
         m2 = int(tag)
         c = width_in if m2 == m_in and m_in != m_head else None
@@ -184,11 +188,18 @@ def cpu_reference(wl, steps, warmup, batch, threads, device="cpu"):
     np.random.seed(1)
     dev = torch.device(device)
     model = nio.make_models(wl["variant"])[wl["cls"]](*wl["args"], *(("cpu",) if wl["ndim"] == 1 else ()))
-    params = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in model.state_dict().items()
-              if not k.startswith("branch.")}
-    opt = torch.optim.Adam(O.trainable(params), lr=wl["lr"])
-    fwd = O.niofp2d_fno_forward if wl["ndim"] == 2 else O.niofp1d_fno_forward
-    kw = {"heads": tuple(model.head_names)}
+    is_nio = not hasattr(model, "FNO_input")
+    learn = {k for k, _ in model.named_parameters()}
+    params = {k: (v.detach().clone().to(dev).requires_grad_(True) if k in learn else v.detach().clone().to(dev))
+              for k, v in model.state_dict().items() if is_nio or not k.startswith("branch.")}
+    if is_nio:      # NIO: the branch CNN and the trunk are trained too; fc0 is detached as everywhere
+        opt = torch.optim.Adam([v for k, v in params.items() if k in learn and not k.startswith(("fc0.", "deeponet."))
+                                or k == "deeponet.b0"], lr=wl["lr"])
+        fwd, kw = O.nio1d_forward, {"heads": tuple(model.head_names), "training": True}
+    else:
+        opt = torch.optim.Adam(O.trainable(params), lr=wl["lr"])
+        fwd = O.niofp2d_fno_forward if wl["ndim"] == 2 else O.niofp1d_fno_forward
+        kw = {"heads": tuple(model.head_names)}
     grid = make_grid(wl).to(dev)
     batches = [(x.to(dev), y.to(dev)) for x, y in make_batches(wl, 2, batch, seed=0)]
 
@@ -216,7 +227,7 @@ def run_reference(args, wl, rank, world):
     warmup = args.warmup if on_gpu else min(args.warmup, 2)
     sps, ms = cpu_reference(wl, steps, warmup, wl["batch"], threads, device=args.ref_device)
     line = {
-        "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": wl.get("metric", METRIC), "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "batch": wl["batch"], "bag": wl["bag"], "grid": wl["n"],
@@ -269,6 +280,8 @@ def run_b200(args, wl, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if not hasattr(model, "FNO_input"):
+        use_graphs = False        # NIO: the cuDNN conv encoder with train-mode BatchNorm runs eager
     n_graphs = 0
     if use_graphs:
         # one CUDA graph per bag size the run can draw (L in [50, L0)), captured before any timing
@@ -350,7 +363,7 @@ def run_b200(args, wl, rank, world, local_rank):
     kernels = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
     total_ms = sum(v["ms"] for v in prof.values()) or 1.0
     mean_keep = sum(keep_counts) / max(len(keep_counts), 1)
-    width_head = wl["args"][5] if wl["ndim"] == 2 else wl["args"][1]
+    width_head = wl.get("head_width") or (wl["args"][5] if wl["ndim"] == 2 else wl["args"][1])
     images = {4: batch * mean_keep, width_head: batch}
 
     def roof(name, rec):
@@ -390,7 +403,7 @@ def run_b200(args, wl, rank, world, local_rank):
 
     x0, y0 = host[0]
     line = {
-        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "metric": wl.get("metric", METRIC), "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.prec == "fp32" else "tf32", "data": "synthetic",
         "config": {"workload": args.workload, "model": f"{wl['cls']}{wl['args']}", "batch_per_gpu": batch,
