@@ -53,6 +53,7 @@ class FlatTrainer:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.loss_fn = loss_fn or nn.functional.mse_loss
         self.step_count = 0
+        self.adam_fn = ops.adam_step_flat
         # CUDA-graph replay of the device work of a step (see step()): one graph per bag size
         self.use_graphs = False
         self._graphs = {}
@@ -151,19 +152,12 @@ class FlatTrainer:
         torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
 
     def optimizer_step(self):
+        """One fused Adam kernel over the flat buffer (1/world of DDP's mean folded in).  There is no CPU
+        arithmetic here: CPU tensors make the op raise.  (The gloo host-logic test replaces ``adam_fn`` with
+        a torch-op restatement of its own.)"""
         self.step_count += 1
-        if self.flat_param.is_cuda:
-            ops.adam_step_flat(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr=self.lr,
-                               betas=self.betas, eps=self.eps, step=self.step_count, grad_scale=1.0 / self.world)
-        else:
-            # host-side logic tests (gloo, CPU tensors): same update written with torch ops
-            g = self.flat_grad / self.world
-            b1, b2 = self.betas
-            self.exp_avg.mul_(b1).add_(g, alpha=1 - b1)
-            self.exp_avg_sq.mul_(b2).addcmul_(g, g, value=1 - b2)
-            bc1, bc2 = 1 - b1 ** self.step_count, 1 - b2 ** self.step_count
-            denom = (self.exp_avg_sq.sqrt() / bc2 ** 0.5).add_(self.eps)
-            self.flat_param.addcdiv_(self.exp_avg, denom, value=-self.lr / bc1)
+        self.adam_fn(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr=self.lr, betas=self.betas,
+                     eps=self.eps, step=self.step_count, grad_scale=1.0 / self.world)
 
     # -- the step --------------------------------------------------------------------------
     def step(self, x: torch.Tensor, grid: torch.Tensor, target: torch.Tensor) -> torch.Tensor:

@@ -20,6 +20,17 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _torch_adam(param, grad, exp_avg, exp_avg_sq, *, lr, betas, eps, step, grad_scale):
+    """torch-op restatement of the fused Adam kernel's update (test only: the product has no CPU path)."""
+    g = grad * grad_scale
+    b1, b2 = betas
+    exp_avg.mul_(b1).add_(g, alpha=1 - b1)
+    exp_avg_sq.mul_(b2).addcmul_(g, g, value=1 - b2)
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    denom = (exp_avg_sq.sqrt() / bc2 ** 0.5).add_(eps)
+    param.addcdiv_(exp_avg, denom, value=-lr / bc1)
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -28,6 +39,10 @@ def _worker(rank, world, port, out):
         model = nio.make_models("2d_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 1, 4, 3, 2)
         ref = [p.detach().clone() for _, p in live_parameters(model)]
         trainer = FlatTrainer(model, lr=1e-2)
+        with pytest.raises(RuntimeError, match="CUDA"):        # the product's optimiser step is the CUDA kernel, nothing else
+            trainer.optimizer_step()
+        trainer.step_count = 0
+        trainer.adam_fn = _torch_adam
         assert trainer.world == world
         # the module parameters are now views of the flat buffer, in FNO slot order
         assert all(p.data_ptr() >= trainer.flat_param.data_ptr() for _, p in live_parameters(model))
