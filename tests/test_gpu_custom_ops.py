@@ -73,7 +73,7 @@ def test_stage_ops_chain_vs_oracle_and_whole_net(ndim, shape, ctor):
     net.zero_grad()
     xw = x.to(DEV).requires_grad_(True)
     whole = net(xw)
-    assert rel_err(whole, got) < 2e-6      # (few-image nets read a mode-major weight copy: other summation order)
+    assert rel_err(whole, got) < 5e-6      # (few-image nets read a mode-major weight copy: other summation order)
     whole.backward(gy.to(DEV))
     for k, p in net.named_parameters():
         _grad_check("whole/" + k, p.grad, g32[k], g64[k], floor=floor)
