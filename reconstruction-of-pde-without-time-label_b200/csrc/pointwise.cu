@@ -481,6 +481,16 @@ template <int CP>
 __host__ __device__ constexpr int proj_nvp() { return CP + 2 <= 8 ? 8 : (CP + 2 <= 16 ? 16 : 32); }
 template <int CP, int NOUT, int JS>
 __host__ __device__ constexpr bool proj_treduce() { return NOUT == 1 && JS == 1 && CP <= 12; }
+// few-pixel regime (JS = 8): the 4 lanes that share a hidden-unit slice transpose-reduce their CP + 1 + NOUT partial
+// sums in 2 butterfly steps (0.75 shuffles per value instead of 2) and add them to warp-private accumulators
+template <int CP, int NOUT, int JS>
+__host__ __device__ constexpr bool proj_qreduce() { return JS == 8; }
+template <int CP, int NOUT>
+__host__ __device__ constexpr int proj_nvq() { return (CP + 1 + NOUT + 3) & ~3; }
+template <int CP, int NOUT, int JS>
+__host__ __device__ constexpr int proj_acc_pitch() {
+  return proj_treduce<CP, NOUT, JS>() ? proj_nvp<CP>() : (proj_qreduce<CP, NOUT, JS>() ? proj_nvq<CP, NOUT>() : 0);
+}
 
 // projection backward.  Same thread mapping; for every hidden unit the pre-activation is
 // recomputed, gz accumulates in registers (reduced over the JS slices at the end), and the weight
@@ -489,7 +499,8 @@ __host__ __device__ constexpr bool proj_treduce() { return NOUT == 1 && JS == 1 
 template <int CP, int NOUT, int JS, int PP>
 __global__ void __launch_bounds__(PROJ_THREADS) project_bwd_kernel(const ProjArgs a, const float* __restrict__ g_out,
                                                                    int pooled_g, int n_keep, float* __restrict__ gz,
-                                                                   float* g_w1, float* g_b1, float* g_w2, float* g_b2) {
+                                                                   float* g_w1, float* g_b1, float* g_w2, float* g_b2,
+                                                                   int wred) {   // warp-private accumulators fit shared memory
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) float smem[];
@@ -502,9 +513,10 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_bwd_kernel(const ProjArg
   float* aw2 = ab1 + hidden;               // [nout][hidden]
   float* ab2 = aw2 + nout * hidden;        // [PROJ_MAX_OUT]
   constexpr bool TREDUCE = proj_treduce<CP, NOUT, JS>();
-  constexpr int NVP = proj_nvp<CP>();
-  float* wacc = ab2 + PROJ_MAX_OUT;        // [warps][hidden][NVP] warp-private accumulators (TREDUCE)
-  if constexpr (TREDUCE)
+  const bool QREDUCE = proj_qreduce<CP, NOUT, JS>() && wred != 0;
+  constexpr int NVP = TREDUCE ? proj_nvp<CP>() : proj_nvq<CP, NOUT>();
+  float* wacc = ab2 + PROJ_MAX_OUT;        // [warps][hidden][NVP] warp-private accumulators (TREDUCE / QREDUCE)
+  if (TREDUCE || QREDUCE)
     for (int i = threadIdx.x; i < (PROJ_THREADS / 32) * hidden * NVP; i += blockDim.x) wacc[i] = 0.f;
   for (int i = threadIdx.x; i < hidden * CP; i += blockDim.x) {
     const int j = i / CP, c = i - j * CP;
@@ -620,6 +632,36 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_bwd_kernel(const ProjArg
           float* dst = wacc + ((size_t)warp * hidden + j) * NVP + lane / (32 / NVP);
           *dst += val[0];
         }
+      } else if (QREDUCE) {
+        // lanes {s, s+8, s+16, s+24} hold the partials of hidden unit j (slice s): after the two steps lane
+        // (bit4, bit3) owns the totals of quarter 2*bit4 + bit3 of the value vector [sw1[CP], sb1, sw2[NOUT], 0..]
+        float val[NVP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) val[c] = sw1[c];
+        val[CP] = sb1;
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) val[CP + 1 + k] = sw2[k];
+#pragma unroll
+        for (int v = CP + 1 + NOUT; v < NVP; ++v) val[v] = 0.f;
+        int base = 0;
+#pragma unroll
+        for (int step = 0; step < 2; ++step) {
+          const int off = 16 >> step;
+          const int n = NVP >> (step + 1);
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < NVP / 2; ++i) {
+            if (i < n) {
+              const float send = up ? val[i] : val[i + n];
+              const float keep = up ? val[i + n] : val[i];
+              val[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          if (up) base += n;
+        }
+        float* dst = wacc + ((size_t)warp * hidden + j) * NVP + base;
+#pragma unroll
+        for (int i = 0; i < NVP / 4; ++i) dst[i] += val[i];
       } else {
         // reduce over the lanes that share this slice (xor offsets >= JS), then one lane per slice adds
 #pragma unroll
@@ -651,15 +693,16 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_bwd_kernel(const ProjArg
     }
   }
   __syncthreads();
-  if constexpr (TREDUCE) {
-    for (int i = threadIdx.x; i < hidden * (CP + 2); i += blockDim.x) {
-      const int j = i / (CP + 2), v = i - j * (CP + 2);
+  if (TREDUCE || QREDUCE) {
+    constexpr int NV = CP + 1 + NOUT;      // (TREDUCE has NOUT == 1)
+    for (int i = threadIdx.x; i < hidden * NV; i += blockDim.x) {
+      const int j = i / NV, v = i - j * NV;
       float s = 0.f;
 #pragma unroll
       for (int w = 0; w < PROJ_THREADS / 32; ++w) s += wacc[((size_t)w * hidden + j) * NVP + v];
       if (v < CP) aw1[j * CP + v] = s;
       else if (v == CP) ab1[j] = s;
-      else aw2[j] = s;
+      else if (v - CP - 1 < nout) aw2[(v - CP - 1) * hidden + j] = s;
     }
     __syncthreads();
   }
@@ -699,10 +742,12 @@ static void launch_project_bwd_t(const ProjArgs& a, const float* g_out, int pool
   const long rounds = (ntiles + cap - 1) / cap;
   const int grid = (int)((ntiles + rounds - 1) / rounds);      // balanced: every block runs `rounds` tiles
   size_t smem = (size_t)(2 * (a.hidden * CP + a.hidden + a.c_out * a.hidden) + PROJ_MAX_OUT) * sizeof(float);
-  if (proj_treduce<CP, NOUT, JS>()) smem += (size_t)(PROJ_THREADS / 32) * a.hidden * proj_nvp<CP>() * sizeof(float);
-  cudaFuncSetAttribute(project_bwd_kernel<CP, NOUT, JS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  const size_t acc = (size_t)(PROJ_THREADS / 32) * a.hidden * proj_acc_pitch<CP, NOUT, JS>() * sizeof(float);
+  const int wred = smem + acc <= 220 * 1024;      // (always true for the reference's hidden = 128)
+  if (wred || proj_treduce<CP, NOUT, JS>()) smem += acc;
+  cudaFuncSetAttribute(project_bwd_kernel<CP, NOUT, JS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   launch_k(project_bwd_kernel<CP, NOUT, JS, PP>, dim3(grid), dim3(PROJ_THREADS), smem, st, a, g_out, pooled_g, n_keep, gz, g_w1, g_b1,
-                                                                        g_w2, g_b2);
+                                                                        g_w2, g_b2, wred);
 }
 
 void launch_project_bwd(const ProjArgs& a, const float* g_out, int pooled_g, int n_keep, float* gz, float* g_w1,
