@@ -402,6 +402,35 @@ def test_tf32_mode_whole_model_within_stated_bound():
     assert worst < TF32_GRAD_TOL, f"worst gradient rel err in TF32 mode: {worst:.3e}"
 
 
+def test_tf32x3_mode_whole_model_meets_the_fp32_bound():
+    """BDN_PREC_TF32X3: the W-forward DFT GEMMs on tcgen05 with operands split into TF32 high + low parts (3 MMAs
+    per K step).  Through the whole 2-D NIO-FNO at the default widths / modes the outputs stay within the FP32
+    bound (1e-5) of the fp64 oracle and the gradients within the same rule as the FFMA path."""
+    torch.manual_seed(1)
+    model = nio.make_models("2d_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 3, 12, 32, 2)
+    params = {k: v.clone() for k, v in model.state_dict().items() if not k.startswith("branch.")}
+    heads = model.head_names
+    model = ops.set_precision(model.to(DEV).train(), ops.PREC_TF32X3)
+    g = torch.Generator().manual_seed(0)
+    x, gy, grid = torch.randn(1, 100, 61, 61, generator=g), torch.randn(1, 61, 61, 2, generator=g), _grid2d(61)
+    np.random.seed(3)
+    idx = O.draw_bag(100, True)
+    np.random.seed(3)
+    ops.profile_begin()
+    y = model(x.to(DEV), grid.to(DEV))
+    y.backward(gy.to(DEV))
+    torch.cuda.synchronize()
+    prof = ops.profile_end()
+    assert any(k.startswith("wfwd_tc") for k in prof), f"the tcgen05 kernel did not run: {sorted(prof)}"
+    (y32, g32, _), (y64, g64, _) = _oracle_grads(O.niofp2d_fno_forward, params, x, gy, extra=(grid,), heads=heads, idx=idx)
+    assert rel_err(y, y64) < TOL
+    got = dict(model.named_parameters())
+    floor = 1.2e-7 * _gmax(g64)
+    for k, v in g64.items():
+        if v is not None:
+            _grad_check(k, got[k].grad, g32[k], v, floor=floor)
+
+
 # ---------------------------------------------------------------------------------------------
 # NIO models (DeepONet branch CNN on cuDNN, trunk FFN, pool-before-contract tail, our bag pool + FNO heads)
 # ---------------------------------------------------------------------------------------------
