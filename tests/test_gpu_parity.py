@@ -283,6 +283,67 @@ def test_full_batch_properties_2d_fpe():
         assert rel_err(lin, 2.0 * layer(a) - 3.0 * layer(b)) < TOL
 
 
+@pytest.mark.parametrize("shape,m", [((400, 4, 76, 76), 12), ((4, 12, 76, 76), 32), ((3200, 4, 100), 12), ((32, 30, 100), 15)])
+def test_spectral_backward_is_the_adjoint_at_full_size(shape, m):
+    """Size-independent property at the BASELINE shapes (the oracle is too slow there): the spectral convolution is
+    linear in x and in W, so its backward must be the exact adjoint in both:
+    <A_W x, g> = <x, A_W^T g> = <W, dW(x, g)>.  All three inner products agree to fp32 summation noise."""
+    torch.manual_seed(len(shape) * 100 + m)
+    c = shape[1]
+    x = torch.randn(*shape, device=DEV, requires_grad=True)
+    gy = torch.randn(*shape, device=DEV)
+    if len(shape) == 4:
+        w1 = (torch.rand(c, c, m, m, 2, device=DEV) / c).requires_grad_(True)
+        w2 = (torch.rand(c, c, m, m, 2, device=DEV) / c).requires_grad_(True)
+        y = ops.spectral_conv(x, w1, w2)
+    else:
+        w1 = (torch.rand(c, c, m, dtype=torch.cfloat, device=DEV) / c).requires_grad_(True)
+        w2 = None
+        y = ops.spectral_conv(x, w1)
+    y.backward(gy)
+    lhs = (y.detach().double() * gy.double()).sum().item()
+    via_x = (x.detach().double() * x.grad.double()).sum().item()
+    via_w = 0.0
+    for w in (w1, w2):
+        if w is not None:
+            a, b = (torch.view_as_real(w.detach()), torch.view_as_real(w.grad)) if w.is_complex() else (w.detach(), w.grad)
+            via_w += (a.double() * b.double()).sum().item()
+    scale = (y.detach().double().norm() * gy.double().norm()).item()
+    assert abs(lhs - via_x) <= 2e-6 * scale, (lhs, via_x, scale)
+    assert abs(lhs - via_w) <= 2e-6 * scale, (lhs, via_w, scale)
+
+
+def test_whole_net_gradient_matches_finite_differences_at_full_size():
+    """Directional derivative of the default-shape NIO-FNO loss along a random parameter direction, by central
+    differences in fp32 with a step large enough to clear rounding: agrees with <grad, direction> to 1 %.  (A
+    size-independent check of forward/backward consistency: the oracle needs minutes per step at this shape.)"""
+    torch.manual_seed(9)
+    model = nio.make_models("2d_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 3, 12, 32, 2).to(DEV).eval()
+    x = torch.randn(2, 100, 61, 61, device=DEV)
+    target = torch.randn(2, 61, 61, 2, device=DEV)
+    grid = _grid2d(61).to(DEV)
+    params = [p for n, p in model.named_parameters() if not n.startswith(("branch.", "fc0."))]
+
+    def loss():
+        return torch.nn.functional.mse_loss(model(x, grid), target)
+
+    val = loss()
+    val.backward()
+    dirs = [torch.randn_like(p) * p.detach().abs().mean() for p in params]
+    analytic = sum((torch.view_as_real(p.grad) * torch.view_as_real(d)).sum().item() if p.is_complex()
+                   else (p.grad * d).sum().item() for p, d in zip(params, dirs))
+    eps = 1e-2
+    with torch.no_grad():
+        for p, d in zip(params, dirs):
+            p.add_(d, alpha=eps)
+        up = loss().item()
+        for p, d in zip(params, dirs):
+            p.add_(d, alpha=-2 * eps)
+        down = loss().item()
+    numeric = (up - down) / (2 * eps)
+    assert abs(numeric - analytic) <= 1e-2 * abs(analytic) + 1e-6, (numeric, analytic)
+
+
 def test_fc0_receives_no_gradient_and_unused_branch_is_untouched():
     model = nio.make_models("2d_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 1, 4, 4, 2).to(DEV).train()
     np.random.seed(0)
