@@ -661,18 +661,18 @@ int bdn_stage_project_backward(const BdnFnoShape* s, const float* z, const float
 int bdn_bag_pool_lift_forward(const float* s, const float* grid, const float* w0, const float* b0, float* out,
                               int32_t n_bags, int32_t n_keep, int32_t npix, int32_t grid_dim, int32_t width,
                               void* stream) {
-  if (!s || !grid || !w0 || !b0 || !out) return set_error(BDN_ERR_INVALID, "null pointer argument");
   if (n_bags < 0 || n_keep < 1 || npix < 1 || grid_dim < 1 || width < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
-  if (n_bags == 0) return BDN_OK;
+  if (n_bags == 0) return BDN_OK;          // an empty batch has empty (null) buffers: nothing to do
+  if (!s || !grid || !w0 || !b0 || !out) return set_error(BDN_ERR_INVALID, "null pointer argument");
   launch_pool_lift(s, grid, w0, b0, out, n_bags, n_keep, npix, grid_dim, width, (cudaStream_t)stream);
   return check_cuda("bdn_bag_pool_lift_forward");
 }
 
 int bdn_bag_pool_lift_backward(const float* g, const float* w0, float* gpool, int32_t n_bags, int32_t npix,
                                int32_t grid_dim, int32_t width, void* stream) {
-  if (!g || !w0 || !gpool) return set_error(BDN_ERR_INVALID, "null pointer argument");
   if (n_bags < 0 || npix < 1 || grid_dim < 1 || width < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
   if (n_bags == 0) return BDN_OK;
+  if (!g || !w0 || !gpool) return set_error(BDN_ERR_INVALID, "null pointer argument");
   launch_pool_lift_bwd(g, w0, gpool, n_bags, npix, grid_dim, width, (cudaStream_t)stream);
   return check_cuda("bdn_bag_pool_lift_backward");
 }

@@ -344,6 +344,35 @@ def test_whole_net_gradient_matches_finite_differences_at_full_size():
     assert abs(numeric - analytic) <= 1e-2 * abs(analytic) + 1e-6, (numeric, analytic)
 
 
+def test_strided_inputs_single_snapshot_bags_and_empty_batches():
+    """Ragged / degenerate inputs: non-contiguous views are accepted (the reference feeds an NHWC-strided view into
+    layer 0), a bag of one snapshot works (the mean of one), an empty batch returns an empty result."""
+    torch.manual_seed(2)
+    p = {"w1": torch.rand(3, 3, 4, 5, 2) / 9, "w2": torch.rand(3, 3, 4, 5, 2) / 9}
+    x = torch.randn(2, 12, 14, 3)                                   # NHWC storage
+    want = O.spectral_conv2d(x.permute(0, 3, 1, 2).double(), p["w1"].double(), p["w2"].double())
+    got = ops.spectral_conv(x.to(DEV).permute(0, 3, 1, 2), p["w1"].to(DEV), p["w2"].to(DEV))      # strided view
+    assert rel_err(got, want) < TOL
+    wide = torch.randn(2, 3, 12, 28).to(DEV)[..., ::2]               # every other column
+    assert rel_err(ops.spectral_conv(wide, p["w1"].to(DEV), p["w2"].to(DEV)),
+                   O.spectral_conv2d(wide.cpu().double(), p["w1"].double(), p["w2"].double())) < TOL
+
+    torch.manual_seed(4)
+    model = nio.make_models("2d_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 2, 6, 5, 2)
+    params = {k: v.clone().double() for k, v in model.state_dict().items() if not k.startswith("branch.")}
+    model = model.to(DEV).eval()
+    grid = _grid2d(20)
+    one = torch.randn(3, 1, 20, 20)
+    with torch.no_grad():
+        y = model(one.to(DEV), grid.to(DEV))
+        want = O.niofp2d_fno_forward(params, one.double(), grid.double())
+        assert rel_err(y, want) < TOL
+        empty = model(torch.zeros(0, 7, 20, 20, device=DEV), grid.to(DEV))
+    assert empty.shape == (0, 20, 20, 2)
+    net = fno.FNO1d(5, 6, 2, 2, 2).to(DEV)
+    assert net(torch.zeros(0, 22, 2, device=DEV)).shape == (0, 22, 2)
+
+
 def test_fc0_receives_no_gradient_and_unused_branch_is_untouched():
     model = nio.make_models("2d_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 1, 4, 4, 2).to(DEV).train()
     np.random.seed(0)
