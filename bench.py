@@ -282,8 +282,6 @@ def run_b200(args, wl, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    if not hasattr(model, "FNO_input"):
-        use_graphs = False        # NIO: the cuDNN conv encoder with train-mode BatchNorm runs eager
     n_graphs = 0
     if use_graphs:
         # one CUDA graph per bag size the run can draw (L in [50, L0)), captured before any timing

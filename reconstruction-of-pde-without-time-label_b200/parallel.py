@@ -162,7 +162,7 @@ class FlatTrainer:
     # -- the step --------------------------------------------------------------------------
     def step(self, x: torch.Tensor, grid: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """zero_grad -> forward -> loss -> backward -> all-reduce -> Adam.  Returns the (device) loss."""
-        if self.use_graphs and (x.is_cuda or x.is_pinned()) and self.flat_param.is_cuda and hasattr(self.model, "FNO_input"):
+        if self.use_graphs and (x.is_cuda or x.is_pinned()) and self.flat_param.is_cuda and getattr(self.model, "accepts_idx", False):
             return self._graph_step(x, grid, target)
         self.zero_grad()
         pred = self.model(x, grid)
@@ -233,7 +233,13 @@ class FlatTrainer:
         with torch.cuda.stream(side):
             if ent["idx"] is None:
                 state = np.random.get_state()
+            # the warm-up run must leave no trace: BatchNorm running statistics (NIO's conv encoder and trunk) are
+            # module buffers that a train-mode forward updates
+            buffers = [(b, b.detach().clone()) for b in self.model.buffers()]
             body()
+            with torch.no_grad():
+                for b, saved in buffers:
+                    b.copy_(saved)
             if ent["idx"] is None:
                 np.random.set_state(state)
         torch.cuda.current_stream(dev).wait_stream(side)

@@ -49,6 +49,7 @@ def _side_streams(device, n):
 
 class _BagModel(nn.Module):
     head_names: tuple = ()
+    accepts_idx = False     # forward(x, grid, idx=<int32 device tensor>): the caller drew the bag (CUDA-graph replay)
 
     def _heads(self, lifted):
         """The output FNO heads read the same lifted bag mean and are independent of each other; with only
@@ -81,6 +82,7 @@ class _NioFnoMixin(_BagModel):
     """FNO_input on every snapshot -> mean over the bag folded into the detached fc0 -> FNO heads."""
     _expose_lifted = False
     _lifted = None
+    accepts_idx = True
 
     def forward(self, x, grid, idx=None):
         """``idx`` (optional int32 device tensor): the kept snapshots, when the caller has already drawn
@@ -103,10 +105,15 @@ class _NioMixin(_BagModel):
     [B, L, p] branch coefficients before the trunk contraction (exact), so the
     [B, L, n_points] DeepONet output of the reference is never materialised."""
 
-    def forward(self, x, grid):
-        idx = draw_bag(x.shape[1], self.training)
+    accepts_idx = True
+
+    def forward(self, x, grid, idx=None):
+        """``idx`` as in the NIO-FNO models: the kept snapshots as a device tensor when the caller has drawn the bag
+        itself (FlatTrainer replays the whole step, cuDNN encoder included, from a CUDA graph per bag size)."""
+        if idx is None:
+            idx = _idx_tensor(draw_bag(x.shape[1], self.training), x.device)
         if idx is not None:
-            x = x[:, torch.as_tensor(idx, device=x.device)]
+            x = x.index_select(1, idx)
         grid_flat = grid.reshape(-1, grid.shape[-1])
         u = x.unsqueeze(2) if grid.dim() == 3 else x
         coeff = self.branch(u)                                   # [B, L, p]  (cuDNN conv stack)

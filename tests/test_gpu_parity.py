@@ -521,6 +521,47 @@ def test_tf32x3_mode_whole_model_meets_the_fp32_bound():
             _grad_check(k, got[k].grad, g32[k], v, floor=floor)
 
 
+def test_graph_replay_of_the_nio_step_matches_eager():
+    """NIO (1d_GPE): the whole step -- cuDNN conv encoder with train-mode BatchNorm, trunk, pooled tail, FNO head,
+    their backward -- is captured per bag size and replayed.  After the first step (identical weights in both runs)
+    loss, BatchNorm statistics and step counters agree tightly; over further steps the losses keep agreeing (the
+    weights themselves drift by Adam-amplified reduction noise: the first Adam steps move every weight by
+    lr * sign(gradient), and cuDNN's weight-gradient reductions are order dependent)."""
+    from blindno_b200.parallel import FlatTrainer
+
+    def make():
+        torch.manual_seed(7)
+        m = nio.make_models("1d_GPE")["NIOFP_schrodinger"](1, 3, 100, 25, 2, 8, 9, 1, DEV).to(DEV).train()
+        return m, FlatTrainer(m, lr=1e-3)
+
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.randn(3, 55, 128, generator=g).to(DEV) for _ in range(4)]
+    ys = [torch.randn(3, 128, 1, generator=g).to(DEV) for _ in range(4)]
+    grid = torch.linspace(0, 1, 128).unsqueeze(-1).to(DEV)
+    (m_eager, eager), (m_graph, graphed) = make(), make()
+    graphed.enable_graphs(True)
+    np.random.seed(11)
+    l_eager = [eager.step(xs[0], grid, ys[0]).item()]
+    state_e = np.random.get_state()
+    np.random.seed(11)
+    l_graph = [graphed.step(xs[0], grid, ys[0]).item()]
+    assert len(graphed._graphs) == 1 and not eager._graphs and graphed.replayed_launches > 0
+    assert abs(l_eager[0] - l_graph[0]) <= 1e-6 * max(abs(l_eager[0]), 1.0)
+    for (k, a), (_, b) in zip(m_eager.state_dict().items(), m_graph.state_dict().items()):
+        if "running_" in k:
+            assert rel_err(b, a) < 1e-5, k            # the capture warm-up left no trace in the BatchNorm buffers
+        if k.endswith("num_batches_tracked"):
+            assert int(a) == int(b) == 1, k
+    assert (graphed.flat_param - eager.flat_param).abs().max().item() <= 2.1e-3      # one Adam step: <= 2 * lr
+    assert (graphed.flat_param - eager.flat_param).abs().mean().item() <= 1e-5
+    state_g = np.random.get_state()
+    assert all(np.array_equal(a, b) for a, b in zip(state_e[1:3], state_g[1:3]))      # same NumPy stream position
+    l_eager += [eager.step(x, grid, y).item() for x, y in zip(xs[1:], ys[1:])]
+    l_graph += [graphed.step(x, grid, y).item() for x, y in zip(xs[1:], ys[1:])]
+    for a, b in zip(l_eager, l_graph):
+        assert abs(a - b) <= 1e-3 * max(abs(a), 1.0), (l_eager, l_graph)
+
+
 # ---------------------------------------------------------------------------------------------
 # NIO models (DeepONet branch CNN on cuDNN, trunk FFN, pool-before-contract tail, our bag pool + FNO heads)
 # ---------------------------------------------------------------------------------------------
