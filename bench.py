@@ -169,6 +169,7 @@ def kernel_bytes(name, wl, images_by_width):
         "mix1d_fwd": imgs * 3 * spec, "mix1d_bwd": imgs * 3 * spec,
         "winv_layer_fwd": imgs * (spec + 2 * act), "winv_layer_bwd": imgs * (spec + 3 * act),
         "winv_plain": imgs * (spec + act),
+        "layer1d_fwd": imgs * (2 * act + spec), "layer1d_bwd": imgs * (3 * act + 2 * spec),
         "project": imgs * (crop + 4 * h * n), "project_bwd": imgs * (crop + 4 * h * n + act),
         "gw_reduce": imgs * 16 * c * K * m2, "lift_bwd": imgs * (crop + 4 * h * n * (1 if c == width_in else c)),
     }

@@ -457,6 +457,10 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
   for (int k = 0; k < s->n_layers; ++k) {
     const int act_in = k > 0;
     float2* xs_k = xs_saved ? (float2*)(xs_saved + (size_t)k * ksp) : nullptr;
+    if (s->ndim == 1 && s->prec == BDN_PREC_FP32 &&
+        launch_layer1d(pl, false, zbuf(k), nullptr, zbuf(k + 1), xs_k, (const float2*)p->spec_w1[k], p->conv_w[k],
+                       p->conv_b[k], nullptr, nullptr, s->images, s->width, act_in, st))
+      continue;
     launch_wfwd(pl, zbuf(k), X1, rows, act_in, st, s->prec);
     if (s->ndim == 2)
       launch_core2d(pl, X1, Z, xs_k, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], s->images, s->width,
@@ -502,6 +506,14 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
                      g->fc1_b, g->fc2_w, g->fc2_b, st);
   const int rows = s->images * s->width * s->hp;
   for (int k = s->n_layers - 1; k >= 0; --k) {
+    if (s->ndim == 1 && s->prec == BDN_PREC_FP32 &&
+        launch_layer1d(pl, true, z_saved + (size_t)k * act, gz[cur], gz[cur ^ 1], GY, (const float2*)p->spec_w1[k],
+                       p->conv_w[k], nullptr, g->conv_w[k], g->conv_b[k], s->images, s->width, k > 0, st)) {
+      launch_gw_reduce(pl, (const float2*)(xs_saved + (size_t)k * ksp), GY, (float2*)g->spec_w1[k],
+                       (float2*)g->spec_w2[k], s->images, s->width, s->width, st);
+      cur ^= 1;
+      continue;
+    }
     launch_wfwd(pl, gz[cur], G1, rows, 0, st, s->prec);
     if (s->ndim == 2)
       launch_core2d(pl, G1, GZ, GY, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], s->images, s->width,
@@ -575,6 +587,10 @@ int bdn_stage_layer_forward(const BdnFnoShape* s, const float* z_in, int32_t act
   float2* X1 = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
   float2* Z = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
   if (!X1 || !Z) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+  if (s->ndim == 1 && s->prec == BDN_PREC_FP32 &&
+      launch_layer1d(pl, false, z_in, nullptr, z_out, (float2*)xs_saved, (const float2*)spec_w1, conv_w, conv_b, nullptr,
+                     nullptr, s->images, s->width, act_in != 0, st))
+    return check_cuda("bdn_stage_layer_forward");
   launch_wfwd(pl, z_in, X1, s->images * s->width * s->hp, act_in != 0, st, s->prec);
   if (s->ndim == 2)
     launch_core2d(pl, X1, Z, (float2*)xs_saved, (const float2*)spec_w1, (const float2*)spec_w2, s->images, s->width,
@@ -606,6 +622,13 @@ int bdn_stage_layer_backward(const BdnFnoShape* s, const float* gz_out, const fl
   float2* GZ = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
   float2* GY = (float2*)cv.take(kspec_floats1(s) * sizeof(float));
   if (!G1 || !GZ || !GY) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+  if (s->ndim == 1 && s->prec == BDN_PREC_FP32 &&
+      launch_layer1d(pl, true, z_in, gz_out, gz_in, GY, (const float2*)spec_w1, conv_w, nullptr, g_conv_w, g_conv_b,
+                     s->images, s->width, act_in != 0, st)) {
+    launch_gw_reduce(pl, (const float2*)xs_saved, GY, (float2*)g_spec_w1, (float2*)g_spec_w2, s->images, s->width,
+                     s->width, st);
+    return check_cuda("bdn_stage_layer_backward");
+  }
   launch_wfwd(pl, gz_out, G1, s->images * s->width * s->hp, 0, st, s->prec);
   if (s->ndim == 2)
     launch_core2d(pl, G1, GZ, GY, (const float2*)spec_w1, (const float2*)spec_w2, s->images, s->width, s->width, true, st);

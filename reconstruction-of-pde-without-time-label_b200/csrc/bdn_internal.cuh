@@ -70,6 +70,13 @@ void launch_mix1d(const Plan* pl, const float2* in, float2* out, float2* spec_ou
 void launch_gw_reduce(const Plan* pl, const float2* xs, const float2* gys, float2* gw1, float2* gw2,
                       int images, int ci, int co, cudaStream_t st);
 
+// Fused 1-D layer (fused1d.cu): W-forward DFT + mix + inverse DFT + 1x1 conv epilogue of one layer in one launch.
+//   fwd: out = z_out, spec = xs_saved (may be null);  bwd: out = gz_in, spec = gys (input of launch_gw_reduce),
+//   g_pw_w / g_pw_b accumulated.  Returns false (nothing launched) when unsupported: use the three-kernel path.
+bool launch_layer1d(const Plan* pl, bool bwd, const float* z_in, const float* g_out, float* out, float2* spec,
+                    const float2* w, const float* pw_w, const float* pw_b, float* g_pw_w, float* g_pw_b, int images, int c,
+                    int act_in, cudaStream_t st);
+
 // ---------------------------------------------------------------------------
 // tensor-core path (tc_gemm.cu)
 // ---------------------------------------------------------------------------
