@@ -204,3 +204,30 @@ def test_end_metric_relative_l2_of_the_oracle_matches_the_reference():
     with torch.no_grad():
         m1 = end_metric(fx, lambda x: O.niofp2d_fno_forward(p, x, grid))
     assert np.abs(m1 - fx.arrays["metric1"]).max() < 2e-5
+
+
+def test_oracle_gradcheck_fp64():
+    """torch.autograd.gradcheck of the fp64 restatement (finite differences vs its autograd), so that
+    the gradients the CUDA path is compared with are themselves pinned by something other than autograd."""
+    g = torch.Generator().manual_seed(0)
+    x2 = torch.randn(2, 2, 6, 8, dtype=torch.float64, generator=g, requires_grad=True)
+    w1 = (torch.rand(2, 3, 2, 3, 2, dtype=torch.float64, generator=g) / 4).requires_grad_(True)
+    w2 = (torch.rand(2, 3, 2, 3, 2, dtype=torch.float64, generator=g) / 4).requires_grad_(True)
+    assert torch.autograd.gradcheck(O.spectral_conv2d, (x2, w1, w2), eps=1e-6, atol=1e-7)
+    x1 = torch.randn(2, 2, 12, dtype=torch.float64, generator=g, requires_grad=True)
+    wr = torch.rand(2, 3, 4, 2, dtype=torch.float64, generator=g) / 4
+    wc = torch.view_as_complex(wr).clone().requires_grad_(True)
+    assert torch.autograd.gradcheck(O.spectral_conv1d, (x1, wc), eps=1e-6, atol=1e-7)
+
+    fx = Fixture("fno2d")
+    p = {k: (v.double() if not v.is_complex() else v.to(torch.complex128)) for k, v in fx.params.items()}
+    names = ["fc0.weight", "conv_list.0.weight", "spectral_list.1.weights2", "fc1.bias", "fc2.weight"]
+    x = fx.t("x")[:1, :7, :7].double().clone().requires_grad_(True)
+
+    def f(xx, *ws):
+        q = dict(p)
+        q.update(dict(zip(names, ws)))
+        return O.fno2d_forward(q, xx)
+
+    leaves = [p[n].clone().requires_grad_(True) for n in names]
+    assert torch.autograd.gradcheck(f, (x, *leaves), eps=1e-6, atol=1e-6, nondet_tol=0.0)
