@@ -46,8 +46,23 @@ WORKLOADS = {
     # 1d_GPE/train_nio_GPE.py; the conv encoder stays on cuDNN, the pooled tail and the head are ours
     "1d_GPE": dict(variant="1d_GPE", ndim=1, n=128, bag=101, batch=32, lr=1e-3, n_out=1, metric="nio_train_samples_per_sec",
                    cls="NIOFP_schrodinger", args=(1, 3, 100, 25, 3, 20, 40, 1), head_width=20, head_modes=40),
+    # the paper's BlinDNO model (permutation-invariant U-Net + bag attention on library kernels, the two
+    # FNO heads on this path), 2d_FPE/NIOModules.py:1086-1181 at its defaults
+    "blindno_2d": dict(variant="2d_FPE", ndim=2, n=61, bag=100, batch=4, lr=5e-4, metric="blindno_train_samples_per_sec",
+                       cls="PermInvUNet_attn", args=(), kwargs=dict(base_ch=1, depth=4, input_size=(61, 61)),
+                       factory="blindno", head_width=12, head_modes=32),
 }
 METRIC = "nio_fno_train_samples_per_sec"
+
+
+def build_model(wl, device=None):
+    """The drop-in model class of a workload (device argument only where the reference's ctor takes one)."""
+    if wl.get("factory") == "blindno":
+        from blindno_b200.surface.blindno import make_blindno_models
+        return make_blindno_models(wl["variant"])[wl["cls"]](*wl["args"], **wl.get("kwargs", {}))
+    from blindno_b200.surface import nio
+    extra = (device,) if wl["ndim"] == 1 else ()
+    return nio.make_models(wl["variant"])[wl["cls"]](*wl["args"], *extra)
 
 # stdout carries exactly ONE line (the JSON result): libraries that write to fd 1 (NCCL prints its version
 # banner there) are sent to stderr for the life of the process, and emit() writes to the saved descriptor.
@@ -188,7 +203,9 @@ def cpu_reference(wl, steps, warmup, batch, threads, device="cpu"):
     torch.manual_seed(1)
     np.random.seed(1)
     dev = torch.device(device)
-    model = nio.make_models(wl["variant"])[wl["cls"]](*wl["args"], *(("cpu",) if wl["ndim"] == 1 else ()))
+    model = build_model(wl, "cpu")
+    if wl.get("factory") == "blindno":
+        return blindno_reference(wl, model, steps, warmup, batch, dev)
     is_nio = not hasattr(model, "FNO_input")
     learn = {k for k, _ in model.named_parameters()}
     params = {k: (v.detach().clone().to(dev).requires_grad_(True) if k in learn else v.detach().clone().to(dev))
@@ -215,6 +232,45 @@ def cpu_reference(wl, steps, warmup, batch, threads, device="cpu"):
     for i in range(steps):
         O.train_step(params, opt, fwd, *batches[i % 2][:1], grid, batches[i % 2][1], **kw).item()   # loss.item() as the scripts do
     sync()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3
+
+
+def blindno_reference(wl, model, steps, warmup, batch, dev):
+    """BlinDNO comparator: the same U-Net / attention modules (stock torch kernels) with the FNO heads evaluated by the
+    oracle's torch.fft restatement, trained eagerly with torch.optim.Adam and a loss.item() per step as train_unet.py does."""
+    from oracle import blindno_oracle as O
+
+    class OracleHead(torch.nn.Module):
+        def __init__(self, head):
+            super().__init__()
+            self.head = head                       # keeps the parameters (trained by Adam below)
+
+        def forward(self, x):
+            return O.fno2d_forward(dict(self.head.named_parameters()), x)
+
+    for name in [n for n, _ in model.named_children() if n.startswith("fno_")]:
+        setattr(model, name, OracleHead(getattr(model, name)))
+    model = model.to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=wl["lr"])
+    batches = [(x.to(dev), y.to(dev)) for x, y in make_batches(wl, 2, batch, seed=0)]
+
+    def step(i):
+        opt.zero_grad()
+        loss = torch.nn.functional.mse_loss(model(batches[i % 2][0]), batches[i % 2][1])
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    for i in range(warmup):
+        step(i)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     return batch * steps / dt, dt / steps * 1e3
 
@@ -261,8 +317,7 @@ def run_b200(args, wl, rank, world, local_rank):
     torch.cuda.set_device(dev)
     torch.manual_seed(1)                       # same initial weights on every rank (DDP broadcasts rank 0's)
     np.random.seed(1 + rank)                   # per-rank bag draws, as train_fno.py:78-81
-    extra = (dev,) if wl["ndim"] == 1 else ()
-    model = nio.make_models(wl["variant"])[wl["cls"]](*wl["args"], *extra).to(dev).train()
+    model = build_model(wl, dev).to(dev).train()
     if args.prec == "tf32":
         ops.set_precision(model, ops.PREC_TF32)     # tcgen05 tensor-core kernels where a stage has one
     elif args.prec == "tf32x3":

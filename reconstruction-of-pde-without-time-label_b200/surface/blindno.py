@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from .fno import FNO1d, FNO2d
-from .nio import _BagModel, draw_bag
+from .nio import _BagModel, _idx_tensor, draw_bag
 
 
 def _nd(name: str, nd: int):
@@ -106,11 +106,16 @@ class _PermInvUNet(_BagModel):
         seq = maps.reshape(n_bags, -1, *maps.shape[1:])
         return self.temp_atts[level](seq).mean(dim=1)
 
-    def forward(self, x):
-        if self.subsample:
-            idx = draw_bag(x.shape[1], self.training)
-            if idx is not None:
-                x = x[:, torch.as_tensor(idx, device=x.device)]
+    accepts_idx = True
+
+    def forward(self, x, grid=None, idx=None):
+        """``model(x)`` as in the reference.  ``grid`` is accepted and ignored (these models carry no coordinate
+        input) and ``idx`` is the bag drawn by the caller, as for the NIO / NIO-FNO models, so that
+        ``parallel.FlatTrainer`` can replay the whole step from a CUDA graph per bag size."""
+        if idx is None and self.subsample:
+            idx = _idx_tensor(draw_bag(x.shape[1], self.training), x.device)
+        if idx is not None:
+            x = x.index_select(1, idx)
         n_bags = x.shape[0]
         h = x.reshape(n_bags * x.shape[1], 1, *x.shape[2:])
         skips = []
