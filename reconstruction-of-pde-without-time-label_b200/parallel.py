@@ -187,7 +187,8 @@ class FlatTrainer:
         return draw_bag(n_snapshots, self.model.training)
 
     def _graph_entry(self, x, grid, target, n_keep):
-        key = (n_keep, tuple(x.shape), tuple(target.shape), tuple(grid.shape), bool(self.model.training))
+        key = (n_keep, tuple(x.shape), tuple(target.shape), None if grid is None else tuple(grid.shape),
+               bool(self.model.training))
         ent = self._graphs.get(key)
         if ent is not None:
             return ent
@@ -195,7 +196,7 @@ class FlatTrainer:
         ent = {
             "x": torch.empty(x.shape, dtype=x.dtype, device=dev),
             "target": torch.empty(target.shape, dtype=target.dtype, device=dev),
-            "grid": grid.detach().to(dev).clone(),
+            "grid": None if grid is None else grid.detach().to(dev).clone(),      # (BlinDNO models take no grid)
             "idx": torch.zeros(max(n_keep, 1), dtype=torch.int32, device=dev) if n_keep else None,
         }
         ent["x"].copy_(x)

@@ -562,6 +562,34 @@ def test_graph_replay_of_the_nio_step_matches_eager():
         assert abs(a - b) <= 1e-3 * max(abs(a), 1.0), (l_eager, l_graph)
 
 
+def test_graph_replay_of_the_blindno_step_matches_eager():
+    """BlinDNO (PermInvUNet_attn): model(x) carries no grid; FlatTrainer passes the caller-drawn bag and replays the
+    whole step (U-Net, bag attention, FNO heads on two streams) from a CUDA graph.  First-step loss, NumPy stream
+    position and the update agree with the eager step."""
+    from blindno_b200.parallel import FlatTrainer
+    from blindno_b200.surface import blindno
+
+    def make():
+        torch.manual_seed(3)
+        m = blindno.make_blindno_models("2d_FPE")["PermInvUNet_attn"](base_ch=2, depth=2, input_size=(52, 52)).to(DEV).train()
+        return m, FlatTrainer(m, lr=1e-3)
+
+    g = torch.Generator().manual_seed(0)
+    x, y = torch.randn(2, 55, 52, 52, generator=g).to(DEV), torch.randn(2, 52, 52, 2, generator=g).to(DEV)
+    (_, eager), (_, graphed) = make(), make()
+    graphed.enable_graphs(True)
+    np.random.seed(5)
+    l_eager = eager.step(x, None, y).item()
+    after_eager = np.random.randint(0, 1 << 30)
+    np.random.seed(5)
+    l_graph = graphed.step(x, None, y).item()
+    assert np.random.randint(0, 1 << 30) == after_eager
+    assert len(graphed._graphs) == 1 and graphed.replayed_launches > 0
+    assert abs(l_eager - l_graph) <= 1e-5 * max(abs(l_eager), 1.0)
+    assert (graphed.flat_param - eager.flat_param).abs().max().item() <= 2.1e-3       # one Adam step: <= 2 * lr
+    assert (graphed.flat_param - eager.flat_param).abs().mean().item() <= 1e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # NIO models (DeepONet branch CNN on cuDNN, trunk FFN, pool-before-contract tail, our bag pool + FNO heads)
 # ---------------------------------------------------------------------------------------------
