@@ -287,7 +287,7 @@ def run_reference(args, wl, rank, world):
         "impl": "reference", "metric": wl.get("metric", METRIC), "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "batch": wl["batch"], "bag": wl["bag"], "grid": wl["n"],
+        "config": {"workload": args.workload, "bags_per_gpu": wl["batch"], "snapshots_per_bag": wl["bag"], "grid": wl["n"],
                    "ref_device": args.ref_device,
                    "note": "the reference's algorithm (torch.fft path) restated in oracle/blindno_oracle.py, "
                            + ("run on stock PyTorch CUDA kernels (cuFFT / cuBLAS / ATen, eager): the GPU status-quo comparator"
@@ -462,8 +462,8 @@ def run_b200(args, wl, rank, world, local_rank):
         "metric": wl.get("metric", METRIC), "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "f32 (3xTF32 tensor-core GEMMs)"}[args.prec], "data": "synthetic",
-        "config": {"workload": args.workload, "model": f"{wl['cls']}{wl['args']}", "batch_per_gpu": batch,
-                   "global_batch": batch * world, "bag": wl["bag"],
+        "config": {"workload": args.workload, "operator": f"{wl['cls']}{wl['args'] or wl.get('kwargs', '')}", "bags_per_gpu": batch,
+                   "bags_global": batch * world, "snapshots_per_bag": wl["bag"],
                    "allreduce": ("none (1 GPU)" if world == 1 else
                                  ("heads' region overlapped with the encoder backward + encoder region at the end"
                                   if trainer.split_backward else "one flat all-reduce after backward")), "bag_subsample": "U[50,99] per step (reference)",
