@@ -74,3 +74,24 @@ def test_null_pointers_are_rejected_not_dereferenced():
     assert rc == -1
     rc = L.bdn_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None)
     assert rc == -1
+
+
+def test_stage_entry_points_validate_without_gpu():
+    """The stage-level entry points (what the fno_lift_pad / fno_layer / fno_project custom ops bind) reject bad
+    shapes and null pointers before any CUDA call, and size their workspace on the host."""
+    L = _lib.lib()
+    s = _shape()
+    assert L.bdn_stage_layer_workspace_bytes(C.byref(s)) > 0
+    assert L.bdn_stage_layer_workspace_bytes(C.byref(_shape(m1=39))) == 0
+    assert L.bdn_stage_lift_forward(C.byref(s), None, None, None, None, None) == -1
+    assert L.bdn_stage_layer_forward(C.byref(s), None, 0, None, None, None, None, None, None, None, 0, None) == -1
+    assert L.bdn_stage_layer_backward(C.byref(s), None, None, 0, None, None, None, None, None, None, None, None, None, None,
+                                      0, None) == -1
+    assert L.bdn_stage_project_forward(C.byref(s), None, None, None, None, None, None, None) == -1
+    assert L.bdn_stage_project_backward(C.byref(s), None, None, None, None, None, None, 0, 1, None, None, None, None, None,
+                                        None) == -1
+    assert b"null" in L.bdn_last_error()
+    # an empty batch is a no-op, not an error, whatever the pointers are
+    empty = _shape(images=0)
+    assert L.bdn_stage_project_forward(C.byref(empty), None, None, None, None, None, None, None) == 0
+    assert L.bdn_bag_pool_lift_forward(None, None, None, None, None, 0, 5, 10, 2, 4, None) == 0
