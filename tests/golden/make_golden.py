@@ -237,13 +237,13 @@ def rel_l2(a, b, eps=1e-12):
     return float(np.linalg.norm((a - b).ravel(), 2) / (np.linalg.norm(b.ravel(), 2) + eps))
 
 
-def end_metric():
+def end_metric(variant="2d_FPE", name="endmetric_2d_fpe"):
     """The reference's reported end metric on a fixed synthetic problem: drift / diffusion relative L2 error of
     the de-normalised prediction (2d_FPE/eval_fno.py:72-97, :274-276) at the initial weights and after 6 steps
     of the reference train loop (2d_FPE/train_fno.py:115-143: Adam 5e-4, MSE, a fresh bag subsample per step)."""
     torch.set_num_threads(1)
     g = torch.Generator()
-    N2 = load_reference("2d_FPE", "NIOModules")
+    N2 = load_reference(variant, "NIOModules")        # (2d_Non_conservative_FPE: the two channels are Fx, Fy)
     torch.manual_seed(61)
     ctor = (2, 3, 100, 25, 2, 6, 5, 2)
     model = N2.NIOFP2D_FNO(*ctor)
@@ -292,9 +292,10 @@ def end_metric():
         opt.step()
         losses.append(loss.item())
     metric1 = evaluate()
-    _save("endmetric_2d_fpe", x_train=_np(x_train), y_train=_np(y_train), x_eval=_np(x_eval), y_eval=_np(y_eval),
+    _save(name, x_train=_np(x_train), y_train=_np(y_train), x_eval=_np(x_eval), y_eval=_np(y_eval),
           grid=_np(grid), metric0=metric0, metric1=metric1, losses=np.asarray(losses, dtype=np.float64),
-          **{"meta.ctor": np.asarray(ctor), "meta.np_seed": np.asarray(9), "meta.lr": np.asarray(5e-4)},
+          **{"meta.ctor": np.asarray(ctor), "meta.np_seed": np.asarray(9), "meta.lr": np.asarray(5e-4),
+             "meta.variant": np.asarray(variant)},
           **{"stats." + k: np.asarray(v) for k, v in stats.items()}, **_pack("p.", state0))
 
 
@@ -343,5 +344,6 @@ if __name__ == "__main__":
         main()
     if not wanted or "end_metric" in wanted:
         end_metric()
+        end_metric("2d_Non_conservative_FPE", "endmetric_2d_nc")
     if not wanted or "blindno" in wanted:
         blindno_cases()

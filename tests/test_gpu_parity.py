@@ -621,16 +621,17 @@ def test_nio_models_golden(name):
 # ---------------------------------------------------------------------------------------------
 # the reference's reported end metric (drift / diffusion relative L2, eval_fno.py) is unchanged
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fixture", ["endmetric_2d_fpe", "endmetric_2d_nc"])
 @pytest.mark.parametrize("loop", ["torch_adam", "flat_trainer", "flat_trainer_graphs"])
-def test_end_metric_relative_l2_unchanged(loop):
+def test_end_metric_relative_l2_unchanged(loop, fixture):
     """Fixed synthetic problem, fixture produced by the unmodified reference: the relative L2 errors the eval
     script reports agree to 6 decimals at the given weights, and after 6 steps of the reference train loop
     (Adam 5e-4, MSE, a fresh bag per step) -- run with stock torch.optim.Adam on the drop-in module exactly as
     train_fno.py does, and through FlatTrainer (flat buffers + fused Adam, eager and CUDA-graph replay)."""
     from blindno_b200.parallel import FlatTrainer
     from tests.helpers import end_metric
-    fx = Fixture("endmetric_2d_fpe")
-    model = nio.make_models("2d_FPE")["NIOFP2D_FNO"](*[int(v) for v in fx.meta("ctor")])
+    fx = Fixture(fixture)           # 2d_FPE: drift / diffusion; 2d_Non_conservative_FPE: the force field (Fx, Fy)
+    model = nio.make_models(str(fx.meta("variant")))["NIOFP2D_FNO"](*[int(v) for v in fx.meta("ctor")])
     model.load_state_dict(fx.params, strict=False)
     model = model.to(DEV)
     grid = fx.t("grid").to(DEV)

@@ -185,24 +185,27 @@ def test_nio_oracle_matches_reference_golden(name):
     assert p["fc0.weight"].grad is None and p["fc0.bias"].grad is None
 
 
-def test_end_metric_relative_l2_of_the_oracle_matches_the_reference():
+@pytest.mark.parametrize("fixture,heads", [("endmetric_2d_fpe", ("fno_drift", "fno_diffusion")),
+                                           ("endmetric_2d_nc", ("fno_Fx", "fno_Fy"))])
+def test_end_metric_relative_l2_of_the_oracle_matches_the_reference(fixture, heads):
     """The number the reference reports (drift / diffusion relative L2, eval_fno.py) on a fixed synthetic problem,
     at the initial weights and after 6 steps of the reference train loop: the oracle reproduces both."""
     from tests.helpers import end_metric
-    fx = Fixture("endmetric_2d_fpe")
+    fx = Fixture(fixture)
     p = {k: v.clone() for k, v in fx.params.items()}
     grid = fx.t("grid")
+    fwd = lambda pp, x, g, **kw: O.niofp2d_fno_forward(pp, x, g, heads=heads, **kw)      # noqa: E731
     with torch.no_grad():
-        m0 = end_metric(fx, lambda x: O.niofp2d_fno_forward(p, x, grid))
+        m0 = end_metric(fx, lambda x: fwd(p, x, grid))
     assert np.abs(m0 - fx.arrays["metric0"]).max() < 5e-7          # unchanged to 6 decimals
     for v in p.values():
         v.requires_grad_(True)
     opt = torch.optim.Adam(O.trainable(p), lr=float(fx.meta("lr")))
     np.random.seed(int(fx.meta("np_seed")))
-    losses = [O.train_step(p, opt, O.niofp2d_fno_forward, fx.t("x_train"), grid, fx.t("y_train")).item() for _ in range(6)]
+    losses = [O.train_step(p, opt, fwd, fx.t("x_train"), grid, fx.t("y_train")).item() for _ in range(6)]
     assert np.allclose(losses, fx.arrays["losses"], rtol=2e-5)
     with torch.no_grad():
-        m1 = end_metric(fx, lambda x: O.niofp2d_fno_forward(p, x, grid))
+        m1 = end_metric(fx, lambda x: fwd(p, x, grid))
     assert np.abs(m1 - fx.arrays["metric1"]).max() < 2e-5
 
 
