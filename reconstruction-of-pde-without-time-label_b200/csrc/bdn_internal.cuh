@@ -139,24 +139,25 @@ void launch_adam(float* p, const float* g, float* m, float* v, size_t n, float l
 // device helpers
 // ---------------------------------------------------------------------------
 // Exact (erf) GELU, F.gelu's default (FNOModules.py:113-114, :231-232), evaluated with ONE ex2 and
-// ONE rcp: Phi(x) = 1 - q (x >= 0) or q (x < 0) with q = erfc(|x|/sqrt2)/2 from Abramowitz-Stegun
-// 7.1.26 (|erf error| <= 1.5e-7, i.e. at fp32 rounding level: measured max |gelu error| 4.2e-7 over
-// [-12, 12] against 1.2e-6 for torch's own fp32 gelu, tests/test_cabi_cpu.py documents the check).
-// The same exp gives the density for the derivative, which is what makes the fused backward of the
-// 128-wide projection cheap.
+// ONE rcp.  Phi(x) = 1 - q (x >= 0) or q (x < 0) with q = phi(|x|) * (b1 t + ... + b5 t^5), t = 1 / (1 + p |x|):
+// Abramowitz-Stegun 26.2.17 (the normal-CDF form of 7.1.26; |error| <= 7.5e-8 on the CDF, measured max |gelu error|
+// 4.2e-7 over [-12, 12] against 1.2e-6 for torch's own fp32 gelu; tests/test_cabi_cpu.py restates the formula in
+// NumPy fp32 and checks that bound).  The density phi(x) = exp(-x^2/2)/sqrt(2 pi) comes straight out of the ex2
+// (its constant is folded into the exponent: log2(1/sqrt(2 pi)) = -1.3257...), so the derivative
+// gelu'(x) = Phi + x phi costs one more FMA: that is what makes the recompute-in-backward projection affordable.
+// 12 FMA-pipe instructions + 2 MUFU for (Phi, phi).
 __device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
-  const float u = fabsf(x) * 0.70710678118654752440f;
   float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));
-  float p = 0.5307027145f;               // coefficients already carry the 1/2 of erfc/2
-  p = fmaf(p, t, -0.7265760135f);
-  p = fmaf(p, t, 0.7107068705f);
-  p = fmaf(p, t, -0.142248368f);
-  p = fmaf(p, t, 0.127414796f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(fabsf(x), 0.2316418882663604f, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(x * x, -0.72134752044448170368f, -1.3257480647361592f)));
+  float p = 1.3302745f;
+  p = fmaf(p, t, -1.8212559f);
+  p = fmaf(p, t, 1.7814779f);
+  p = fmaf(p, t, -0.35656378f);
+  p = fmaf(p, t, 0.31938154f);
   const float q = p * t * e;
   cdf = x >= 0.f ? 1.0f - q : q;
-  pdf = 0.39894228040143267794f * e;
+  pdf = e;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
   float cdf, pdf;

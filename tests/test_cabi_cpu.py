@@ -95,3 +95,25 @@ def test_stage_entry_points_validate_without_gpu():
     empty = _shape(images=0)
     assert L.bdn_stage_project_forward(C.byref(empty), None, None, None, None, None, None, None) == 0
     assert L.bdn_bag_pool_lift_forward(None, None, None, None, None, 0, 5, 10, 2, 4, None) == 0
+
+
+def test_gelu_formula_accuracy_in_fp32():
+    """The exact-GELU evaluation the kernels use (csrc/bdn_internal.cuh: Abramowitz-Stegun 26.2.17, one reciprocal
+    and one exponential), restated in NumPy fp32: |Phi error| <= 3.5e-7, |gelu error| <= 5e-7, |phi error| <= 1e-7
+    over [-12, 12] -- at the rounding level of fp32 and below the 1e-5 parity bound by a wide margin."""
+    import math
+    import numpy as np
+    f = np.float32
+    x = np.linspace(-12, 12, 400001).astype(f)
+    t = f(1) / (np.abs(x) * f(0.2316418882663604) + f(1))
+    e = np.exp2((x * x) * f(-0.72134752044448170368) + f(-1.3257480647361592)).astype(f)
+    p = f(1.3302745)
+    for c in (-1.8212559, 1.7814779, -0.35656378, 0.31938154):
+        p = (p * t + f(c)).astype(f)
+    q = (p * t * e).astype(f)
+    cdf = np.where(x >= 0, f(1) - q, q).astype(np.float64)
+    xd = x.astype(np.float64)
+    ref = np.array([0.5 * (1.0 + math.erf(v / math.sqrt(2.0))) for v in xd[::40]])
+    assert np.abs(cdf[::40] - ref).max() <= 3.5e-7
+    assert np.abs(xd[::40] * cdf[::40] - xd[::40] * ref).max() <= 5e-7
+    assert np.abs(e.astype(np.float64) - np.exp(-0.5 * xd * xd) / math.sqrt(2 * math.pi)).max() <= 1e-7
