@@ -456,7 +456,7 @@ static void launch_project_t(const ProjArgs& a, float* out, long total, cudaStre
   const long ntiles = (total + TILE - 1) / TILE;
   const int grid = (int)(ntiles < 148L * 8 ? ntiles : 148L * 8);
   const size_t smem = (size_t)(a.hidden * CP + a.hidden + a.c_out * a.hidden) * sizeof(float);
-  cudaFuncSetAttribute(project_kernel<CP, NOUT, JS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(project_kernel<CP, NOUT, JS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);   // hidden = 512, width 32, 4 outputs: 76 KB
   launch_k(project_kernel<CP, NOUT, JS, PP>, dim3(grid), dim3(PROJ_THREADS), smem, st, a, out);
 }
 

@@ -101,6 +101,31 @@ def test_layer_op_alone_vs_oracle_including_gelu_on_load():
             assert rel_err(got_t.grad, ref_t.grad) < 2e-5, (name, gelu_in)
 
 
+@pytest.mark.parametrize("hidden,c_out,width,shape", [(128, 1, 12, (4, 12, 20, 24)), (256, 2, 30, (6, 30, 50)), (512, 3, 30, (6, 30, 50)),
+                                                    (512, 1, 4, (300, 4, 40, 40))])
+def test_project_op_other_hidden_sizes(hidden, c_out, width, shape):
+    """fno_project on its own with fc1 widths other than the reference's 128 (the C ABI serves up to 512): few-pixel
+    and many-pixel regimes, including the size at which the backward's warp-private accumulators no longer fit
+    shared memory and the shuffle + shared-atomic reduction is used instead."""
+    torch.manual_seed(hidden + c_out)
+    nd = len(shape) - 2
+    z = torch.randn(*shape)
+    fc1_w, fc1_b = torch.randn(hidden, width) / width ** 0.5, torch.randn(hidden)
+    fc2_w, fc2_b = torch.randn(c_out, hidden) / hidden ** 0.5, torch.randn(c_out)
+    out_h, out_w = (shape[2] - 3, shape[3] - 4) if nd == 2 else (1, shape[2] - 7)
+    args = [t.to(DEV).requires_grad_(True) for t in (z, fc1_w, fc1_b, fc2_w, fc2_b)]
+    out = NSO.fno_project(*args, out_h, out_w)
+    gy = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    out.backward(gy.to(DEV))
+    ref = [t.double().requires_grad_(True) for t in (z, fc1_w, fc1_b, fc2_w, fc2_b)]
+    crop = ref[0][..., :out_h, :out_w].permute(0, 2, 3, 1) if nd == 2 else ref[0][..., :out_w].transpose(1, 2)
+    want = F.linear(F.gelu(F.linear(crop, ref[1], ref[2])), ref[3], ref[4])
+    want.backward(gy.double())
+    assert rel_err(out, want) < TOL
+    for a, r, name in zip(args, ref, ("z", "fc1_w", "fc1_b", "fc2_w", "fc2_b")):
+        assert rel_err(a.grad, r.grad) < 2e-5, name
+
+
 def test_pooled_tails_vs_oracle():
     torch.manual_seed(7)
     B, L, n, C = 2, 5, 12, 4
