@@ -41,6 +41,8 @@ def _stage_chain(net, x, ndim):
     (1, (4, 33, 3), dict(modes=7, width=5, n_layers=2, input_dim=3, output_dim=1)),
     (1, (3, 128, 20), dict(modes=40, width=20, n_layers=3, input_dim=20, output_dim=1)),     # the 1D-GPE head (fused 1-D layer)
     (1, (2, 800, 2), dict(modes=64, width=6, n_layers=2, input_dim=2, output_dim=1)),        # too wide for the fused 1-D layer
+    (1, (3, 40, 32), dict(modes=20, width=32, n_layers=8, input_dim=32, output_dim=4)),      # the C ABI's limits: width, c_in, layers, c_out
+    (2, (2, 20, 24, 32), dict(modes=6, width=32, n_layers=2, input_dim=32, output_dim=1)),
 ])
 def test_stage_ops_chain_vs_oracle_and_whole_net(ndim, shape, ctor):
     torch.manual_seed(3)
