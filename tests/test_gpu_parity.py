@@ -283,7 +283,8 @@ def test_full_batch_properties_2d_fpe():
         assert rel_err(lin, 2.0 * layer(a) - 3.0 * layer(b)) < TOL
 
 
-@pytest.mark.parametrize("shape,m", [((400, 4, 76, 76), 12), ((4, 12, 76, 76), 32), ((3200, 4, 100), 12), ((32, 30, 100), 15)])
+@pytest.mark.parametrize("shape,m", [((400, 4, 76, 76), 12), ((4, 12, 76, 76), 32), ((3200, 4, 100), 12), ((32, 30, 100), 15),
+                                     ((160, 4, 320, 320), 12), ((4, 12, 320, 320), 64)])      # the sweep's largest grid
 def test_spectral_backward_is_the_adjoint_at_full_size(shape, m):
     """Size-independent property at the BASELINE shapes (the oracle is too slow there): the spectral convolution is
     linear in x and in W, so its backward must be the exact adjoint in both:
