@@ -33,8 +33,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (FnoGrads, FnoParams, FnoShape, LiftInput, MAX_LAYERS, PREC_FP32, PREC_TF32, PREC_TF32X3, SpectralShape,
-                   check, pad_amount)
+from ._lib import FnoParams, FnoShape, LiftInput, PREC_FP32, PREC_TF32, PREC_TF32X3, SpectralShape, check, pad_amount
 
 __all__ = ["FnoSpec", "set_precision", "stage_wfwd", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat",
            "kernel_launches", "fno_lift_pad", "fno_layer", "fno_project", "OP_NAMES",

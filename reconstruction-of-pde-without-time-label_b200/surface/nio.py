@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops  # noqa: F401  (registers torch.ops.blindno_b200)
 from .baselines import make_encoders
 from .deeponet import FFN, DeepOnetNoBiasOrg
 from .fno import FNO1d, FNO2d
