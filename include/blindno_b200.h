@@ -33,7 +33,7 @@ extern "C" {
 #endif
 
 #define BDN_MAX_LAYERS 8
-#define BDN_ABI_VERSION 1
+#define BDN_ABI_VERSION 2
 
 typedef enum BdnStatus {
   BDN_OK = 0,
@@ -43,14 +43,20 @@ typedef enum BdnStatus {
   BDN_ERR_UNSUPPORTED = -4  /* valid request this build cannot serve              */
 } BdnStatus;
 
-/* Arithmetic of the DFT GEMMs.  FP32 = CUDA-core FFMA (the 1e-5 parity mode);
- * TF32 = tcgen05 tensor cores with TF32 operands, fp32 accumulation in TMEM
- * (bound stated in DESIGN.md).  */
+/* Arithmetic of the DFT GEMMs.
+ *   FP32   = CUDA-core FFMA kernels.
+ *   TF32X3 = tcgen05 tensor cores, every operand split into a TF32 high part and the TF32-rounded
+ *            remainder, three MMAs per K step (lo*hi + hi*lo + hi*hi) accumulated in fp32 in tensor
+ *            memory: fp32-level accuracy, meets the 1e-5 bound.  The default of the 2-D nets.
+ *   TF32   = one MMA per K step (bound 2e-3 on outputs, 1e-2 on gradients).
+ * 2-D nets run the fused tensor-core layer kernels (all four DFT GEMMs of a layer on tcgen05) when the
+ * shape fits their shared-memory plan; bdn_fno_layer_path() tells.  A shape that does not fit runs the
+ * FFMA layer kernels (W-forward stage alone on tcgen05) and says so once on stderr.  1-D nets: the
+ * W-forward stage only. */
 typedef enum BdnPrecision {
-  BDN_PREC_FP32 = 0,     /* CUDA-core FFMA everywhere                                             */
-  BDN_PREC_TF32 = 1,     /* tcgen05 TF32 where a stage has a tensor-core kernel (bound 2e-3)      */
-  BDN_PREC_TF32X3 = 2    /* tcgen05 with operands split into TF32 high + low parts, 3 MMAs per K
-                            step: fp32-level accuracy (meets the 1e-5 bound)                      */
+  BDN_PREC_FP32 = 0,
+  BDN_PREC_TF32 = 1,
+  BDN_PREC_TF32X3 = 2
 } BdnPrecision;
 
 /* ---------------------------------------------------------------------------
@@ -199,6 +205,10 @@ int bdn_stage_layer_backward(const BdnFnoShape* s, const float* gz_out, const fl
                              const float* conv_w, float* gz_in /* overwritten */,
                              float* g_spec_w1, float* g_spec_w2, float* g_conv_w, float* g_conv_b,
                              void* ws, size_t ws_bytes, void* stream);
+/* Which kernels serve the spectral layers of this net (FNO2d.forward 2d_FPE/FNOModules.py:226-232):
+ * 1 = fused tensor-core layer kernels (tc_p / tc_q_fwd / tc_q_bwd), 0 = FFMA layer kernels,
+ * negative = BdnStatus.  Depends on ndim, images, width, hp, wp, m1, m2 and prec only. */
+int bdn_fno_layer_path(const BdnFnoShape* s);
 /* crop + fc1 + exact GELU + fc2   FNOModules.py:116-121 (1-D), :234-239 (2-D).
  * z: the last layer's output [images, width, hp, wp]; out: [images, out_h, out_w, c_out].
  * backward: gz [images, width, hp, wp] is overwritten (zero outside the crop); pooled_g as in

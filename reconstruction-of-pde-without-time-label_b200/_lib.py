@@ -11,6 +11,7 @@ import threading
 
 MAX_LAYERS = 8
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
+ABI_VERSION = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libblindno_b200.so")
@@ -72,6 +73,7 @@ EXPORTS = {
                                           C.c_size_t, _fp]),
     "bdn_stage_layer_backward": (C.c_int, [C.POINTER(FnoShape), _fp, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                                            _fp, _fp, _fp, C.c_size_t, _fp]),
+    "bdn_fno_layer_path": (C.c_int, [C.POINTER(FnoShape)]),
     "bdn_stage_project_forward": (C.c_int, [C.POINTER(FnoShape)] + [_fp] * 7),
     "bdn_stage_project_backward": (C.c_int, [C.POINTER(FnoShape)] + [_fp] * 6 + [C.c_int32, C.c_int32] + [_fp] * 6),
     "bdn_bag_pool_lift_forward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -97,14 +99,13 @@ def lib() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            from . import build as _build
-            _build.build()
+        from . import build as _build
+        _build.ensure_current()       # rebuilds a missing or stale library; raises if it cannot
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(handle, name)     # AttributeError here = header/library mismatch
             fn.restype, fn.argtypes = res, args
-        if handle.bdn_abi_version() != 1:
+        if handle.bdn_abi_version() != ABI_VERSION:
             raise BlindnoError("libblindno_b200.so ABI version mismatch")
         _lib = handle
     return _lib

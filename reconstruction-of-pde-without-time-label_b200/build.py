@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libblindno_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["spectral.cu", "pointwise.cu", "fused1d.cu", "tc_gemm.cu", "api.cu"]
+SOURCES = ["spectral.cu", "pointwise.cu", "fused1d.cu", "tc_gemm.cu", "tc_layer.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -63,6 +63,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with open(stamp, "w") as fh:
         fh.write(fp)
     return LIBPATH
+
+
+def ensure_current() -> str:
+    """What every load of the library goes through: the in-tree .so must have been built from the sources that
+    are in the tree now.  With nvcc present a missing or stale library is rebuilt (the stamp comparison is a hash
+    of csrc/, the header and the flags); without nvcc a stale library is an error, never silently loaded."""
+    stamp = os.path.join(LIBDIR, "build.stamp")
+    fp = _fingerprint()
+    if os.path.exists(LIBPATH) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
+        return LIBPATH
+    try:
+        _nvcc()
+    except RuntimeError:
+        raise RuntimeError(f"{LIBPATH} is missing or was built from other sources than the tree holds "
+                           f"(fingerprint {fp[:12]}), and nvcc is not available to rebuild it")
+    return build()
+
+
+def fingerprint() -> str:
+    """Fingerprint of the sources the loaded library was built from (bench.py prints it)."""
+    return _fingerprint()
 
 
 if __name__ == "__main__":

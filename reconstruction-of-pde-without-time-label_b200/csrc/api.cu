@@ -150,6 +150,8 @@ const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2) {
     pl->tc_fwd_b = upload(img);      // optional: a failed upload only disables the tensor-core path
   }
 
+  tcl_build_tables(pl);              // optional as well (2-D, hp and wp <= 128)
+
   if (!pl->t_wl || !pl->t_lw_cos || !pl->t_lw_sin || !pl->col_fwd || !pl->col_dc ||
       (ndim == 2 && (!pl->t_hk || !pl->t_kh))) {
     set_error(BDN_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -384,9 +386,29 @@ size_t bdn_fno_spec_floats(const BdnFnoShape* s) {
 }
 size_t bdn_fno_workspace_bytes(const BdnFnoShape* s) {
   if (check_fno(s) != BDN_OK) return 0;
-  return 2 * align_up(spec1_bytes(s->images, s->width, s->hp, s->m2)) + 2 * align_up(act_floats1(s) * sizeof(float)) +
+  return 2 * align_up(spec1_bytes(s->images, s->width, s->hp, s->m2)) + 3 * align_up(act_floats1(s) * sizeof(float)) +
          align_up(kspec_floats1(s) * sizeof(float)) +
          (use_mode_major(s) ? align_up((size_t)s->n_layers * wt_floats1(s) * sizeof(float)) : 0) + 256;
+}
+
+// The fused tensor-core layer kernels (tc_layer.cu) serve 2-D nets in the TF32 / 3xTF32 modes when the shape fits
+// their shared-memory plan.  A tensor-core mode that cannot be served says so once on stderr and runs the FFMA
+// kernels (bdn_fno_layer_path reports which path a shape takes; the profile tags name the kernels that ran).
+static bool use_tc_layer(const BdnFnoShape* s, const Plan* pl) {
+  if (s->ndim != 2 || s->prec == BDN_PREC_FP32) return false;
+  if (tcl_supported(pl, s->images, s->width)) return true;
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int, int, int, int>, bool> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_tuple(s->images, s->width, s->hp, s->wp, s->m1, s->m2);
+  if (!seen[key]) {
+    seen[key] = true;
+    fprintf(stderr,
+            "blindno_b200: tensor-core layer path not available for images=%d width=%d grid=%dx%d modes=%dx%d; "
+            "running the fp32 FFMA kernels for this shape\n",
+            s->images, s->width, s->hp, s->wp, s->m1, s->m2);
+  }
+  return false;
 }
 
 static LiftArgs make_lift(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftInput* in) {
@@ -443,8 +465,12 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
   if (!X1 || !Z || (!z_saved && (!zping[0] || !zping[1])))
     return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
   auto zbuf = [&](int k) { return z_saved ? z_saved + (size_t)k * act : zping[k & 1]; };
+  const bool tc = use_tc_layer(s, pl);
+  float* abuf = nullptr;            // act(z_k) planes: written by kernel P, read by kernel Q's 1x1 conv
+  if (tc && s->n_layers > 1 && !(abuf = (float*)cv.take(act * sizeof(float))))
+    return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
   float2* wt = nullptr;
-  if (use_mode_major(s)) {
+  if (use_mode_major(s) && !tc) {
     wt = xs_saved ? (float2*)(xs_saved + (size_t)s->n_layers * ksp)
                   : (float2*)cv.take((size_t)s->n_layers * wt_floats1(s) * sizeof(float));
     if (!wt) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
@@ -457,6 +483,14 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
   for (int k = 0; k < s->n_layers; ++k) {
     const int act_in = k > 0;
     float2* xs_k = xs_saved ? (float2*)(xs_saved + (size_t)k * ksp) : nullptr;
+    if (tc) {
+      float2* xsp = xs_k ? xs_k : X1;
+      launch_tcl_p(pl, zbuf(k), act_in ? abuf : nullptr, xsp, pl->col_dc, s->images, s->width, act_in, s->prec, st);
+      launch_tcl_q(pl, false, xsp, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], act_in ? abuf : zbuf(k),
+                   nullptr, zbuf(k + 1), p->conv_w[k], p->conv_b[k], nullptr, nullptr, pl->col_fwd, s->images, s->width,
+                   act_in, s->prec, st);
+      continue;
+    }
     if (s->ndim == 1 && s->prec == BDN_PREC_FP32 &&
         launch_layer1d(pl, false, zbuf(k), nullptr, zbuf(k + 1), xs_k, (const float2*)p->spec_w1[k], p->conv_w[k],
                        p->conv_b[k], nullptr, nullptr, s->images, s->width, act_in, st))
@@ -499,13 +533,24 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
   float2* GY = (float2*)cv.take(ksp * sizeof(float));
   if (!G1 || !GZ || !gz[0] || !gz[1] || !GY) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
 
-  const float2* wt = use_mode_major(s) ? (const float2*)(xs_saved + (size_t)s->n_layers * ksp) : nullptr;
+  const bool tc = use_tc_layer(s, pl);
+  const float2* wt = use_mode_major(s) && !tc ? (const float2*)(xs_saved + (size_t)s->n_layers * ksp) : nullptr;
   const size_t wt1 = wt_floats1(s) / 2;
   int cur = 0;
   launch_project_bwd(make_proj(s, p, z_saved + (size_t)s->n_layers * act), g_out, pooled_g, n_keep, gz[cur], g->fc1_w,
                      g->fc1_b, g->fc2_w, g->fc2_b, st);
   const int rows = s->images * s->width * s->hp;
   for (int k = s->n_layers - 1; k >= 0; --k) {
+    if (tc) {
+      launch_tcl_p(pl, gz[cur], nullptr, GY, pl->col_fwd, s->images, s->width, 0, s->prec, st);
+      launch_gw_reduce(pl, (const float2*)(xs_saved + (size_t)k * ksp), GY, (float2*)g->spec_w1[k],
+                       (float2*)g->spec_w2[k], s->images, s->width, s->width, st);
+      launch_tcl_q(pl, true, GY, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], gz[cur],
+                   z_saved + (size_t)k * act, gz[cur ^ 1], p->conv_w[k], nullptr, g->conv_w[k], g->conv_b[k], pl->col_dc,
+                   s->images, s->width, k > 0, s->prec, st);
+      cur ^= 1;
+      continue;
+    }
     if (s->ndim == 1 && s->prec == BDN_PREC_FP32 &&
         launch_layer1d(pl, true, z_saved + (size_t)k * act, gz[cur], gz[cur ^ 1], GY, (const float2*)p->spec_w1[k],
                        p->conv_w[k], nullptr, g->conv_w[k], g->conv_b[k], s->images, s->width, k > 0, st)) {
@@ -569,7 +614,17 @@ int bdn_stage_lift_backward(const BdnFnoShape* s, const float* fc0_w, const floa
 
 size_t bdn_stage_layer_workspace_bytes(const BdnFnoShape* s) {
   if (check_fno(s) != BDN_OK) return 0;
-  return 2 * align_up(spec1_bytes(s->images, s->width, s->hp, s->m2)) + align_up(kspec_floats1(s) * sizeof(float)) + 256;
+  return 2 * align_up(spec1_bytes(s->images, s->width, s->hp, s->m2)) + align_up(kspec_floats1(s) * sizeof(float)) +
+         align_up(act_floats1(s) * sizeof(float)) + 256;
+}
+
+int bdn_fno_layer_path(const BdnFnoShape* s) {
+  int rc = check_fno(s);
+  if (rc != BDN_OK) return rc;
+  if (s->ndim != 2 || s->prec == BDN_PREC_FP32) return 0;
+  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  if (!pl) return BDN_ERR_CUDA;
+  return tcl_supported(pl, s->images, s->width) ? 1 : 0;
 }
 
 int bdn_stage_layer_forward(const BdnFnoShape* s, const float* z_in, int32_t act_in, const float* spec_w1,
@@ -587,6 +642,16 @@ int bdn_stage_layer_forward(const BdnFnoShape* s, const float* z_in, int32_t act
   float2* X1 = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
   float2* Z = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
   if (!X1 || !Z) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+  if (use_tc_layer(s, pl)) {
+    float* abuf = nullptr;
+    if (act_in && !(abuf = (float*)cv.take(act_floats1(s) * sizeof(float))))
+      return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+    float2* xsp = xs_saved ? (float2*)xs_saved : X1;
+    launch_tcl_p(pl, z_in, abuf, xsp, pl->col_dc, s->images, s->width, act_in != 0, s->prec, st);
+    launch_tcl_q(pl, false, xsp, (const float2*)spec_w1, (const float2*)spec_w2, act_in ? abuf : z_in, nullptr, z_out,
+                 conv_w, conv_b, nullptr, nullptr, pl->col_fwd, s->images, s->width, act_in != 0, s->prec, st);
+    return check_cuda("bdn_stage_layer_forward");
+  }
   if (s->ndim == 1 && s->prec == BDN_PREC_FP32 &&
       launch_layer1d(pl, false, z_in, nullptr, z_out, (float2*)xs_saved, (const float2*)spec_w1, conv_w, conv_b, nullptr,
                      nullptr, s->images, s->width, act_in != 0, st))
@@ -622,6 +687,14 @@ int bdn_stage_layer_backward(const BdnFnoShape* s, const float* gz_out, const fl
   float2* GZ = (float2*)cv.take(spec1_bytes(s->images, s->width, s->hp, s->m2));
   float2* GY = (float2*)cv.take(kspec_floats1(s) * sizeof(float));
   if (!G1 || !GZ || !GY) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+  if (use_tc_layer(s, pl)) {
+    launch_tcl_p(pl, gz_out, nullptr, GY, pl->col_fwd, s->images, s->width, 0, s->prec, st);
+    launch_gw_reduce(pl, (const float2*)xs_saved, GY, (float2*)g_spec_w1, (float2*)g_spec_w2, s->images, s->width,
+                     s->width, st);
+    launch_tcl_q(pl, true, GY, (const float2*)spec_w1, (const float2*)spec_w2, gz_out, z_in, gz_in, conv_w, nullptr,
+                 g_conv_w, g_conv_b, pl->col_dc, s->images, s->width, act_in != 0, s->prec, st);
+    return check_cuda("bdn_stage_layer_backward");
+  }
   if (s->ndim == 1 && s->prec == BDN_PREC_FP32 &&
       launch_layer1d(pl, true, z_in, gz_out, gz_in, GY, (const float2*)spec_w1, conv_w, nullptr, g_conv_w, g_conv_b,
                      s->images, s->width, act_in != 0, st)) {

@@ -28,6 +28,8 @@ struct Plan {
   // TF32 tensor-core path: the W tables as K-major GEMM operands (see tc_gemm.cu)
   float* tc_fwd_b;   // [ceil(wp/32)][2*m2 rounded up to 16][32] fp32, 128-byte-swizzled smem image (or null)
   float* tc_inv_b;   // reserved for the inverse transform
+  // fused tensor-core layer (tc_layer.cu): the four DFT operands F1..F4 as (hi | lo) no-swizzle K-major smem images
+  float* tcl_f1; float* tcl_f2; float* tcl_f3; float* tcl_f4;
 };
 
 const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2);   // nullptr on failure
@@ -89,6 +91,19 @@ void tc_build_b_image(int wp, int m2, std::vector<float>& img);     // host imag
 bool tc_wfwd_supported(const Plan* pl, const float* x, bool split);
 // act: exact GELU on load; split: 3xTF32 (hi/lo operands, fp32-level accuracy) instead of plain TF32
 bool launch_wfwd_tc(const Plan* pl, const float* x, float2* out, int rows, int act, bool split, cudaStream_t st);
+
+// ---------------------------------------------------------------------------
+// fused tensor-core layer (tc_layer.cu): kernel P (planes -> kept spectrum) and kernel Q (kept spectrum -> planes
+// with the layer epilogue).  prec: 1 = TF32, 2 = 3xTF32.  The launchers return false (nothing launched) when the
+// shape does not fit; tcl_supported says so beforehand.
+// ---------------------------------------------------------------------------
+void tcl_build_tables(Plan* pl);
+bool tcl_supported(const Plan* pl, int images, int C);
+bool launch_tcl_p(const Plan* pl, const float* x, float* a_out, float2* spec_out, const float* pre, int images, int C,
+                  int act, int prec, cudaStream_t st);
+bool launch_tcl_q(const Plan* pl, bool bwd, const float2* xin, const float2* w1, const float2* w2, const float* a_in,
+                  const float* zin, float* out, const float* pw_w, const float* pw_b, float* g_pw_w, float* g_pw_b,
+                  const float* post, int images, int C, int act_in, int prec, cudaStream_t st);
 
 enum WinvMode { WINV_PLAIN = 0, WINV_LAYER_FWD = 1, WINV_LAYER_BWD = 2 };
 struct WinvArgs {

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_channel():
     L = _lib.lib()
-    assert L.bdn_abi_version() == 1
+    assert L.bdn_abi_version() == _lib.ABI_VERSION
     s = _lib.FnoShape()
     s.ndim = 3
     assert L.bdn_fno_workspace_bytes(C.byref(s)) == 0
