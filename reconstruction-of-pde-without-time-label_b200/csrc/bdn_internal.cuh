@@ -29,7 +29,8 @@ struct Plan {
   float* tc_fwd_b;   // [ceil(wp/32)][2*m2 rounded up to 16][32] fp32, 128-byte-swizzled smem image (or null)
   float* tc_inv_b;   // reserved for the inverse transform
   // fused tensor-core layer (tc_layer.cu): the four DFT operands F1..F4 as (hi | lo) no-swizzle K-major smem images
-  float* tcl_f1; float* tcl_f2; float* tcl_f3; float* tcl_f4;
+  float* tcl_f1; float* tcl_f2; float* tcl_f3; float* tcl_f4;   // shared-memory images
+  float* tcl_t1; float* tcl_t3; float* tcl_t4;                   // tensor-memory tables of the operands that can be MMA operand A
 };
 
 const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2);   // nullptr on failure
