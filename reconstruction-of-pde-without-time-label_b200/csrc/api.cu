@@ -343,6 +343,11 @@ int bdn_stage_wfwd(int32_t hp, int32_t wp, int32_t m1, int32_t m2, int32_t rows,
   if (rows == 0) return BDN_OK;
   const Plan* pl = get_plan(ndim, hp, wp, m1, m2);
   if (!pl) return BDN_ERR_CUDA;
+  // a single stage asked for in a tensor-core mode either runs on the tensor cores or fails: no silent change of
+  // the arithmetic (the whole-net calls fall back per shape and say so, see launch_wfwd / use_tc_layer)
+  if (prec != BDN_PREC_FP32 && !wfwd_uses_tensor_cores(pl, x, rows, prec))
+    return set_error(BDN_ERR_UNSUPPORTED, "W-forward DFT wp=%d modes=%d rows=%d does not fit the tcgen05 kernel in mode %d", wp,
+                     m2, rows, prec);
   launch_wfwd(pl, x, (float2*)out, rows, act, (cudaStream_t)stream, prec);
   return check_cuda("bdn_stage_wfwd");
 }

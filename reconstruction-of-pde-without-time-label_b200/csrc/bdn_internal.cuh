@@ -29,7 +29,7 @@ struct Plan {
   float* tc_fwd_b;   // [ceil(wp/32)][2*m2 rounded up to 16][32] fp32, 128-byte-swizzled smem image (or null)
   float* tc_inv_b;   // reserved for the inverse transform
   // fused tensor-core layer (tc_layer.cu): the four DFT operands F1..F4 as (hi | lo) no-swizzle K-major smem images
-  float* tcl_f1; float* tcl_f2; float* tcl_f3; float* tcl_f4;   // shared-memory images
+  float* tcl_f1; float* tcl_f1r; float* tcl_f2; float* tcl_f3; float* tcl_f4;   // shared-memory images
   float* tcl_t1; float* tcl_t3; float* tcl_t4;                   // tensor-memory tables of the operands that can be MMA operand A
 };
 
@@ -55,7 +55,9 @@ struct LaunchScope {
 // ---------------------------------------------------------------------------
 // rows x wp real -> rows x m2 complex; act != 0 applies exact GELU on load.
 // prec = BDN_PREC_TF32 routes eligible calls (no activation on load, shape fits) to the tcgen05 kernel.
-void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st, int prec = 0);
+// returns true when the tcgen05 kernel ran (false: the FFMA kernel)
+bool launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st, int prec = 0);
+bool wfwd_uses_tensor_cores(const Plan* pl, const float* x, int rows, int prec);
 
 // 2-D middle stage for one pass over `images` images:
 //   in  [images, ca, hp, m2] complex  --H fwd, *pre--> spec_out [images, ca, K, m2] (if non-null)

@@ -8,6 +8,11 @@
 // FNO2d.forward :226-232 / FNO1d.forward :108-114.
 #include "bdn_internal.cuh"
 
+#include <cstdio>
+#include <mutex>
+#include <set>
+#include <tuple>
+
 namespace bdn {
 
 // ===========================================================================
@@ -243,18 +248,29 @@ __global__ void __launch_bounds__(256) wfwd_pipe_kernel(const WfwdParams p) {
   }
 }
 
-void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st, int prec) {
+bool wfwd_uses_tensor_cores(const Plan* pl, const float* x, int rows, int prec) {
+  return (prec == 1 || prec == 2) && rows >= 128 && tc_wfwd_supported(pl, x, prec == 2);
+}
+
+bool launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act, cudaStream_t st, int prec) {
   // prec 1 = TF32 tensor cores (2e-3 mode); prec 2 = 3xTF32 tensor cores (operands split into TF32 high and
-  // low parts, three MMAs per K step: fp32-level accuracy).  Either falls back to the FFMA kernel below when
-  // the shape does not fit the tensor-core kernel's shared memory budget.
-  if ((prec == 1 || prec == 2) && rows >= 128 && tc_wfwd_supported(pl, x, prec == 2) &&
-      launch_wfwd_tc(pl, x, out, rows, act, prec == 2, st))
-    return;
+  // low parts, three MMAs per K step: fp32-level accuracy).  A shape that does not fit the tensor-core kernel's
+  // shared-memory budget runs the FFMA kernel below: the return value says which (true = tcgen05), the profile
+  // tag names the kernel, and the first such fallback of a shape is reported on stderr.
+  if (wfwd_uses_tensor_cores(pl, x, rows, prec) && launch_wfwd_tc(pl, x, out, rows, act, prec == 2, st)) return true;
+  if (prec == 1 || prec == 2) {
+    static std::mutex mu;
+    static std::set<std::tuple<int, int, int>> seen;
+    std::lock_guard<std::mutex> lock(mu);
+    if (seen.insert(std::make_tuple(pl->wp, pl->m2, prec)).second)
+      fprintf(stderr, "blindno_b200: W-forward DFT (wp=%d, modes=%d, rows=%d) does not fit the tcgen05 kernel in %s mode; "
+                      "running the fp32 FFMA kernel\n", pl->wp, pl->m2, rows, prec == 2 ? "3xTF32" : "TF32");
+  }
   LaunchScope scope(act ? "wfwd_gelu" : "wfwd", st, pl->m2);
   const int m2 = pl->m2, wp = pl->wp;
   if ((wp & 3) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) {   // bulk copies need 16-byte rows
     launch_wfwd_generic(pl, x, out, rows, act, st);
-    return;
+    return false;
   }
   WfwdParams p;
   p.x = x; p.out = out; p.t_wl = pl->t_wl; p.rows = rows; p.wp = wp; p.m2 = m2; p.act = act;
@@ -270,7 +286,7 @@ void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act,
   while (rt > 1 && (ceil_div(rows, 32 * rt * p.nrg) < 2 * 148 || smem_of(rt) > 100 * 1024)) rt >>= 1;
   if (smem_of(rt) > 200 * 1024) {
     launch_wfwd_generic(pl, x, out, rows, act, st);
-    return;
+    return false;
   }
   const int BR = 32 * rt * p.nrg;
   p.ntiles = ceil_div(rows, BR);
@@ -285,6 +301,7 @@ void launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act,
   }
   if (rt == 4) BDN_WFWD(4) else if (rt == 2) BDN_WFWD(2) else BDN_WFWD(1)
 #undef BDN_WFWD
+  return false;
 }
 
 // ===========================================================================

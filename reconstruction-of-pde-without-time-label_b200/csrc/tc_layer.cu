@@ -1041,7 +1041,7 @@ using namespace tcl;
 
 // Built by get_plan for 2-D shapes that can ever fit (hp, wp <= 128); a failed upload only disables the path.
 void tcl_build_tables(Plan* pl) {
-  pl->tcl_f1 = pl->tcl_f2 = pl->tcl_f3 = pl->tcl_f4 = pl->tcl_t1 = pl->tcl_t3 = pl->tcl_t4 = nullptr;
+  pl->tcl_f1 = pl->tcl_f1r = pl->tcl_f2 = pl->tcl_f3 = pl->tcl_f4 = pl->tcl_t1 = pl->tcl_t3 = pl->tcl_t4 = nullptr;
   if (pl->ndim != 2 || pl->hp > 128 || pl->wp > 128 || (pl->wp & 3) != 0 || 2 * pl->m2 > 128) return;
   const int hp = pl->hp, wp = pl->wp, m1 = pl->m1, m2 = pl->m2, K = pl->K;
   const double two_pi = 6.283185307179586476925286766559;
@@ -1072,6 +1072,8 @@ void tcl_build_tables(Plan* pl) {
   std::vector<float> img;
   build_image(img, d.rowsF1, d.K1, 1, f1);
   pl->tcl_f1 = upload_f(img);
+  build_image(img, 128, d.K1, 1, [&](int r, int w) { return f1(r % (128 / d.rep1), w); });
+  pl->tcl_f1r = upload_f(img);      // rows replicated rep1 times: every TMEM quadrant gets a copy of the S1 result
   // F2 (B operand of S2): rows (k, cos|sin), K = h
   build_image(img, d.N2, d.K2, 1, [&](int n, int h) {
     if (n >= 2 * K || h >= hp) return 0.0;
@@ -1088,9 +1090,9 @@ void tcl_build_tables(Plan* pl) {
   build_tmem_table(img, d.tiles3, d.K3, f3);
   pl->tcl_t3 = upload_f(img);
   pl->tcl_t4 = pl->tcl_t3;      // (S4's constant operand is the B operand: always from shared memory)
-  if (!pl->tcl_f1 || !pl->tcl_f2 || !pl->tcl_f3 || !pl->tcl_f4 || !pl->tcl_t1 || !pl->tcl_t3 || !pl->tcl_t4) {
+  if (!pl->tcl_f1 || !pl->tcl_f1r || !pl->tcl_f2 || !pl->tcl_f3 || !pl->tcl_f4 || !pl->tcl_t1 || !pl->tcl_t3 || !pl->tcl_t4) {
     cudaGetLastError();
-    pl->tcl_f1 = pl->tcl_f2 = pl->tcl_f3 = pl->tcl_f4 = pl->tcl_t1 = pl->tcl_t3 = pl->tcl_t4 = nullptr;
+    pl->tcl_f1 = pl->tcl_f1r = pl->tcl_f2 = pl->tcl_f3 = pl->tcl_f4 = pl->tcl_t1 = pl->tcl_t3 = pl->tcl_t4 = nullptr;
   }
 }
 
@@ -1181,6 +1183,7 @@ static bool plan_p(const Plan* pl, int images, int C, int passes, PParams& p, si
     if (p.split1) p.ts1 = 0;
   }
   p.rep1 = p.ts1 ? d.rep1 : 1;
+  int rowsF1 = d.rowsF1;
   p.colF1 = 0;
   p.colD = p.ts1 ? (uint32_t)(2 * p.K1) : 0u;
   p.tmem_cols = pow2_cols((int)p.colD + (p.split1 ? 3 * cg * p.N1 : dcols));
@@ -1188,14 +1191,24 @@ static bool plan_p(const Plan* pl, int images, int C, int passes, PParams& p, si
   if (nblk > NW * 11) return false;
   maxb = nblk <= NW * 5 ? 5 : (nblk <= NW * 7 ? 7 : (nblk <= NW * 9 ? 9 : 11));
   const int rowsA1 = p.N1, rowsA2 = pad_to(((cg * pl->m2 + 15) / 16) * 32, 8);
-  p.lboA1 = ns_lbo(rowsA1); p.lboF1 = ns_lbo(d.rowsF1); p.lboA2 = ns_lbo(rowsA2); p.lboF2 = ns_lbo(p.N2);
-  p.partA1 = ns_part_bytes(rowsA1, p.K1); p.partF1 = ns_part_bytes(d.rowsF1, p.K1);
+  p.lboA1 = ns_lbo(rowsA1); p.lboA2 = ns_lbo(rowsA2); p.lboF2 = ns_lbo(p.N2);
+  p.partA1 = ns_part_bytes(rowsA1, p.K1);
   p.partA2 = ns_part_bytes(rowsA2, p.K2); p.partF2 = ns_part_bytes(p.N2, p.K2);
   p.passes = passes;
-  // layouts tried in order: two A1 buffers + own A2; one A1 buffer + own A2; A2 overlaid on the single A1 buffer
-  for (int variant = 0; variant < 3; ++variant) {
-    const int nbuf = variant == 0 ? 2 : 1;
-    const bool overlay = variant == 2;
+  // F1 from shared memory: first with its rows replicated over the 128 accumulator lanes (E1 then runs on every SM
+  // sub-partition instead of the one that owns lanes 0..31), then compact.
+  // A-operand layouts tried in order: two A1 buffers + own A2; one A1 buffer + own A2; A2 overlaid on the single A1 buffer
+  for (int variant = 0; variant < 6; ++variant) {
+    const bool replicate = variant < 3 && !p.ts1 && d.rep1 > 1 && !p.split1;
+    if (variant < 3 && !replicate) continue;
+    if (!p.ts1) {
+      rowsF1 = replicate ? 128 : d.rowsF1;
+      p.rep1 = replicate ? d.rep1 : 1;
+    }
+    p.lboF1 = ns_lbo(rowsF1);
+    p.partF1 = ns_part_bytes(rowsF1, p.K1);
+    const int nbuf = variant % 3 == 0 ? 2 : 1;
+    const bool overlay = variant % 3 == 2;
     uint32_t off = 0;
     p.offF1 = off; if (!p.ts1) off += 2 * p.partF1;
     p.offF2 = off; off += 2 * p.partF2;
@@ -1285,7 +1298,7 @@ bool launch_tcl_p(const Plan* pl, const float* x, float* a_out, float2* spec_out
   if (!plan_p(pl, images, C, prec == 2 ? 3 : 1, p, smem, maxb)) return false;
   LaunchScope scope(act ? "tc_p_gelu" : "tc_p", st, C);
   p.x = x; p.a_out = a_out; p.spec_out = spec_out; p.pre = pre;
-  p.f1 = pl->tcl_f1; p.f2 = pl->tcl_f2; p.t1 = pl->tcl_t1;
+  p.f1 = (!p.ts1 && p.rep1 > 1) ? pl->tcl_f1r : pl->tcl_f1; p.f2 = pl->tcl_f2; p.t1 = pl->tcl_t1;
   p.act = act;
   p.dbg = dbg_buffer();
   const int grid = p.nitems < sm_count() ? p.nitems : sm_count();

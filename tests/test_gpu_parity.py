@@ -482,7 +482,9 @@ def test_tf32_mode_whole_model_within_stated_bound():
     torch.cuda.synchronize()
     prof = ops.profile_end()
     assert ops.kernel_launches() > profile0
-    assert any(k.startswith("wfwd_tc") for k in prof), f"the tcgen05 kernel did not run: {sorted(prof)}"
+    for tag in ("tc_p", "tc_q_fwd", "tc_q_bwd"):      # every spectral layer ran the fused tensor-core kernels
+        assert any(k.startswith(tag) for k in prof), f"{tag}* did not run: {sorted(prof)}"
+    assert not any(k.startswith(("wfwd", "core2d", "winv")) for k in prof), f"an FFMA layer kernel ran: {sorted(prof)}"
     (y32, g32, _), _ = _oracle_grads(O.niofp2d_fno_forward, params, x, gy, extra=(grid,), heads=heads, idx=idx)
     assert rel_err(y, y32) < TF32_TOL
     got = dict(model.named_parameters())
@@ -494,8 +496,8 @@ def test_tf32_mode_whole_model_within_stated_bound():
 
 
 def test_tf32x3_mode_whole_model_meets_the_fp32_bound():
-    """BDN_PREC_TF32X3: the W-forward DFT GEMMs on tcgen05 with operands split into TF32 high + low parts (3 MMAs
-    per K step).  Through the whole 2-D NIO-FNO at the default widths / modes the outputs stay within the FP32
+    """BDN_PREC_TF32X3: all four DFT GEMMs of every spectral layer on tcgen05 (csrc/tc_layer.cu) with operands split
+    into TF32 high + low parts (3 MMAs per K step).  Through the whole 2-D NIO-FNO at the default widths / modes the outputs stay within the FP32
     bound (1e-5) of the fp64 oracle and the gradients within the same rule as the FFMA path."""
     torch.manual_seed(1)
     model = nio.make_models("2d_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 3, 12, 32, 2)
@@ -512,7 +514,9 @@ def test_tf32x3_mode_whole_model_meets_the_fp32_bound():
     y.backward(gy.to(DEV))
     torch.cuda.synchronize()
     prof = ops.profile_end()
-    assert any(k.startswith("wfwd_tc") for k in prof), f"the tcgen05 kernel did not run: {sorted(prof)}"
+    for tag in ("tc_p", "tc_q_fwd", "tc_q_bwd"):
+        assert any(k.startswith(tag) for k in prof), f"{tag}* did not run: {sorted(prof)}"
+    assert not any(k.startswith(("wfwd", "core2d", "winv")) for k in prof), f"an FFMA layer kernel ran: {sorted(prof)}"
     (y32, g32, _), (y64, g64, _) = _oracle_grads(O.niofp2d_fno_forward, params, x, gy, extra=(grid,), heads=heads, idx=idx)
     assert rel_err(y, y64) < TOL
     got = dict(model.named_parameters())
