@@ -5,9 +5,20 @@ fused Adam over the flat buffer.
 Replaces what ``accelerate`` + DistributedDataParallel do around the reference's loop
 (2d_FPE/train_fno.py:75-77,116-123,139-145): DDP ships every parameter (13.5 M floats, of which
 9.9 M belong to the Encoder2D branch NIOFP2D_FNO never calls, hence find_unused_parameters=True)
-in 25 MiB buckets; here only the live gradients (3.56 M floats for the 2-D NIO-FNO) travel, in one
-call on one registered buffer.  Samples are sharded across ranks (pure data parallel, weak scaling),
-each rank draws its own bag subsample from its own NumPy stream (seed + rank, train_fno.py:78-81).
+in 25 MiB buckets; here only the live gradients (3.56 M floats for the 2-D NIO-FNO) travel, as plain
+NCCL all-reduce calls on slices of one flat buffer (one call, or two to three when the heads' region is
+reduced early under the encoder backward).  Samples are sharded across ranks (pure data parallel, weak
+scaling), each rank draws its own bag subsample from its own NumPy stream (seed + rank,
+train_fno.py:78-81).
+
+Replica consistency: the reference seeds every process differently (seed + process_index,
+train_fno.py:78-81) and relies on DistributedDataParallel broadcasting rank 0's parameters and buffers
+when it wraps the model.  FlatTrainer does the same at construction (``sync_from_rank0``): the flat
+parameter buffer, the parameters outside it (the detached ``fc0``, the never-called branch) and every
+module buffer (BatchNorm statistics of the NIO / BlinDNO models) are broadcast from rank 0.  After that
+BatchNorm running statistics evolve per rank: DDP's default re-broadcasts rank 0's buffers before every
+forward, but they do not enter train-mode outputs or gradients, so the trained weights are identical;
+``sync_buffers()`` restores DDP's state (e.g. before saving a checkpoint or switching to eval()).
 
 The optimiser maths is torch.optim.Adam's (lr, betas, eps; no weight decay); parameters that never
 receive a gradient in the reference (``fc0`` used through ``.data``; the unused branch) are left
@@ -46,7 +57,7 @@ class FlatTrainer:
     """Owns the flat parameter / gradient / Adam-state buffers of ``model`` and runs train steps."""
 
     def __init__(self, model: nn.Module, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group: Optional[dist.ProcessGroup] = None, loss_fn=None):
+                 process_group: Optional[dist.ProcessGroup] = None, loss_fn=None, sync_from_rank0: bool = True):
         self.model = model
         self.lr, self.betas, self.eps = lr, betas, eps
         self.group = process_group
@@ -65,6 +76,10 @@ class FlatTrainer:
         self.split_backward = self.world > 1 and hasattr(model, "FNO_input") and hasattr(model, "_expose_lifted")
         self._comm_stream = None
         self._late_span = None
+        # The heads' Adam update follows their early all-reduce on the communication stream, so that only the
+        # small FNO_input region is reduced and updated after the encoder backward (off: one Adam over everything).
+        self.early_adam = True
+        self.timing = None                 # set to a dict by enable_timing(): per-step event pairs of the step's tail
 
         named = live_parameters(model)
         if not named:
@@ -117,6 +132,39 @@ class FlatTrainer:
                 mod._grad_sink = self.flat_grad[base: base + n]
                 if mod is getattr(model, "FNO_input", None):
                     self._late_span = (base, base + n)
+        if sync_from_rank0 and self.world > 1:
+            self.sync_from_rank0()
+
+    # -- replica consistency ---------------------------------------------------------------
+    def _src(self) -> int:
+        return dist.get_global_rank(self.group, 0) if self.group is not None else 0
+
+    def sync_from_rank0(self):
+        """What DistributedDataParallel does when it wraps a model: every rank continues from rank 0's parameters
+        and buffers (the reference builds its replicas from different seeds, 2d_FPE/train_fno.py:78-81)."""
+        if self.world == 1:
+            return
+        src = self._src()
+        dist.broadcast(self.flat_param, src=src, group=self.group)
+        flat_ids = {id(p) for _, p in live_parameters(self.model)}
+        seen = set()
+        with torch.no_grad():
+            for p in self.model.parameters():
+                if id(p) in flat_ids or id(p) in seen:
+                    continue
+                seen.add(id(p))
+                t = torch.view_as_real(p.data) if p.is_complex() else p.data
+                dist.broadcast(t, src=src, group=self.group)
+        self.sync_buffers()
+
+    def sync_buffers(self):
+        """Rank 0's module buffers (BatchNorm running statistics, step counters) to every rank."""
+        if self.world == 1:
+            return
+        src = self._src()
+        with torch.no_grad():
+            for b in self.model.buffers():
+                dist.broadcast(b, src=src, group=self.group)
 
     # -- pieces of a step ----------------------------------------------------------------
     def zero_grad(self):
@@ -143,6 +191,10 @@ class FlatTrainer:
         with torch.cuda.stream(self._comm_stream):
             for lo, hi in self._early_spans():
                 dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+                if self.early_adam:
+                    # same stream: the update starts when this span's sum has landed, under the encoder backward
+                    # (which reads none of these parameters)
+                    self._adam(lo, hi, self.step_count + 1)
 
     def reduce_late(self):
         if self.world == 1:
@@ -151,13 +203,17 @@ class FlatTrainer:
         dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.group)
         torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
 
-    def optimizer_step(self):
-        """One fused Adam kernel over the flat buffer (1/world of DDP's mean folded in).  There is no CPU
-        arithmetic here: CPU tensors make the op raise.  (The gloo host-logic test replaces ``adam_fn`` with
+    def _adam(self, lo: int, hi: int, step: int):
+        self.adam_fn(self.flat_param[lo:hi], self.flat_grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], lr=self.lr,
+                     betas=self.betas, eps=self.eps, step=step, grad_scale=1.0 / self.world)
+
+    def optimizer_step(self, spans=None):
+        """Fused Adam over the flat buffer, or over ``spans`` of it (1/world of DDP's mean folded in).  There is no
+        CPU arithmetic here: CPU tensors make the op raise.  (The gloo host-logic test replaces ``adam_fn`` with
         a torch-op restatement of its own.)"""
         self.step_count += 1
-        self.adam_fn(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr=self.lr, betas=self.betas,
-                     eps=self.eps, step=self.step_count, grad_scale=1.0 / self.world)
+        for lo, hi in (spans if spans is not None else [(0, self.numel)]):
+            self._adam(lo, hi, self.step_count)
 
     # -- the step --------------------------------------------------------------------------
     def step(self, x: torch.Tensor, grid: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
@@ -275,15 +331,48 @@ class FlatTrainer:
             # pageable source: the runtime stages it before returning, so the host array may be reused
             ent["idx"].copy_(torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int32)))
         ent["graph"].replay()
+        late_only = None
         if ent["graph_b"] is not None:
-            self.reduce_early()            # heads' gradients travel while the per-snapshot net back-propagates
+            t = self._tail_events()
+            self.reduce_early()            # heads' gradients travel (and are applied) while the per-snapshot net back-propagates
             ent["graph_b"].replay()
+            if t:
+                t[0].record()
             self.reduce_late()
+            if t:
+                t[1].record()
+            if self.early_adam and self.world > 1:
+                late_only = [self._late_span]
         else:
             self.reduce_gradients()
         self.replayed_launches += ent["launches"]
-        self.optimizer_step()
+        self.optimizer_step(late_only)
+        if ent["graph_b"] is not None and t:
+            t[2].record()
         return ent["loss"]
+
+    # -- timing of the step's tail (bench.py's scaling_breakdown) ---------------------------------
+    def enable_timing(self, enabled: bool = True):
+        self.timing = {"events": []} if enabled else None
+        return self
+
+    def _tail_events(self):
+        if self.timing is None:
+            return None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self.timing["events"].append(ev)
+        return ev
+
+    def tail_times_ms(self):
+        """(mean ms between the end of the encoder backward and the end of the late all-reduce [includes waiting for the
+        slowest rank and for the early all-reduce], mean ms of the Adam that follows) over the recorded steps."""
+        if not self.timing or not self.timing["events"]:
+            return None
+        torch.cuda.synchronize(self.device)
+        red = [a.elapsed_time(b) for a, b, _ in self.timing["events"]]
+        adam = [b.elapsed_time(c) for _, b, c in self.timing["events"]]
+        self.timing["events"].clear()
+        return sum(red) / len(red), sum(adam) / len(adam)
 
     def prepare_graphs(self, x, grid, target, bag_sizes=None):
         """Capture the graphs of every bag size a training run can draw (L in [50, L0)) up front."""

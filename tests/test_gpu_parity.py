@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from blindno_b200 import ops
+from blindno_b200 import _lib, ops
 from blindno_b200.surface import fno, nio
 from oracle import blindno_oracle as O
 from oracle import dft64
@@ -456,7 +456,15 @@ def test_stage_wfwd_fp32_and_tf32_tensor_core(rows, wp, m2, hp, m1):
     assert rel_err(ops.stage_wfwd(x.to(DEV), m2, hp=hp, m1=m1, act=True), want_act) < TOL
     assert rel_err(ops.stage_wfwd(x.to(DEV), m2, hp=hp, m1=m1, act=True, prec=ops.PREC_TF32), want_act) < TF32_TOL
     # 3xTF32: operands split into TF32 high and low parts, three MMAs per K step -> the fp32 bound
+    # (the split operands double the kernel's shared memory: 32 modes at width 76 do not fit, and the stage call
+    # then refuses instead of computing in another arithmetic -- round 1 fell back to the FFMA kernel silently)
+    kch, n_pad = -(-wp // 32), -(-2 * m2 // 16) * 16            # the kernel's budget (csrc/tc_gemm.cu: tc_smem_bytes)
+    fits3 = 1024 + 2 * kch * 16384 * 2 + -(-kch * n_pad * 128 * 2 // 1024) * 1024 + 256 <= 224 * 1024
     for act, ref in ((False, want), (True, want_act)):
+        if not fits3:
+            with pytest.raises(_lib.BlindnoError, match="does not fit the tcgen05 kernel"):
+                ops.stage_wfwd(x.to(DEV), m2, hp=hp, m1=m1, act=act, prec=ops.PREC_TF32X3)
+            continue
         got3 = ops.stage_wfwd(x.to(DEV), m2, hp=hp, m1=m1, act=act, prec=ops.PREC_TF32X3)
         e3 = rel_err(got3, ref)
         assert e3 < TOL, f"tcgen05 3xTF32 W-forward (act={act}): rel err {e3:.3e}"

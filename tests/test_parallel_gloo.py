@@ -99,3 +99,85 @@ def test_live_parameters_skip_dead_ones():
     names = [n for n, _ in live_parameters(model)]
     assert not any(n.startswith(("fc0.", "branch.")) for n in names)          # Q7, Q8
     assert any(n.startswith("FNO_input.") for n in names) and any(n.startswith("fno_drift.") for n in names)
+
+
+def _sync_worker(rank, world, port, out):
+    """Replicas built from different seeds (the reference seeds with seed + process_index, 2d_FPE/train_fno.py:78-81)
+    must continue from rank 0's weights and buffers, as under DistributedDataParallel."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(11 + rank)                           # DIFFERENT initial weights per rank
+        model = nio.make_models("1d_GPE")["NIOFP_schrodinger"](1, 3, 100, 25, 1, 4, 5, 1, "cpu")
+        for b in model.buffers():                              # BatchNorm statistics differ too
+            if b.dtype.is_floating_point:
+                b.add_(float(rank))
+        trainer = FlatTrainer(model, lr=1e-3)
+        state = torch.cat([v.detach().reshape(-1).double() if not v.is_complex() else torch.view_as_real(v.detach()).reshape(-1).double()
+                           for v in model.state_dict().values()])
+        gathered = [torch.zeros_like(state) for _ in range(world)]
+        dist.all_gather(gathered, state)
+        spread = max((g - gathered[0]).abs().max().item() for g in gathered)
+        # without the broadcast the ranks would keep their own weights
+        torch.manual_seed(11 + rank)
+        lone = nio.make_models("1d_GPE")["NIOFP_schrodinger"](1, 3, 100, 25, 1, 4, 5, 1, "cpu")
+        unsynced = FlatTrainer(lone, lr=1e-3, sync_from_rank0=False)
+        flat = [torch.zeros_like(unsynced.flat_param) for _ in range(world)]
+        dist.all_gather(flat, unsynced.flat_param)
+        out[rank] = (spread, (flat[0] - flat[1]).abs().max().item(), trainer.flat_param.abs().sum().item())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicas_start_from_rank0_weights_and_buffers():
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_sync_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for rank in range(world):
+        spread, unsynced_spread, norm = out[rank]
+        assert spread == 0.0, f"rank {rank}: state_dict differs across ranks by {spread} after construction"
+        assert unsynced_spread > 1e-3 and norm > 0           # the seeds really differed
+    assert out[0][2] == out[1][2]
+
+
+def _split_worker(rank, world, port, out):
+    """The split step's tail: heads' region reduced early and updated early (its own Adam call on the same step number),
+    encoder region reduced and updated late -- must equal one all-reduce + one Adam over the whole buffer."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def make():
+            torch.manual_seed(5)
+            m = nio.make_models("2d_FPE")["NIOFP2D_FNO"](2, 3, 100, 25, 1, 4, 3, 2)
+            t = FlatTrainer(m, lr=1e-2)
+            t.adam_fn = _torch_adam
+            return t
+        split, whole = make(), make()
+        assert split._late_span is not None and 0 < split._late_span[1] - split._late_span[0] < split.numel
+        for step in range(3):
+            g = torch.Generator().manual_seed(7 * step + rank)
+            grad = torch.randn(split.numel, generator=g)
+            for t in (split, whole):
+                t.flat_grad.copy_(grad)
+            # whole: one collective, one Adam
+            whole.reduce_gradients()
+            whole.optimizer_step()
+            # split (what _graph_step does, minus CUDA streams): early spans reduced + updated, then the late span
+            for lo, hi in split._early_spans():
+                dist.all_reduce(split.flat_grad[lo:hi])
+                split._adam(lo, hi, split.step_count + 1)
+            a, b = split._late_span
+            dist.all_reduce(split.flat_grad[a:b])
+            split.optimizer_step([split._late_span])
+        out[rank] = ((split.flat_param - whole.flat_param).abs().max().item(), split.step_count, whole.step_count)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_split_tail_equals_single_allreduce_and_adam():
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_split_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for rank in range(world):
+        err, s1, s2 = out[rank]
+        assert err == 0.0 and s1 == s2 == 3
