@@ -15,7 +15,10 @@ forward, loss, backward, gradient all-reduce (N > 1), Adam.  Data: synthetic N(0
           (pinned) batches: H2D of every batch and D2H of the loss inside the timed region
   roofline   dominant kernel of the step, per-kernel device time from CUDA event pairs recorded by
           the library around every launch in a separate profiled pass of the same steps
-  cpu_baseline  the CPU oracle's train step (torch CPU, all host threads) on the same workload
+  cpu_baseline  the reference's own train step on the host CPU (all host threads) on the same workload: the
+          UNMODIFIED reference modules staged under oracle/_ref (kind "reference"; oracle/stage_reference.py), or --
+          when they are not staged -- the oracle's restatement of them (kind "port")
+  --impl reference   the same CPU arm as its own JSON line (same config / metric / steps as the CUDA arm)
 """
 from __future__ import annotations
 
@@ -53,6 +56,15 @@ WORKLOADS = {
                        factory="blindno", head_width=12, head_modes=32),
 }
 METRIC = "nio_fno_train_samples_per_sec"
+
+
+def make_config(args, wl, world):
+    """What defines the measured job -- identical in both arms (the driver compares the two lines' configs)."""
+    batch = args.batch_per_gpu or wl["batch"]
+    return {"workload": args.workload, "operator": f"{wl['cls']}{wl['args'] or wl.get('kwargs', '')}", "bags_per_gpu": batch,
+            "bags_global": batch * world, "snapshots_per_bag": wl["bag"], "grid": wl["n"],
+            "bag_subsample": "U[50,99] per step (reference)", "parallelism": f"dp{world}",
+            "step": "zero_grad + forward + MSE + backward + gradient mean over ranks + Adam", "arithmetic": "fp32"}
 
 
 def build_model(wl, device=None):
@@ -194,6 +206,59 @@ def kernel_bytes(name, wl, images_by_width):
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU oracle's train step
 # ---------------------------------------------------------------------------------------------
+def staged_reference(wl, steps, warmup, batch, threads, device="cpu"):
+    """The UNMODIFIED reference modules (oracle/_ref, staged by oracle/stage_reference.py) driven exactly as the
+    reference's train loop drives them (2d_FPE/train_fno.py:116-117,139-145: MSELoss, Adam over model.parameters(),
+    zero_grad / forward / backward / step, loss.item() every step).  Returns None when nothing is staged."""
+    from oracle import stage_reference as S
+    try:
+        S.root()
+    except FileNotFoundError:
+        return None
+    torch.set_num_threads(threads)
+    torch.manual_seed(1)
+    np.random.seed(1)
+    dev = torch.device(device)
+    M = S.load(wl["variant"], "NIOModules")
+    extra = ("cpu" if dev.type == "cpu" else dev,) if wl["ndim"] == 1 and wl.get("factory") != "blindno" else ()
+    model = getattr(M, wl["cls"])(*wl["args"], *extra, **wl.get("kwargs", {})).to(dev).train()
+    criterion = torch.nn.MSELoss()
+    optimizer = torch.optim.Adam(model.parameters(), lr=wl["lr"])
+    grid = make_grid(wl).to(dev)
+    batches = [(x.to(dev), y.to(dev)) for x, y in make_batches(wl, 2, batch, seed=0)]
+    takes_grid = wl.get("factory") != "blindno"
+
+    def step(i):
+        x, y = batches[i % 2]
+        optimizer.zero_grad()
+        pred = model(x, grid) if takes_grid else model(x)
+        loss = criterion(pred, y)
+        loss.backward()
+        optimizer.step()
+        return loss.item()
+
+    for i in range(warmup):
+        step(i)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3
+
+
+def reference_arm(wl, steps, warmup, batch, threads, device="cpu"):
+    """(samples/s, ms/step, kind): the staged reference itself when available, else the oracle's port of it."""
+    got = staged_reference(wl, steps, warmup, batch, threads, device)
+    if got is not None:
+        return got[0], got[1], "reference"
+    sps, ms = cpu_reference(wl, steps, warmup, batch, threads, device)
+    return sps, ms, "port"
+
+
 def cpu_reference(wl, steps, warmup, batch, threads, device="cpu"):
     """The reference's algorithm (oracle restatement: torch.fft / einsum / conv / gelu) timed on the host CPU, or -- with
     device="cuda", the GPU status-quo comparator of SURVEY.md 8(d) -- on stock PyTorch CUDA kernels (cuFFT / cuBLAS)."""
@@ -276,25 +341,27 @@ def blindno_reference(wl, model, steps, warmup, batch, dev):
 
 
 def run_reference(args, wl, rank, world):
+    """The reference arm: rank 0 alone times the reference's CPU train step (every host thread it can use) for exactly
+    --steps steps after --warmup warm-up steps, on the CUDA arm's config and metric."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     on_gpu = args.ref_device == "cuda"
-    steps = args.steps if on_gpu else min(args.steps, 10)
-    warmup = args.warmup if on_gpu else min(args.warmup, 2)
-    sps, ms = cpu_reference(wl, steps, warmup, wl["batch"], threads, device=args.ref_device)
+    batch = args.batch_per_gpu or wl["batch"]
+    sps, ms, kind = reference_arm(wl, args.steps, args.warmup, batch, threads, device=args.ref_device)
+    what = ("the unmodified reference modules (staged copy, oracle/_ref) under the reference's own train loop" if kind == "reference"
+            else "the reference's algorithm restated in oracle/blindno_oracle.py (no staged reference found)")
     line = {
         "impl": "reference", "metric": wl.get("metric", METRIC), "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "bags_per_gpu": wl["batch"], "snapshots_per_bag": wl["bag"], "grid": wl["n"],
-                   "ref_device": args.ref_device,
-                   "note": "the reference's algorithm (torch.fft path) restated in oracle/blindno_oracle.py, "
-                           + ("run on stock PyTorch CUDA kernels (cuFFT / cuBLAS / ATen, eager): the GPU status-quo comparator"
-                              if on_gpu else "timed on the host CPU")
-                           + "; the reference is pure Python and cannot travel to the GPU box"},
-        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} full train steps of batch {wl['batch']} after {warmup} warm-up"
+        "config": make_config(args, wl, world),
+        "arm": {"ref_device": args.ref_device,
+                "note": what + (", on stock PyTorch CUDA kernels (cuFFT / cuBLAS / ATen, eager): the GPU status-quo comparator"
+                                if on_gpu else ", timed on the host CPU")
+                        + "; one process on rank 0 whatever --gpus says (the reference's CPU path does not shard)"},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": kind,
+                         "sample": f"{args.steps} full train steps of batch {batch} after {args.warmup} warm-up"
                                    + (" (on cuda:0 with stock PyTorch kernels, not on the CPU)" if on_gpu else "")},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -451,27 +518,34 @@ def run_b200(args, wl, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cpu_steps = 4
-        sps, _ = cpu_reference(wl, cpu_steps, 1, wl["batch"], threads)
-        cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"{cpu_steps} full train steps of batch {wl['batch']} (same workload) after 1 warm-up, "
-                         "oracle/blindno_oracle.py on torch CPU"}
+        cpu_steps, cpu_warm = 10, 2
+        sps, _, kind = reference_arm(wl, cpu_steps, cpu_warm, batch, threads)
+        cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": kind,
+               "sample": f"{cpu_steps} full train steps of batch {batch} (same workload) after {cpu_warm} warm-up, "
+                         + ("unmodified reference modules (oracle/_ref) on torch CPU" if kind == "reference"
+                            else "oracle/blindno_oracle.py on torch CPU")}
+    try:   # tensor-pipe utilisation of the spectral kernels from the committed `ncu --set full` captures
+        tensor_pipe = json.load(open(os.path.join(ROOT, "profiles", "ncu_tensor_pipe.json")))
+    except Exception:
+        tensor_pipe = None
+    from blindno_b200 import build as _build
 
     x0, y0 = host[0]
     line = {
         "metric": wl.get("metric", METRIC), "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "f32 (3xTF32 tensor-core GEMMs)"}[args.prec], "data": "synthetic",
-        "config": {"workload": args.workload, "operator": f"{wl['cls']}{wl['args'] or wl.get('kwargs', '')}", "bags_per_gpu": batch,
-                   "bags_global": batch * world, "snapshots_per_bag": wl["bag"],
-                   "allreduce": ("none (1 GPU)" if world == 1 else
+        "config": make_config(args, wl, world),
+        "arm": {   "allreduce": ("none (1 GPU)" if world == 1 else
                                  ("heads' region overlapped with the encoder backward + encoder region at the end"
-                                  if trainer.split_backward else "one flat all-reduce after backward")), "bag_subsample": "U[50,99] per step (reference)",
-                   "grid": wl["n"], "parallelism": f"dp{world}", "precision_mode": {
-                       "fp32": "fp32 (1e-5 parity mode)",
-                       "tf32": "tf32: tcgen05 tensor-core W-forward DFT GEMM, fp32 accumulate (bound 2e-3 outputs / 1e-2 grads)",
-                       "tf32x3": "tf32x3: tcgen05 W-forward DFT GEMM with hi + lo split operands (3 MMAs per K step), meets the 1e-5 bound",
+                                  if trainer.split_backward else "one flat all-reduce after backward")),
+                   "precision_mode": {
+                       "fp32": "fp32: CUDA-core FFMA DFT GEMMs (1e-5 parity mode)",
+                       "tf32": "tf32: all four DFT GEMMs of every 2-D spectral layer on tcgen05 (csrc/tc_layer.cu), fp32 accumulate "
+                               "in tensor memory (bound 2e-3 outputs / 1e-2 grads)",
+                       "tf32x3": "tf32x3: the same tcgen05 kernels with hi + lo split operands (3 MMAs per K step), meets the 1e-5 bound",
                    }[args.prec],
+                   "lib_fingerprint": _build.fingerprint()[:16],
                    "cuda_graphs": f"{n_graphs} graphs (one per bag size), captured before timing" if use_graphs else "off",
                    "l2": f"rotating pool of {args.pool} distinct resident batches; per-step working set "
                          "(~0.3 GB of saved activations at B=4) exceeds the 126 MB L2",
@@ -485,6 +559,7 @@ def run_b200(args, wl, rank, world, local_rank):
         "roofline_hbm_kernels": [{k: r[k] for k in ("kernel", "achieved", "frac", "us_per_launch", "share_of_kernel_time")}
                                  for r in roof_all[:10] if not r["kernel"].startswith("project")][:6],
         "cpu_baseline": cpu,
+        "tensor_pipe_pct": tensor_pipe,
         "top_kernels": top,
         "kernel_time_us_per_step": total_ms * 1e3 / prof_steps,
         "final_loss": losses[-1] if losses else None,

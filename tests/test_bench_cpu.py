@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -21,7 +23,18 @@ def test_reference_arm_prints_one_contract_line():
         assert key in d, key
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
     assert d["config"]["workload"] == "1d_FPE" and "model" not in d["config"]
-    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
+    from oracle import stage_reference as S
+    try:
+        S.root()
+        kind = "reference"          # the unmodified reference modules are staged (or mounted): the arm runs THEM
+    except FileNotFoundError:
+        kind = "port"
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == kind
+    assert d["steps"] == 1 and d["warmup"] == 1, "the arm must time exactly the steps it was asked for"
+    # the two arms' config dicts must be equal: both come from make_config (the CUDA arm cannot run here)
+    import bench
+    args = type("A", (), {"workload": "1d_FPE", "batch_per_gpu": 0})()
+    assert d["config"] == bench.make_config(args, bench.WORKLOADS["1d_FPE"], 1)
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
 
 
