@@ -43,3 +43,24 @@ def test_synthetic_datasets_follow_the_scripts_schemas():
     assert d["y"].shape == (5, 8, 128) and d["V"].shape == (5, 128) and d["g"].shape == (5,)
     with pytest.raises(FileNotFoundError):
         H.synthetic_dataset("/x/unknown.npz", 1, 1)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "2d_FPE")), reason="reference tree not mounted")
+def test_eval_script_path_checkpoint_with_ddp_prefix(tmp_path):
+    """The eval path of the harness, validated with the reference's own modules: train_fno.py for two steps, the model
+    saved as under DDP (``module.`` keys), eval_fno.py unchanged on that file (its own prefix stripping and
+    load_state_dict), metrics.csv summarised."""
+    h = os.path.join(ROOT, "tools", "run_reference_script.py")
+    ckpt = str(tmp_path / "ck.pt")
+    res = subprocess.run([sys.executable, h, os.path.join(REF, "2d_FPE", "train_fno.py"), "--steps", "1", "--warmup", "1", "--samples",
+                          "10", "--bag", "60", "--modules", "reference", "--device", "cpu", "--workdir", str(tmp_path / "t"),
+                          "--save-ckpt", ckpt, "--ckpt-prefix", "module."], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["checkpoint"]["tensors"] > 100 and os.path.exists(ckpt)
+    res = subprocess.run([sys.executable, h, os.path.join(REF, "2d_FPE", "eval_fno.py"), "--modules", "reference", "--device", "cpu",
+                          "--samples", "4", "--bag", "60", "--workdir", str(tmp_path / "e"), "--script-args",
+                          f"--ckpt {ckpt} --outdir out --start 0 --end 1 --device cpu"], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["status"] == "completed" and out["metrics"]["rows"] == 2 and out["metrics"]["columns"][1] == "rel_l2_drift"

@@ -1,8 +1,11 @@
 #!/usr/bin/env python
-"""Run one of the reference's train scripts UNCHANGED against this package.
+"""Run one of the reference's train / eval scripts UNCHANGED against this package.
 
-    python tools/run_reference_script.py /path/to/reference/2d_FPE/train_fno.py --steps 20
+    python tools/run_reference_script.py oracle/_ref/2d_FPE/train_fno.py --steps 20 --save-ckpt gpurun_out/ckpt.pt
+    python tools/run_reference_script.py oracle/_ref/2d_FPE/eval_fno.py --script-args "--ckpt gpurun_out/ckpt.pt --start 0 --end 3"
     python tools/run_reference_script.py /path/to/reference/1d_FPE/train_fno.py --steps 5 --modules reference --device cpu
+
+(oracle/_ref is the staged copy of the reference's files, oracle/stage_reference.py; any path to the reference tree works.)
 
 The scripts are flat files with hard-coded dataset paths, 400 epochs, plots and an `accelerate` launcher.
 Without touching them this harness supplies, in-process and only for the run:
@@ -15,7 +18,12 @@ Without touching them this harness supplies, in-process and only for the run:
     as accelerate would), `timm`;
   * a synthetic dataset in the schema the script's Dataset class reads, served when `np.load` is asked for
     the script's (absent) hard-coded file;
-  * a step limit: after ``--steps`` optimiser steps the run stops and one JSON line reports samples/s.
+  * a step limit: after ``--steps`` optimiser steps the run stops and one JSON line reports samples/s;
+  * ``--save-ckpt``: when the run stops, the model the script trains is saved the way the scripts save their best
+    checkpoint (``accelerator.save(model.state_dict(), ...)``: under DDP the keys carry the ``module.`` prefix that
+    eval_fno.py:104-122 strips; ``--ckpt-prefix module.`` reproduces that in a single-process run);
+  * eval scripts (argparse, no optimiser): ``--script-args`` is handed to the script as its command line, the run ends
+    when the script does, and the rows of the ``metrics.csv`` it wrote are summarised in the JSON line.
 
 Outputs the script writes (checkpoints, curves) go to ``--workdir`` (default gpurun_out/script_run).
 """
@@ -153,6 +161,9 @@ def synthetic_dataset(path: str, n_samples: int, bag: int):
     rng = np.random.default_rng(0)
     name = os.path.basename(path)
     f32 = np.float32
+    if name.startswith("test_"):                        # eval scripts: a held-out file in the train file's schema
+        name = name[len("test_"):]
+        rng = np.random.default_rng(1)
     if name == "dataset_2D_drift_diffusion.npz":        # 2d_FPE/train_fno.py:20-23
         return {"trajectories": (rng.standard_normal((n_samples, bag, 61, 61)) * 1e-10).astype(f32),
                 "potential": (rng.standard_normal((n_samples, 61, 61)) * 1e-21).astype(f32),
@@ -184,7 +195,14 @@ def main():
     ap.add_argument("--modules", default="ours", choices=["ours", "reference"])
     ap.add_argument("--device", default=None)
     ap.add_argument("--workdir", default=os.path.join(ROOT, "gpurun_out", "script_run"))
+    ap.add_argument("--save-ckpt", default=None, help="save the trained model's state_dict here when the run stops")
+    ap.add_argument("--ckpt-prefix", default="", help="key prefix of the saved state_dict ('module.' = as saved under DDP)")
+    ap.add_argument("--script-args", default="", help="command line handed to the script (eval scripts use argparse)")
+    ap.add_argument("--seed", type=int, default=None, help="torch / numpy seed set before the script starts")
     args = ap.parse_args()
+    for k in ("save_ckpt",):
+        if getattr(args, k):
+            setattr(args, k, os.path.abspath(getattr(args, k)))
 
     script = os.path.abspath(args.script)
     variant = os.path.basename(os.path.dirname(script))
@@ -232,6 +250,25 @@ def main():
 
     torch.optim.Adam.step = step
 
+    # the model the script trains: the first bag model put in train mode (every script calls model.train() per epoch)
+    trained = {}
+    real_train = torch.nn.Module.train
+
+    def train(self, mode=True):
+        if mode and "model" not in trained and type(self).__name__.startswith(("NIOFP", "PermInv")):
+            trained["model"] = self
+        return real_train(self, mode)
+
+    torch.nn.Module.train = train
+    import shlex
+    argv = sys.argv
+    script_args = shlex.split(args.script_args)
+    script_args = [os.path.abspath(a) if (a.endswith(".pt") and not os.path.isabs(a)) else a for a in script_args]
+    sys.argv = [script] + script_args
+    if args.seed is not None:
+        torch.manual_seed(args.seed)
+        np.random.seed(args.seed)
+
     os.makedirs(args.workdir, exist_ok=True)
     cwd = os.getcwd()
     os.chdir(args.workdir)
@@ -247,17 +284,38 @@ def main():
     finally:
         os.chdir(cwd)
         np.load, torch.nn.MSELoss.forward, torch.optim.Adam.step = real_load, real_mse, real_step
+        torch.nn.Module.train, sys.argv = real_train, argv
     if dev.type == "cuda":
         torch.cuda.synchronize()
     sec = time.perf_counter() - stats["t0"] if stats["t0"] else float("nan")
     world = int(os.environ.get("WORLD_SIZE", 1))
     res = {"script": os.path.join(variant, os.path.basename(script)), "modules": args.modules, "device": str(dev), "status": status,
-           "optimizer_steps": stats["steps"], "timed_steps": stats["steps"] - args.warmup, "batch_per_process": stats["batch"],
+           "optimizer_steps": stats["steps"], "timed_steps": max(stats["steps"] - args.warmup, 0), "batch_per_process": stats["batch"],
            "world": world, "samples_per_s": world * stats["samples"] / sec if sec == sec and sec > 0 else None,
            "note": "eager loop of the unchanged script (its own DataLoader, torch.optim.Adam, loss.item() per step)"}
     if launches0 is not None:
         from blindno_b200 import ops
         res["gpu_launches"] = ops.kernel_launches() - launches0
+    if args.save_ckpt and "model" in trained and int(os.environ.get("RANK", 0)) == 0:
+        model = getattr(trained["model"], "module", trained["model"])
+        sd = {args.ckpt_prefix + k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        os.makedirs(os.path.dirname(args.save_ckpt) or ".", exist_ok=True)
+        torch.save(sd, args.save_ckpt)
+        res["checkpoint"] = {"path": os.path.relpath(args.save_ckpt, ROOT), "tensors": len(sd),
+                             "model": type(model).__name__, "prefix": args.ckpt_prefix}
+    if stats["steps"] == 0:           # an eval script: summarise the metrics.csv it wrote (2d_FPE/eval_fno.py:193-198,275-278)
+        import csv
+        import glob
+        res["note"] = "unchanged eval script: checkpoint load, per-sample forward under no_grad, de-normalised relative L2"
+        res.pop("samples_per_s", None)
+        outdirs = [a for i, a in enumerate(script_args) if i and script_args[i - 1] == "--outdir"]
+        roots = [os.path.join(args.workdir, o) if not os.path.isabs(o) else o for o in outdirs] or [args.workdir]
+        for path in [q for r_ in roots for q in glob.glob(os.path.join(r_, "**", "metrics.csv"), recursive=True)][:1]:
+            rows = list(csv.reader(open(path)))
+            body = [[float(v) for v in r] for r in rows[1:] if r]
+            res["metrics"] = {"file": os.path.relpath(path, args.workdir), "columns": rows[0], "rows": len(body),
+                              "mean": [sum(c) / len(body) for c in list(zip(*body))[1:]] if body else None,
+                              "values": body}
     if int(os.environ.get("RANK", 0)) == 0:
         print(json.dumps(res))
 
