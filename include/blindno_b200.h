@@ -252,10 +252,15 @@ int bdn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int bdn_abi_version(void);
 const char* bdn_last_error(void);          /* thread-local, valid until the next failing call */
 int bdn_pad_amount(int n);                 /* int(round(n / 4)) with Python's banker's rounding */
+/* Build (and cache) the DFT tables of a shape now.  The first use of a shape allocates and copies synchronously,
+ * which a CUDA-graph capture does not survive: compute entry points refuse (BDN_ERR_UNSUPPORTED text in
+ * bdn_last_error) a first use under capture; call this, or the entry point once eagerly, beforehand. */
+int bdn_prepare_plan(int32_t ndim, int32_t hp, int32_t wp, int32_t m1, int32_t m2);
 int64_t bdn_kernel_launches(void);         /* kernels launched by this library so far (process-wide) */
 int bdn_device_sm_count(void);
 /* Per-kernel device timing for bench.py's roofline: between begin and end every kernel this
- * library launches is bracketed by a CUDA event pair on its stream.  end synchronises those
+ * library launches is bracketed by a CUDA event pair on its stream (launches into a stream that is being captured
+ * into a CUDA graph are not timed).  Every launch is also an NVTX range named after the kernel.  end synchronises those
  * events and writes a JSON object {"kernel/tag": {"launches": n, "ms": total}, ...} into buf
  * (truncated to cap); returns the number of bytes the full text needs. */
 int bdn_profile_begin(void);

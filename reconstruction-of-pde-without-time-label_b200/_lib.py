@@ -52,6 +52,7 @@ EXPORTS = {
     "bdn_pad_amount": (C.c_int, [C.c_int]),
     "bdn_kernel_launches": (C.c_int64, []),
     "bdn_device_sm_count": (C.c_int, []),
+    "bdn_prepare_plan": (C.c_int, [C.c_int32] * 5),
     "bdn_profile_begin": (C.c_int, []),
     "bdn_profile_end": (C.c_long, [C.c_char_p, C.c_size_t]),
     "bdn_spectral_workspace_bytes": (C.c_size_t, [C.POINTER(SpectralShape)]),

@@ -3,6 +3,8 @@
 #include "../../include/blindno_b200.h"
 #include "bdn_internal.cuh"
 
+#include <nvtx3/nvToolsExt.h>      // header-only (NVTX 3): ranges show up in Nsight Systems / Compute, no library to link
+
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -46,13 +48,26 @@ static std::mutex g_prof_mu;
 static std::atomic<bool> g_prof_on{false};
 static std::vector<ProfRecord> g_prof;
 
+// Event pairs cannot be recorded into a stream that is being captured into a CUDA graph (the events would belong to
+// the graph and could never be read back): profiling is skipped for launches under capture.
+static bool stream_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return st != cudaStreamCaptureStatusNone;
+}
+
 LaunchScope::LaunchScope(const char* n, cudaStream_t s, int t) : name(n), tag(t), st(s), e0(nullptr), on(false) {
-  if (g_prof_on.load(std::memory_order_relaxed)) {
+  nvtxRangePushA(n);           // one NVTX range per kernel launch of this library (a no-op without a tool attached)
+  if (g_prof_on.load(std::memory_order_relaxed) && !stream_capturing(s)) {
     on = cudaEventCreate(&e0) == cudaSuccess && cudaEventRecord(e0, st) == cudaSuccess;
   }
 }
 
 LaunchScope::~LaunchScope() {
+  nvtxRangePop();
   count_launch(1);
   if (!on) return;
   cudaEvent_t e1;
@@ -83,7 +98,10 @@ static T* upload(const std::vector<T>& v) {
   if (v.empty()) return nullptr;
   T* d = nullptr;
   if (cudaMalloc(&d, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
-  if (cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(d);
+    return nullptr;
+  }
   return d;
 }
 
@@ -160,6 +178,25 @@ const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2) {
   }
   g_plans[key] = pl;
   return pl;
+}
+
+static bool plan_cached(int ndim, int hp, int wp, int m1, int m2) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  return g_plans.count(std::make_tuple(dev, ndim, hp, wp, m1, m2)) != 0;
+}
+
+// The entry points' way to a plan.  Building one allocates and copies synchronously; inside a CUDA-graph capture that
+// would invalidate the capture with an opaque error, so a first use of a shape under capture is refused with advice.
+static const Plan* plan_for(int ndim, int hp, int wp, int m1, int m2, void* stream) {
+  if (!plan_cached(ndim, hp, wp, m1, m2) && stream_capturing((cudaStream_t)stream)) {
+    set_error(BDN_ERR_UNSUPPORTED,
+              "first use of shape ndim=%d %dx%d modes %dx%d inside a CUDA-graph capture: run the call once eagerly, or "
+              "call bdn_prepare_plan, before capturing", ndim, hp, wp, m1, m2);
+    return nullptr;
+  }
+  return get_plan(ndim, hp, wp, m1, m2);
 }
 
 // ---------------------------------------------------------------------------
@@ -250,6 +287,12 @@ long bdn_profile_end(char* buf, size_t cap) {
   return (long)js.size() + 1;
 }
 
+int bdn_prepare_plan(int32_t ndim, int32_t hp, int32_t wp, int32_t m1, int32_t m2) {
+  int rc = check_modes(ndim, hp, wp, m1, m2);
+  if (rc != BDN_OK) return rc;
+  return get_plan(ndim, hp, wp, m1, m2) ? BDN_OK : BDN_ERR_CUDA;
+}
+
 int bdn_device_sm_count(void) {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -281,7 +324,7 @@ int bdn_spectral_forward(const BdnSpectralShape* s, const float* x, const float*
   if (s->images == 0) return BDN_OK;
   if (!x || !w1 || !y || !ws || (s->ndim == 2 && !w2)) return set_error(BDN_ERR_INVALID, "null pointer argument");
   if (s->prec != BDN_PREC_FP32) return set_error(BDN_ERR_UNSUPPORTED, "standalone spectral op is fp32 only");
-  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  const Plan* pl = plan_for(s->ndim, s->hp, s->wp, s->m1, s->m2, stream);
   if (!pl) return BDN_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   Carver cv{(char*)ws, ws_bytes};
@@ -307,7 +350,7 @@ int bdn_spectral_backward(const BdnSpectralShape* s, const float* gy, const floa
   if (rc != BDN_OK) return rc;
   if (!gy || !xs_saved || !w1 || !gw1 || !ws || (s->ndim == 2 && (!w2 || !gw2)))
     return set_error(BDN_ERR_INVALID, "null pointer argument");
-  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  const Plan* pl = plan_for(s->ndim, s->hp, s->wp, s->m1, s->m2, stream);
   if (!pl) return BDN_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   const int K = pl->K, m1r = s->ndim == 2 ? s->m1 : 1;
@@ -341,7 +384,7 @@ int bdn_stage_wfwd(int32_t hp, int32_t wp, int32_t m1, int32_t m2, int32_t rows,
   if (rc != BDN_OK) return rc;
   if (!x || !out || rows < 0) return set_error(BDN_ERR_INVALID, "bad arguments");
   if (rows == 0) return BDN_OK;
-  const Plan* pl = get_plan(ndim, hp, wp, m1, m2);
+  const Plan* pl = plan_for(ndim, hp, wp, m1, m2, stream);
   if (!pl) return BDN_ERR_CUDA;
   // a single stage asked for in a tensor-core mode either runs on the tensor cores or fails: no silent change of
   // the arithmetic (the whole-net calls fall back per shape and say so, see launch_wfwd / use_tc_layer)
@@ -368,6 +411,8 @@ static int check_fno(const BdnFnoShape* s) {
   if (s->out_h < 1 || s->out_w < 1 || s->out_h > s->hp || s->out_w > s->wp)
     return set_error(BDN_ERR_INVALID, "bad cropped extents %dx%d", s->out_h, s->out_w);
   if (s->ndim == 1 && s->h != 1) return set_error(BDN_ERR_INVALID, "1-D needs h=1");
+  // the pointwise kernels split flat pixel indices with a float reciprocal (exact while the plane has < 2^22 pixels)
+  if ((long)s->hp * s->wp >= (1L << 22)) return set_error(BDN_ERR_UNSUPPORTED, "padded plane %dx%d has >= 2^22 pixels", s->hp, s->wp);
   return check_modes(s->ndim, s->hp, s->wp, s->m1, s->m2);
 }
 
@@ -455,7 +500,7 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
   if ((rc = check_lift_input(s, in)) != BDN_OK) return rc;
   if (s->prec != BDN_PREC_FP32 && s->prec != BDN_PREC_TF32 && s->prec != BDN_PREC_TF32X3)
     return set_error(BDN_ERR_INVALID, "bad precision");
-  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  const Plan* pl = plan_for(s->ndim, s->hp, s->wp, s->m1, s->m2, stream);
   if (!pl) return BDN_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t act = act_floats1(s), ksp = kspec_floats1(s);
@@ -525,7 +570,7 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
   if ((rc = check_lift_input(s, in)) != BDN_OK) return rc;
   if (pooled_g && (n_keep < 1 || s->images % n_keep != 0))
     return set_error(BDN_ERR_INVALID, "pooled gradient: images=%d not a multiple of n_keep=%d", s->images, n_keep);
-  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  const Plan* pl = plan_for(s->ndim, s->hp, s->wp, s->m1, s->m2, stream);
   if (!pl) return BDN_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t act = act_floats1(s), ksp = kspec_floats1(s);
@@ -640,7 +685,7 @@ int bdn_stage_layer_forward(const BdnFnoShape* s, const float* z_in, int32_t act
   if (s->images == 0) return BDN_OK;
   if (!z_in || !spec_w1 || (s->ndim == 2 && !spec_w2) || !conv_w || !conv_b || !z_out || !ws)
     return set_error(BDN_ERR_INVALID, "null pointer argument");
-  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  const Plan* pl = plan_for(s->ndim, s->hp, s->wp, s->m1, s->m2, stream);
   if (!pl) return BDN_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   Carver cv{(char*)ws, ws_bytes};
@@ -684,7 +729,7 @@ int bdn_stage_layer_backward(const BdnFnoShape* s, const float* gz_out, const fl
   if (!gz_out || !z_in || !xs_saved || !spec_w1 || (s->ndim == 2 && (!spec_w2 || !g_spec_w2)) || !conv_w || !gz_in ||
       !g_spec_w1 || !g_conv_w || !g_conv_b || !ws)
     return set_error(BDN_ERR_INVALID, "null pointer argument");
-  const Plan* pl = get_plan(s->ndim, s->hp, s->wp, s->m1, s->m2);
+  const Plan* pl = plan_for(s->ndim, s->hp, s->wp, s->m1, s->m2, stream);
   if (!pl) return BDN_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   Carver cv{(char*)ws, ws_bytes};

@@ -32,7 +32,7 @@ def _run(args, timeout=900):
     ("2d_FPE/train_fno.py", 4, []),
     ("2d_Non_conservative_FPE/train_fno.py", 4, []),
     ("1d_FPE/train_fno.py", 32, ["--samples", "80"]),
-    ("1d_GPE/train_nio_GPE.py", 8, ["--samples", "20"]),
+    ("1d_GPE/train_nio_GPE.py", 16, ["--samples", "20"]),      # the script's batch of 32, capped by the 80 % train split
     ("2d_FPE/train_nio.py", 4, []),
 ])
 def test_unchanged_train_script_runs_on_the_cuda_path(script, batch, extra, tmp_path):
