@@ -446,10 +446,49 @@ def run_b200(args, wl, rank, world, local_rank):
         if prev is not None:
             losses.append(prev)
 
+    drawn = []                                 # bag sizes this rank drew in the timed region (reference: per-rank draws, Q13)
+    real_draw = trainer._draw
+
+    def logging_draw(n):
+        idx = real_draw(n)
+        drawn.append(n if idx is None else len(idx))
+        return idx
+
+    trainer._draw = logging_draw
     with ClockSampler(local_rank) as clocks:
         ms, launches = timed(step_resident, args.steps, args.warmup)
+    own_sizes = drawn[-args.steps:]
+    trainer._draw = real_draw
     ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
     losses.append(pipe.flush())
+
+    # N > 1: where the weak-scaling loss comes from.  (1) every rank draws its own bag size each step, as the reference
+    # does, so the step waits for the largest draw of the N ranks; (2) what is left on the critical path after the
+    # encoder backward: the late all-reduce (+ waiting for the slowest rank) and the Adam that follows.  A second timed
+    # run with the bag size pinned to its mean on every rank separates the two.
+    scaling = None
+    if world > 1 and use_graphs and wl["ndim"] == 2:
+        sizes = torch.tensor(own_sizes, dtype=torch.float32, device=dev)
+        gathered = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(gathered, sizes)
+        allsz = torch.stack(gathered)                              # [world, steps]
+        n_tail = min(args.steps, 20)
+        trainer.enable_timing(True)
+        timed(step_resident, n_tail, 2)
+        tail = trainer.tail_times_ms()
+        trainer.enable_timing(False)
+        pinned_l = int(round((50 + wl["bag"] - 1) / 2))
+        trainer._draw = lambda n: np.random.choice(n, pinned_l)
+        ms_pin, _ = timed(step_resident, args.steps, 3)
+        trainer._draw = real_draw
+        scaling = {"bag_size_mean_own": float(allsz.mean()), "bag_size_mean_max_over_ranks": float(allsz.max(dim=0).values.mean()),
+                   "late_allreduce_incl_wait_for_slowest_rank_ms": tail[0] if tail else None,
+                   "late_adam_ms": tail[1] if tail else None,
+                   "early_adam": "heads' region updated on the communication stream under the encoder backward" if trainer.early_adam else "off",
+                   "value_with_bag_size_pinned": world * batch * args.steps / (ms_pin / 1e3), "pinned_bag_size": pinned_l,
+                   "ms_per_step_with_bag_size_pinned": ms_pin / args.steps,
+                   "note": "per-rank bag draws are the reference's semantics (2d_FPE/train_fno.py:78-81): the step time is the "
+                           "slowest rank's; value_with_bag_size_pinned is the same job with equal bag sizes on all ranks"}
 
     # per-kernel device time: a separate profiled pass of the same steps (event pair around every launch)
     prof_steps = min(args.steps, 10)
@@ -546,6 +585,7 @@ def run_b200(args, wl, rank, world, local_rank):
                        "tf32x3": "tf32x3: the same tcgen05 kernels with hi + lo split operands (3 MMAs per K step), meets the 1e-5 bound",
                    }[args.prec],
                    "lib_fingerprint": _build.fingerprint()[:16],
+                   "nccl_gradient_buffer_registered": bool(getattr(trainer, "nccl_registered", False)),
                    "cuda_graphs": f"{n_graphs} graphs (one per bag size), captured before timing" if use_graphs else "off",
                    "l2": f"rotating pool of {args.pool} distinct resident batches; per-step working set "
                          "(~0.3 GB of saved activations at B=4) exceeds the 126 MB L2",
@@ -555,6 +595,7 @@ def run_b200(args, wl, rank, world, local_rank):
         "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": (x0.numel() + y0.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world},
         "gpu_launches": launches,
+        "scaling_breakdown": scaling,
         "roofline": roofline,
         "roofline_hbm_kernels": [{k: r[k] for k in ("kernel", "achieved", "frac", "us_per_launch", "share_of_kernel_time")}
                                  for r in roof_all[:10] if not r["kernel"].startswith("project")][:6],

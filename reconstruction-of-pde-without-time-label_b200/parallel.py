@@ -109,7 +109,7 @@ class FlatTrainer:
             total += n
         self.numel = total
         self.flat_param = torch.zeros(total, dtype=torch.float32, device=self.device)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.flat_grad = self._alloc_grad_buffer(total)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.n_live = 0
@@ -134,6 +134,30 @@ class FlatTrainer:
                     self._late_span = (base, base + n)
         if sync_from_rank0 and self.world > 1:
             self.sync_from_rank0()
+
+    def _alloc_grad_buffer(self, total: int) -> torch.Tensor:
+        """The flat gradient buffer.  With BDN_NCCL_REGISTER=1 (and world > 1, NCCL) it is allocated from NCCL's own
+        allocator (ncclMemAlloc through torch's MemPool) and registered with the communicator, which lets NCCL reduce it
+        in place over NVLink SHARP (NVLS) without staging copies; ``self.nccl_registered`` says whether that happened
+        (any failure falls back to a plain allocation and says so on stderr -- the arithmetic is the same)."""
+        import os
+        import sys
+        self.nccl_registered = False
+        want = os.environ.get("BDN_NCCL_REGISTER", "0") == "1"
+        if want and self.world > 1 and self.device.type == "cuda" and dist.get_backend(self.group) == "nccl":
+            try:
+                pg = self.group if self.group is not None else dist.distributed_c10d._get_default_group()
+                backend = pg._get_backend(self.device)
+                pool = torch.cuda.MemPool(backend.mem_allocator)
+                with torch.cuda.use_mem_pool(pool):
+                    buf = torch.zeros(total, dtype=torch.float32, device=self.device)
+                backend.register_mem_pool(pool)
+                self._nccl_pool = pool
+                self.nccl_registered = True
+                return buf
+            except Exception as e:      # noqa: BLE001 -- optional fast path
+                print(f"blindno_b200: NCCL buffer registration unavailable ({type(e).__name__}: {e}); plain allocation", file=sys.stderr)
+        return torch.zeros(total, dtype=torch.float32, device=self.device)
 
     # -- replica consistency ---------------------------------------------------------------
     def _src(self) -> int:
