@@ -238,6 +238,25 @@ int bdn_bag_pool_lift_backward(const float* g, const float* w0, float* gpool,
                                void* stream);
 
 /* ---------------------------------------------------------------------------
+ * NIO tail: bag mean of the branch coefficients + DeepONet contraction + detached lift in one kernel
+ *   DeepOnetNoBiasOrg.forward  1d_GPE/DeepONetModules.py:142-151   (branch(u) @ trunk(x)^T + b0) / sqrt(p)
+ *   followed by the bag mean + fc0 lift of NIOFP_schrodinger.forward 1d_GPE/NIOModules.py:209-219
+ *   (NIOFP2D.forward 2d_FPE/NIOModules.py:64-76, NIOFP.forward 1d_FPE/NIOModules.py:70-80).
+ * By linearity the bag mean is taken on the coefficients, so the reference's [B, L, n_points] tensor is never formed.
+ * w: [n_bags, n_keep, p] branch coefficients; basis: [npix, p] trunk output; b0: scalar (device);
+ * grid: [npix, grid_dim]; fc0_w: [width, grid_dim + 1]; fc0_b: [width]; out: [n_bags, npix, width];
+ * wbar_saved: [n_bags, p] (the pooled coefficients, needed by backward).
+ * backward: g [n_bags, npix, width] -> g_w [n_bags, n_keep, p], g_basis [npix, p], g_b0 [1] (all OVERWRITTEN);
+ * g_wbar_ws: [n_bags, p] scratch.  fc0 is detached in the reference (.data): it receives no gradient.
+ * ------------------------------------------------------------------------- */
+int bdn_nio_tail_forward(const float* w, const float* basis, const float* b0, const float* grid, const float* fc0_w,
+                         const float* fc0_b, float* out, float* wbar_saved, int32_t n_bags, int32_t n_keep, int32_t p,
+                         int32_t npix, int32_t grid_dim, int32_t width, void* stream);
+int bdn_nio_tail_backward(const float* g, const float* basis, const float* wbar_saved, const float* fc0_w, float* g_w,
+                          float* g_basis, float* g_b0, float* g_wbar_ws, int32_t n_bags, int32_t n_keep, int32_t p,
+                          int32_t npix, int32_t grid_dim, int32_t width, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Optimiser step fused over a flat fp32 buffer (torch.optim.Adam semantics,
  * 2d_FPE/train_fno.py:117; eps added after the bias-corrected sqrt, no
  * weight decay / amsgrad).  step = 1-based step count.

@@ -823,6 +823,33 @@ int bdn_bag_pool_lift_backward(const float* g, const float* w0, float* gpool, in
   return check_cuda("bdn_bag_pool_lift_backward");
 }
 
+int bdn_nio_tail_forward(const float* w, const float* basis, const float* b0, const float* grid, const float* fc0_w,
+                         const float* fc0_b, float* out, float* wbar_saved, int32_t n_bags, int32_t n_keep, int32_t p,
+                         int32_t npix, int32_t grid_dim, int32_t width, void* stream) {
+  if (n_bags < 0 || n_keep < 1 || p < 1 || npix < 1 || grid_dim < 1 || width < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
+  if (p > 64) return set_error(BDN_ERR_UNSUPPORTED, "n_basis=%d > 64 not built", p);
+  if (n_bags == 0) return BDN_OK;
+  if (!w || !basis || !b0 || !grid || !fc0_w || !fc0_b || !out || !wbar_saved) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  launch_nio_tail(w, basis, b0, grid, fc0_w, fc0_b, out, wbar_saved, n_bags, n_keep, p, npix, grid_dim, width, (cudaStream_t)stream);
+  return check_cuda("bdn_nio_tail_forward");
+}
+
+int bdn_nio_tail_backward(const float* g, const float* basis, const float* wbar_saved, const float* fc0_w, float* g_w,
+                          float* g_basis, float* g_b0, float* g_wbar_ws, int32_t n_bags, int32_t n_keep, int32_t p, int32_t npix,
+                          int32_t grid_dim, int32_t width, void* stream) {
+  if (n_bags < 0 || n_keep < 1 || p < 1 || npix < 1 || grid_dim < 1 || width < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
+  if (p > 64) return set_error(BDN_ERR_UNSUPPORTED, "n_basis=%d > 64 not built", p);
+  if (!g_basis || !g_b0) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(g_basis, 0, (size_t)npix * p * sizeof(float), st);
+  cudaMemsetAsync(g_b0, 0, sizeof(float), st);
+  if (n_bags == 0) return check_cuda("bdn_nio_tail_backward");
+  if (!g || !basis || !wbar_saved || !fc0_w || !g_w || !g_wbar_ws) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  cudaMemsetAsync(g_wbar_ws, 0, (size_t)n_bags * p * sizeof(float), st);
+  launch_nio_tail_bwd(g, basis, wbar_saved, fc0_w, g_wbar_ws, g_basis, g_b0, g_w, n_bags, n_keep, p, npix, grid_dim, width, st);
+  return check_cuda("bdn_nio_tail_backward");
+}
+
 int bdn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float grad_scale, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq) return set_error(BDN_ERR_INVALID, "null pointer argument");

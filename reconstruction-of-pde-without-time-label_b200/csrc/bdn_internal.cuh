@@ -150,6 +150,11 @@ void launch_pool_lift(const float* s, const float* grid, const float* w0, const 
                       int n_bags, int n_keep, int npix, int grid_dim, int width, cudaStream_t st);
 void launch_pool_lift_bwd(const float* g, const float* w0, float* gpool, int n_bags, int npix,
                           int grid_dim, int width, cudaStream_t st);
+// NIO tail (K6): bag mean of the branch coefficients + DeepONet contraction + detached lift, and its backward
+void launch_nio_tail(const float* w, const float* basis, const float* b0, const float* grid, const float* w0, const float* fb,
+                     float* out, float* wbar, int n_bags, int L, int p, int npix, int gd, int width, cudaStream_t st);
+void launch_nio_tail_bwd(const float* g, const float* basis, const float* wbar, const float* w0, float* g_wbar, float* g_basis,
+                         float* g_b0, float* g_w, int n_bags, int L, int p, int npix, int gd, int width, cudaStream_t st);
 void launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,
                  float eps, int step, float grad_scale, cudaStream_t st);
 

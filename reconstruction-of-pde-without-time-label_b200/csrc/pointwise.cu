@@ -833,6 +833,105 @@ void launch_pool_lift_bwd(const float* g, const float* w0, float* gpool, int n_b
 }
 
 // ===========================================================================
+// NIO tail (K6): bag mean of the branch coefficients -> DeepONet contraction with the trunk basis -> (+ b0) / sqrt(p)
+// -> detached fc0 lift, one kernel.  DeepOnetNoBiasOrg.forward */DeepONetModules.py:142-151 followed by the bag mean +
+// lift of NIOFP_schrodinger.forward 1d_GPE/NIOModules.py:209-219 (NIOFP2D.forward 2d_FPE/NIOModules.py:64-76).  By
+// linearity the mean over the bag is taken on the [B, L, p] coefficients, so the [B, L, n_points] DeepONet output of
+// the reference is never formed.
+//   out[b, x, j] = fc0_b[j] + sum_d W0[j, d] grid[x, d] + W0[j, gd] * (sum_q wbar[b, q] basis[x, q] + b0) / sqrt(p)
+// ===========================================================================
+constexpr int TAIL_MAXP = 64;
+
+__global__ void __launch_bounds__(128) nio_tail_fwd_kernel(const float* __restrict__ w, const float* __restrict__ basis,
+                                                           const float* __restrict__ b0, const float* __restrict__ grid,
+                                                           const float* __restrict__ w0, const float* __restrict__ fb,
+                                                           float* __restrict__ out, float* __restrict__ wbar_out, int L, int p,
+                                                           int npix, int gd, int width) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float wbar[TAIL_MAXP];
+  const int b = blockIdx.y;
+  if ((int)threadIdx.x < p) {
+    const float* wp = w + (size_t)b * L * p + threadIdx.x;
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += __ldg(wp + (size_t)l * p);
+    s /= (float)L;
+    wbar[threadIdx.x] = s;
+    if (blockIdx.x == 0) wbar_out[b * p + threadIdx.x] = s;
+  }
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= npix) return;
+  float s = __ldg(b0);
+  const float* bx = basis + (size_t)x * p;
+  for (int q = 0; q < p; ++q) s = fmaf(wbar[q], __ldg(bx + q), s);
+  s *= rsqrtf((float)p);
+  float* o = out + ((size_t)b * npix + x) * width;
+  for (int j = 0; j < width; ++j) {
+    float v = __ldg(fb + j);
+    for (int d = 0; d < gd; ++d) v = fmaf(__ldg(w0 + j * (gd + 1) + d), __ldg(grid + (size_t)x * gd + d), v);
+    o[j] = fmaf(__ldg(w0 + j * (gd + 1) + gd), s, v);
+  }
+}
+
+// backward: gs[b, x] = sum_j W0[j, gd] g[b, x, j] / sqrt(p);  g_wbar[b, q] += sum_x gs basis[x, q];
+//           g_basis[x, q] += sum_b gs wbar[b, q];  g_b0 += sum gs          (all three zeroed by the caller)
+__global__ void __launch_bounds__(128) nio_tail_bwd_kernel(const float* __restrict__ g, const float* __restrict__ basis,
+                                                           const float* __restrict__ wbar, const float* __restrict__ w0,
+                                                           float* g_wbar, float* g_basis, float* g_b0, int p, int npix, int gd,
+                                                           int width) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  float gs = 0.f;
+  if (x < npix) {
+    const float* gp = g + ((size_t)b * npix + x) * width;
+    for (int j = 0; j < width; ++j) gs = fmaf(__ldg(w0 + j * (gd + 1) + gd), __ldg(gp + j), gs);
+    gs *= rsqrtf((float)p);
+  }
+  for (int q = 0; q < p; ++q) {
+    const float bv = x < npix ? __ldg(basis + (size_t)x * p + q) : 0.f;
+    if (x < npix) atomicAdd(g_basis + (size_t)x * p + q, gs * __ldg(wbar + b * p + q));
+    const float t = warp_sum(gs * bv);
+    if (lane == 0) atomicAdd(g_wbar + b * p + q, t);
+  }
+  const float t = warp_sum(gs);
+  if (lane == 0) atomicAdd(g_b0, t);
+}
+
+// g_w[b, l, q] = g_wbar[b, q] / L  (backward of the bag mean)
+__global__ void nio_tail_expand_kernel(const float* __restrict__ g_wbar, float* __restrict__ g_w, int n_bags, int L, int p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long total = (long)n_bags * L * p;
+  const float inv = 1.0f / (float)L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int q = i % p, b = i / ((long)L * p);
+    g_w[i] = __ldg(g_wbar + b * p + q) * inv;
+  }
+}
+
+void launch_nio_tail(const float* w, const float* basis, const float* b0, const float* grid, const float* w0, const float* fb,
+                     float* out, float* wbar, int n_bags, int L, int p, int npix, int gd, int width, cudaStream_t st) {
+  LaunchScope scope("nio_tail", st);
+  launch_k(nio_tail_fwd_kernel, dim3(ceil_div(npix, 128), n_bags), dim3(128), 0, st, w, basis, b0, grid, w0, fb, out, wbar, L, p,
+           npix, gd, width);
+}
+
+void launch_nio_tail_bwd(const float* g, const float* basis, const float* wbar, const float* w0, float* g_wbar, float* g_basis,
+                         float* g_b0, float* g_w, int n_bags, int L, int p, int npix, int gd, int width, cudaStream_t st) {
+  {
+    LaunchScope scope("nio_tail_bwd", st);
+    launch_k(nio_tail_bwd_kernel, dim3(ceil_div(npix, 128), n_bags), dim3(128), 0, st, g, basis, wbar, w0, g_wbar, g_basis, g_b0,
+             p, npix, gd, width);
+  }
+  LaunchScope scope("nio_tail_expand", st);
+  const long total = (long)n_bags * L * p;
+  launch_k(nio_tail_expand_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float*)g_wbar, g_w, n_bags, L, p);
+}
+
+// ===========================================================================
 // Adam over a flat buffer (torch.optim.Adam defaults: no weight decay, no amsgrad)
 // ===========================================================================
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,

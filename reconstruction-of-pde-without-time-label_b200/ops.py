@@ -937,12 +937,84 @@ def _bag_project_pool_lift(z, n_keep, fc1_w, fc1_b, fc2_w, fc2_b, grid, fc0_w, f
     return _OPS.bag_pool_lift(s.reshape(z.shape[0] // n_keep, n_keep, *gshape), grid, fc0_w.detach(), fc0_b.detach())
 
 
+def _nio_tail_dims(w, basis, grid, fc0_w):
+    if w.dim() != 3 or basis.dim() != 2 or basis.shape[1] != w.shape[2]:
+        raise RuntimeError(f"nio_tail expects w [bags, keep, p] and basis [points, p], got {tuple(w.shape)}, {tuple(basis.shape)}")
+    gshape = tuple(grid.shape[:-1])
+    npix = 1
+    for d in gshape:
+        npix *= d
+    if npix != basis.shape[0] or fc0_w.shape[1] != grid.shape[-1] + 1:
+        raise RuntimeError("nio_tail: grid / basis / fc0 shapes do not match")
+    return w.shape[0], w.shape[1], w.shape[2], gshape, npix, grid.shape[-1], fc0_w.shape[0]
+
+
+def _nio_tail_forward_cuda(w, basis, b0, grid, fc0_w, fc0_b):
+    _need_cuda(w, basis, b0, grid, fc0_w, fc0_b)
+    wc, bc, b0c, gc, w0c, fbc = (_f32c(t) for t in (w, basis, b0, grid, fc0_w, fc0_b))
+    n_bags, n_keep, p, gshape, npix, gd, width = _nio_tail_dims(wc, bc, gc, w0c)
+    out = torch.empty((n_bags,) + gshape + (width,), dtype=torch.float32, device=wc.device)
+    wbar = torch.empty(n_bags, p, dtype=torch.float32, device=wc.device)
+    with torch.cuda.device(wc.device):
+        check(_lib.lib().bdn_nio_tail_forward(_ptr(wc), _ptr(bc), _ptr(b0c), _ptr(gc), _ptr(w0c), _ptr(fbc), _ptr(out),
+                                              _ptr(wbar), n_bags, n_keep, p, npix, gd, width, _stream()), "bdn_nio_tail_forward")
+    return out, wbar
+
+
+def _nio_tail_backward_cuda(g, basis, wbar, fc0_w, n_keep, grid_dim):
+    _need_cuda(g, basis, wbar, fc0_w)
+    gc, bc, wbc, w0c = (_f32c(t) for t in (g, basis, wbar, fc0_w))
+    n_bags, p = wbc.shape
+    npix, width = bc.shape[0], w0c.shape[0]
+    g_w = torch.empty(n_bags, n_keep, p, dtype=torch.float32, device=gc.device)
+    g_basis = torch.empty_like(bc)
+    g_b0 = torch.empty(1, dtype=torch.float32, device=gc.device)
+    scratch = torch.empty(n_bags, p, dtype=torch.float32, device=gc.device)
+    with torch.cuda.device(gc.device):
+        check(_lib.lib().bdn_nio_tail_backward(_ptr(gc), _ptr(bc), _ptr(wbc), _ptr(w0c), _ptr(g_w), _ptr(g_basis), _ptr(g_b0),
+                                               _ptr(scratch), n_bags, n_keep, p, npix, grid_dim, width, _stream()),
+              "bdn_nio_tail_backward")
+    return g_w, g_basis, g_b0
+
+
+def _nio_tail_fake(w, basis, b0, grid, fc0_w, fc0_b):
+    n_bags, _, p, gshape, _, _, width = _nio_tail_dims(w, basis, grid, fc0_w)
+    return w.new_empty((n_bags,) + gshape + (width,)), w.new_empty(n_bags, p)
+
+
+_define("nio_tail_forward", "(Tensor w, Tensor basis, Tensor b0, Tensor grid, Tensor fc0_w, Tensor fc0_b) -> (Tensor, Tensor)",
+        _nio_tail_forward_cuda, _nio_tail_fake)
+_define("nio_tail_backward", "(Tensor g, Tensor basis, Tensor wbar, Tensor fc0_w, int n_keep, int grid_dim) -> "
+        "(Tensor, Tensor, Tensor)", _nio_tail_backward_cuda,
+        lambda g, basis, wbar, fc0_w, n_keep, grid_dim: (g.new_empty(wbar.shape[0], n_keep, wbar.shape[1]),
+                                                         torch.empty_like(basis), g.new_empty(1)))
+
+
+def _nio_tail_setup(ctx, inputs, output):
+    w, basis, b0, grid, fc0_w, fc0_b = inputs
+    ctx.save_for_backward(basis, output[1], fc0_w)
+    ctx.n_keep, ctx.grid_dim, ctx.b0_shape = w.shape[1], grid.shape[-1], tuple(b0.shape)
+    ctx.mark_non_differentiable(output[1])
+
+
+def _nio_tail_bwd(ctx, g, _g_wbar):
+    basis, wbar, fc0_w = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    if not any(need[:3]):
+        return (None,) * 6
+    g_w, g_basis, g_b0 = _OPS.nio_tail_backward(g, basis, wbar, fc0_w, ctx.n_keep, ctx.grid_dim)
+    # fc0 is detached in the reference (.data): no gradient, by construction
+    return (g_w if need[0] else None, g_basis if need[1] else None, g_b0.reshape(ctx.b0_shape) if need[2] else None,
+            None, None, None)
+
+
+torch.library.register_autograd(f"{NS}::nio_tail_forward", _nio_tail_bwd, setup_context=_nio_tail_setup, lib=_LIB)
+
+
 def _deeponet_pool_contract_lift(w, basis, b0, grid, fc0_w, fc0_b):
-    """(mean_l w_l) @ basis^T + b0) / sqrt(p), then the detached lift: by linearity the bag mean is taken on the
-    [B, L, p] branch coefficients, so the [B, L, n_points] DeepONet output is never materialised (NIO tail)."""
-    p = w.shape[-1]
-    pooled = (w.mean(dim=1) @ basis.T + b0) / p ** 0.5                        # [B, n_points]  (library GEMM, K = p)
-    return _OPS.bag_pool_lift(pooled.reshape(w.shape[0], 1, *grid.shape[:-1]), grid, fc0_w.detach(), fc0_b.detach())
+    """((mean_l w_l) @ basis^T + b0) / sqrt(p), then the detached lift, in one kernel: by linearity the bag mean is taken
+    on the [B, L, p] branch coefficients, so the [B, L, n_points] DeepONet output is never materialised (NIO tail, K6)."""
+    return _OPS.nio_tail_forward(w, basis, b0, grid, fc0_w.detach(), fc0_b.detach())[0]
 
 
 _define_composite("bag_project_pool_lift",
