@@ -118,7 +118,8 @@ const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2) {
   Plan* pl = new Plan();
   pl->ndim = ndim; pl->hp = hp; pl->wp = wp; pl->m1 = m1; pl->m2 = m2;
   pl->K = ndim == 2 ? 2 * m1 : 1;
-  pl->Kp = round_up(pl->K, 8);
+  pl->F = ndim == 2 ? m1 + 1 : 1;
+  pl->Fp = round_up(pl->F, 4);
   pl->hp8 = round_up(hp, 8);
   pl->wp4 = round_up(wp, 4);
   const double two_pi = 6.283185307179586476925286766559;
@@ -137,21 +138,21 @@ const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2) {
   pl->t_lw_cos = upload(t_cos);
   pl->t_lw_sin = upload(t_sin);
 
-  pl->t_hk = nullptr; pl->t_kh = nullptr;
+  pl->t_hf = nullptr; pl->t_fh = nullptr;
   if (ndim == 2) {
-    std::vector<float2> t_hk((size_t)hp * pl->Kp, make_float2(0.f, 0.f));
-    std::vector<float2> t_kh((size_t)pl->K * pl->hp8, make_float2(0.f, 0.f));
-    for (int k = 0; k < pl->K; ++k) {
-      const int kk = k < m1 ? k : hp - 2 * m1 + k;
+    // kept rows k = 0..m1-1 (frequency +k) and k = m1..2*m1-1 (frequency k - 2*m1 = -m1..-1): rows f and 2*m1 - f are a
+    // conjugate pair, so one (cos, sin) per frequency f = 0..m1 serves both (f = 0 and f = m1 have one row each)
+    std::vector<float2> t_hf((size_t)hp * pl->Fp, make_float2(0.f, 0.f));
+    std::vector<float2> t_fh((size_t)pl->F * pl->hp8, make_float2(0.f, 0.f));
+    for (int f = 0; f < pl->F; ++f)
       for (int h = 0; h < hp; ++h) {
-        const double ph = two_pi * (double)(((long long)kk * h) % hp) / (double)hp;
+        const double ph = two_pi * (double)(((long long)f * h) % hp) / (double)hp;
         const float2 v = make_float2((float)std::cos(ph), (float)std::sin(ph));
-        t_hk[(size_t)h * pl->Kp + k] = v;
-        t_kh[(size_t)k * pl->hp8 + h] = v;
+        t_hf[(size_t)h * pl->Fp + f] = v;
+        t_fh[(size_t)f * pl->hp8 + h] = v;
       }
-    }
-    pl->t_hk = upload(t_hk);
-    pl->t_kh = upload(t_kh);
+    pl->t_hf = upload(t_hf);
+    pl->t_fh = upload(t_fh);
   }
   std::vector<float> col_fwd(m2), col_dc(m2, 1.f);
   for (int l = 0; l < m2; ++l) {
@@ -171,7 +172,7 @@ const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2) {
   tcl_build_tables(pl);              // optional as well (2-D, hp and wp <= 128)
 
   if (!pl->t_wl || !pl->t_lw_cos || !pl->t_lw_sin || !pl->col_fwd || !pl->col_dc ||
-      (ndim == 2 && (!pl->t_hk || !pl->t_kh))) {
+      (ndim == 2 && (!pl->t_hf || !pl->t_fh))) {
     set_error(BDN_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete pl;
     return nullptr;
@@ -461,6 +462,36 @@ static bool use_tc_layer(const BdnFnoShape* s, const Plan* pl) {
   return false;
 }
 
+// A side stream per (device, caller stream slot) for work that depends on the parameters only (the mode-major copy of
+// the heads' spectral weights): forked from the caller's stream by an event and joined before its first consumer, so
+// it runs next to the lift and the first W transform instead of in front of them.  Under graph capture the fork / join
+// become parallel branches.  The pool is created outside capture (first eager call); until then the work stays in
+// the caller's stream.
+struct SideCtx { cudaStream_t side; cudaEvent_t fork, join; };
+static std::mutex g_side_mu;
+static std::map<std::pair<int, int>, SideCtx> g_side;
+
+static bool side_ctx(cudaStream_t st, SideCtx* out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  const int slot = (int)((reinterpret_cast<uintptr_t>(st) >> 4) % 8);
+  std::lock_guard<std::mutex> lock(g_side_mu);
+  auto it = g_side.find({dev, slot});
+  if (it == g_side.end()) {
+    if (stream_capturing(st)) return false;
+    SideCtx c{};
+    if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    it = g_side.emplace(std::make_pair(dev, slot), c).first;
+  }
+  *out = it->second;
+  return true;
+}
+
 static LiftArgs make_lift(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftInput* in) {
   LiftArgs a{};
   a.x_cl = in->x_cl; a.bags = in->bags; a.idx = in->idx; a.grid = in->grid;
@@ -520,11 +551,21 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
   if (tc && s->n_layers > 1 && !(abuf = (float*)cv.take(act * sizeof(float))))
     return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
   float2* wt = nullptr;
+  cudaEvent_t wt_join = nullptr;     // the mode-major copy runs on a side stream; joined before the first core2d
   if (use_mode_major(s) && !tc) {
     wt = xs_saved ? (float2*)(xs_saved + (size_t)s->n_layers * ksp)
                   : (float2*)cv.take((size_t)s->n_layers * wt_floats1(s) * sizeof(float));
     if (!wt) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
-    launch_spec_weights_mode_major(pl, p->spec_w1, p->spec_w2, s->n_layers, s->width, s->width, wt, st);
+    SideCtx sc{};
+    if (side_ctx(st, &sc) && cudaEventRecord(sc.fork, st) == cudaSuccess &&
+        cudaStreamWaitEvent(sc.side, sc.fork, 0) == cudaSuccess) {
+      launch_spec_weights_mode_major(pl, p->spec_w1, p->spec_w2, s->n_layers, s->width, s->width, wt, sc.side);
+      cudaEventRecord(sc.join, sc.side);
+      wt_join = sc.join;
+    } else {
+      cudaGetLastError();
+      launch_spec_weights_mode_major(pl, p->spec_w1, p->spec_w2, s->n_layers, s->width, s->width, wt, st);
+    }
   }
   const size_t wt1 = wt_floats1(s) / 2;   // float2 per layer
 
@@ -546,6 +587,10 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
                        p->conv_b[k], nullptr, nullptr, s->images, s->width, act_in, st))
       continue;
     launch_wfwd(pl, zbuf(k), X1, rows, act_in, st, s->prec);
+    if (wt_join != nullptr) {
+      cudaStreamWaitEvent(st, wt_join, 0);
+      wt_join = nullptr;
+    }
     if (s->ndim == 2)
       launch_core2d(pl, X1, Z, xs_k, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], s->images, s->width,
                     s->width, false, st, wt ? wt + (size_t)k * wt1 : nullptr);
@@ -556,6 +601,7 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
     wa.images = s->images; wa.c = s->width; wa.act_in = act_in;
     launch_winv(pl, WINV_LAYER_FWD, wa, st);
   }
+  if (wt_join != nullptr) cudaStreamWaitEvent(st, wt_join, 0);
   launch_project(make_proj(s, p, zbuf(s->n_layers)), out, st);
   return check_cuda("bdn_fno_forward");
 }
@@ -587,6 +633,9 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
   const float2* wt = use_mode_major(s) && !tc ? (const float2*)(xs_saved + (size_t)s->n_layers * ksp) : nullptr;
   const size_t wt1 = wt_floats1(s) / 2;
   int cur = 0;
+  SideCtx sc{};
+  const bool side_ok = use_mode_major(s) && !tc && side_ctx(st, &sc);
+  cudaEvent_t gw_join = nullptr;
   launch_project_bwd(make_proj(s, p, z_saved + (size_t)s->n_layers * act), g_out, pooled_g, n_keep, gz[cur], g->fc1_w,
                      g->fc1_b, g->fc2_w, g->fc2_b, st);
   const int rows = s->images * s->width * s->hp;
@@ -610,13 +659,26 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
       continue;
     }
     launch_wfwd(pl, gz[cur], G1, rows, 0, st, s->prec);
+    if (gw_join != nullptr) {          // the previous layer's weight-gradient reduction still reads GY
+      cudaStreamWaitEvent(st, gw_join, 0);
+      gw_join = nullptr;
+    }
     if (s->ndim == 2)
       launch_core2d(pl, G1, GZ, GY, (const float2*)p->spec_w1[k], (const float2*)p->spec_w2[k], s->images, s->width,
                     s->width, true, st, wt ? wt + (size_t)k * wt1 : nullptr);
     else
       launch_mix1d(pl, G1, GZ, GY, (const float2*)p->spec_w1[k], s->images, s->width, s->width, true, st);
-    launch_gw_reduce(pl, (const float2*)(xs_saved + (size_t)k * ksp), GY, (float2*)g->spec_w1[k],
-                     (float2*)g->spec_w2[k], s->images, s->width, s->width, st);
+    // few images (the heads): neither the weight-gradient reduction nor the inverse transform fills the machine, so the
+    // reduction runs on the side stream next to the inverse transform and the next layer's W transform
+    if (side_ok && cudaEventRecord(sc.fork, st) == cudaSuccess && cudaStreamWaitEvent(sc.side, sc.fork, 0) == cudaSuccess) {
+      launch_gw_reduce(pl, (const float2*)(xs_saved + (size_t)k * ksp), GY, (float2*)g->spec_w1[k],
+                       (float2*)g->spec_w2[k], s->images, s->width, s->width, sc.side);
+      cudaEventRecord(sc.join, sc.side);
+      gw_join = sc.join;
+    } else {
+      launch_gw_reduce(pl, (const float2*)(xs_saved + (size_t)k * ksp), GY, (float2*)g->spec_w1[k],
+                       (float2*)g->spec_w2[k], s->images, s->width, s->width, st);
+    }
     WinvArgs wa{};
     wa.z = GZ; wa.y = gz[cur ^ 1]; wa.a = gz[cur]; wa.zin = z_saved + (size_t)k * act;
     wa.pw_w = p->conv_w[k]; wa.g_pw_w = g->conv_w[k]; wa.g_pw_b = g->conv_b[k];
@@ -625,6 +687,7 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
     cur ^= 1;
   }
   launch_lift_bwd(make_lift(s, p, in), gz[cur], g->fc0_w, g->fc0_b, gx_cl, st);
+  if (gw_join != nullptr) cudaStreamWaitEvent(st, gw_join, 0);
   return check_cuda("bdn_fno_backward");
 }
 

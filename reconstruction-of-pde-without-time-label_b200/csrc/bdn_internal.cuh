@@ -15,14 +15,15 @@ namespace bdn {
 struct Plan {
   int ndim, hp, wp, m1, m2;
   int K;        // 2*m1 (1-D: 1)
-  int Kp;       // K rounded up to 8 (table row pitch of t_hk)
-  int hp8;      // hp rounded up to 8 (table row pitch of t_kh)
+  int F;        // m1 + 1 row frequencies 0..m1: the kept rows come in conjugate pairs (k = f, k = -f) that share cos / sin
+  int Fp;       // F rounded up to 4 (table row pitch of t_hf)
+  int hp8;      // hp rounded up to 8 (table row pitch of t_fh)
   int wp4;      // wp rounded up to 4 (row pitch of t_lw_cos / t_lw_sin)
   float2* t_wl;      // [wp][m2]   (cos theta, sin theta)      forward W transform
   float* t_lw_cos;   // [m2][wp4]  cos theta                   inverse W transform
   float* t_lw_sin;   // [m2][wp4]  sin theta
-  float2* t_hk;      // [hp][Kp]   (cos phi, sin phi)          forward H transform
-  float2* t_kh;      // [K][hp8]   (cos phi, sin phi)          inverse H transform
+  float2* t_hf;      // [hp][Fp]   (cos phi, sin phi), phi = 2*pi*f*h/hp     forward H transform (h-major)
+  float2* t_fh;      // [F][hp8]   (cos phi, sin phi)                          inverse H transform (f-major)
   float* col_fwd;    // [m2]  c_l / (hp*wp)   Hermitian doubling + irfft normalisation
   float* col_dc;     // [m2]  1-D: 0.5 at l = 0 (reference halves the DC bin), else 1
   // TF32 tensor-core path: the W tables as K-major GEMM operands (see tc_gemm.cu)

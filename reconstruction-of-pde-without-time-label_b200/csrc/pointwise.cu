@@ -7,6 +7,8 @@
 // tensor of the projection lives in registers only and is recomputed in backward.
 #include "bdn_internal.cuh"
 
+#include <cstdlib>
+
 namespace bdn {
 
 // ===========================================================================
@@ -738,7 +740,8 @@ static void launch_project_bwd_t(const ProjArgs& a, const float* g_out, int pool
                                  float* g_w1, float* g_b1, float* g_w2, float* g_b2, long total, cudaStream_t st) {
   constexpr int TILE = PROJ_THREADS / JS * PP;
   const long ntiles = (total + TILE - 1) / TILE;
-  const long cap = JS == 1 ? 148L * 2 : 148L * 4;
+  static const long cap8 = [] { const char* e = getenv("BDN_PROJ_BWD_CAP8"); return e ? atol(e) : 148L * 4; }();   // (tuning knob)
+  const long cap = JS == 1 ? 148L * 2 : cap8;
   const long rounds = (ntiles + cap - 1) / cap;
   const int grid = (int)((ntiles + rounds - 1) / rounds);      // balanced: every block runs `rounds` tiles
   size_t smem = (size_t)(2 * (a.hidden * CP + a.hidden + a.c_out * a.hidden) + PROJ_MAX_OUT) * sizeof(float);

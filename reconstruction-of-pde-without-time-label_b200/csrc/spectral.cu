@@ -306,74 +306,106 @@ bool launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act,
 
 // ===========================================================================
 // 2-D middle stage: H-forward -> mix -> H-inverse for one image and TL mode columns.
+//
+// The kept rows are k = 0..m1-1 (row frequency +k) and k = m1..2*m1-1 (frequency k - 2*m1 = -m1..-1): rows f and
+// K - f are a conjugate pair that shares cos / sin of phi = 2*pi*f*h/hp.  Both transforms work per FREQUENCY
+// f = 0..m1 (F = m1 + 1 of them) instead of per kept row, which halves their multiply-adds:
+//   forward   A_f = sum_h x_h cos, B_f = sum_h x_h sin  (4 FMA per h for the pair);  X[f] = A - iB,  X[K-f] = A + iB
+//   inverse   z_h = sum_f P_f cos + Q_f sin             (4 FMA per f for the pair);  P = Y[f] + Y[K-f],  Q = i (Y[f] - Y[K-f])
+// (f = 0 has only row 0 and f = m1 only row m1: the missing partner counts as zero.)
 // ===========================================================================
 struct CoreParams {
   const float2* in; float2* out; float2* spec_out;
   const float2* w1; const float2* w2;
   const float2* wt;      // optional mode-major copy [m2][K][ci][co] (few-image regime, see spec_weights_mode_major)
-  const float2* t_hk; const float2* t_kh;
+  const float2* t_hf; const float2* t_fh;
   const float* pre; const float* post;
-  int ca, cb, co_layer, hp, hp8, m1, m2, K, Kp, TL;
-  int tables_global;     // large hp x K: the DFT tables do not fit shared memory and are read through L1/L2
+  int ca, cb, co_layer, hp, hp8, m1, m2, K, F, Fp, TL;
+  int tables_global;     // large hp x F: the DFT tables do not fit shared memory and are read through L1/L2
 };
 
-// G = kept rows (phase 1) / spatial rows (phase 3) accumulated per work item.  Small G gives more
+// G = frequencies (phase 1) / spatial rows (phase 3) accumulated per work item.  Small G gives more
 // items per block (the few-image heads need that to keep 256 threads busy), large G more FMAs per
 // shared/L1 load (the many-image per-snapshot net).
 template <int G>
-__device__ __forceinline__ void cacc_rows(const float2 x, const float2* __restrict__ t, float (&re)[G], float (&im)[G],
-                                          const bool conj_table) {
-  // conj_table: multiply by (cos - i sin); otherwise by (cos + i sin)
+__device__ __forceinline__ void pacc_freqs(const float2 x, const float2* __restrict__ t, float (&ar)[G], float (&ai)[G],
+                                           float (&br)[G], float (&bi)[G]) {
   if constexpr (G == 1) {
     const float2 cs = *t;
-    if (conj_table) { re[0] = fmaf(x.x, cs.x, fmaf(x.y, cs.y, re[0])); im[0] = fmaf(x.y, cs.x, fmaf(-x.x, cs.y, im[0])); }
-    else            { re[0] = fmaf(x.x, cs.x, fmaf(-x.y, cs.y, re[0])); im[0] = fmaf(x.x, cs.y, fmaf(x.y, cs.x, im[0])); }
+    ar[0] = fmaf(x.x, cs.x, ar[0]); ai[0] = fmaf(x.y, cs.x, ai[0]);
+    br[0] = fmaf(x.x, cs.y, br[0]); bi[0] = fmaf(x.y, cs.y, bi[0]);
   } else {
     const float4* t4 = reinterpret_cast<const float4*>(t);
 #pragma unroll
     for (int q = 0; q < G / 2; ++q) {
       const float4 cs = t4[q];
-      if (conj_table) {
-        re[2 * q] = fmaf(x.x, cs.x, fmaf(x.y, cs.y, re[2 * q]));
-        im[2 * q] = fmaf(x.y, cs.x, fmaf(-x.x, cs.y, im[2 * q]));
-        re[2 * q + 1] = fmaf(x.x, cs.z, fmaf(x.y, cs.w, re[2 * q + 1]));
-        im[2 * q + 1] = fmaf(x.y, cs.z, fmaf(-x.x, cs.w, im[2 * q + 1]));
-      } else {
-        re[2 * q] = fmaf(x.x, cs.x, fmaf(-x.y, cs.y, re[2 * q]));
-        im[2 * q] = fmaf(x.x, cs.y, fmaf(x.y, cs.x, im[2 * q]));
-        re[2 * q + 1] = fmaf(x.x, cs.z, fmaf(-x.y, cs.w, re[2 * q + 1]));
-        im[2 * q + 1] = fmaf(x.x, cs.w, fmaf(x.y, cs.z, im[2 * q + 1]));
-      }
+      ar[2 * q] = fmaf(x.x, cs.x, ar[2 * q]);         ai[2 * q] = fmaf(x.y, cs.x, ai[2 * q]);
+      br[2 * q] = fmaf(x.x, cs.y, br[2 * q]);         bi[2 * q] = fmaf(x.y, cs.y, bi[2 * q]);
+      ar[2 * q + 1] = fmaf(x.x, cs.z, ar[2 * q + 1]); ai[2 * q + 1] = fmaf(x.y, cs.z, ai[2 * q + 1]);
+      br[2 * q + 1] = fmaf(x.x, cs.w, br[2 * q + 1]); bi[2 * q + 1] = fmaf(x.y, cs.w, bi[2 * q + 1]);
     }
   }
 }
 
-template <bool BWD, int G1, int G3>   // kept rows per phase-1 item, spatial rows per phase-3 item
+// pq = (P.re, P.im, Q.re, Q.im) of one frequency; z_h += P cos + Q sin for G rows h
+template <int G>
+__device__ __forceinline__ void pacc_rows(const float4 pq, const float2* __restrict__ t, float (&re)[G], float (&im)[G]) {
+  if constexpr (G == 1) {
+    const float2 cs = *t;
+    re[0] = fmaf(pq.x, cs.x, fmaf(pq.z, cs.y, re[0]));
+    im[0] = fmaf(pq.y, cs.x, fmaf(pq.w, cs.y, im[0]));
+  } else {
+    const float4* t4 = reinterpret_cast<const float4*>(t);
+#pragma unroll
+    for (int q = 0; q < G / 2; ++q) {
+      const float4 cs = t4[q];
+      re[2 * q] = fmaf(pq.x, cs.x, fmaf(pq.z, cs.y, re[2 * q]));
+      im[2 * q] = fmaf(pq.y, cs.x, fmaf(pq.w, cs.y, im[2 * q]));
+      re[2 * q + 1] = fmaf(pq.x, cs.z, fmaf(pq.z, cs.w, re[2 * q + 1]));
+      im[2 * q + 1] = fmaf(pq.y, cs.z, fmaf(pq.w, cs.w, im[2 * q + 1]));
+    }
+  }
+}
+
+// rows of the conjugate pair of frequency f: X[f] = A - iB (f < m1), X[K-f] = A + iB (f > 0), scaled
+__device__ __forceinline__ float2 pair_lo(float ar, float ai, float br, float bi, float sc) {
+  return make_float2((ar + bi) * sc, (ai - br) * sc);
+}
+__device__ __forceinline__ float2 pair_hi(float ar, float ai, float br, float bi, float sc) {
+  return make_float2((ar - bi) * sc, (ai + br) * sc);
+}
+// (P, Q) of the pair (Y[f], Y[K-f]); a missing partner is zero
+__device__ __forceinline__ float4 pair_pq(const float2 y1, const float2 y2) {
+  return make_float4(y1.x + y2.x, y1.y + y2.y, y2.y - y1.y, y1.x - y2.x);
+}
+
+template <bool BWD, int G1, int G3>   // frequencies per phase-1 item, spatial rows per phase-3 item
 __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
   extern __shared__ __align__(16) float smem[];
-  const int TL = p.TL, Pa = p.ca * TL, Pb = p.cb * TL, K = p.K, hp = p.hp, m2 = p.m2;
-  const int nA = (max(hp * Pa, K * Pb) + 1) & ~1;
-  float2* bufA = reinterpret_cast<float2*>(smem);
+  const int TL = p.TL, Pa = p.ca * TL, Pb = p.cb * TL, K = p.K, F = p.F, hp = p.hp, m2 = p.m2;
+  const int nA = (max(hp * Pa, 2 * F * Pb) + 1) & ~1;
+  float2* bufA = reinterpret_cast<float2*>(smem);            // phase 0/1: x[h][pa]; phase 2/3: (P, Q)[f][pb] as float4
+  float4* bufPQ = reinterpret_cast<float4*>(smem);
   float2* bufX = bufA + nA;
   float2* tab = bufX + K * Pa + ((K * Pa) & 1);
   const bool tg = p.tables_global != 0;
-  const float2* s_hk = tg ? p.t_hk : tab;                  // [hp][Kp], 16-byte aligned rows
-  const float2* s_kh = tg ? p.t_kh : tab + hp * p.Kp;      // [K][hp8]
+  const float2* s_hf = tg ? p.t_hf : tab;                  // [hp][Fp], 16-byte aligned rows
+  const float2* s_fh = tg ? p.t_fh : tab + hp * p.Fp;      // [F][hp8]
   const int l0 = blockIdx.x * TL, b = blockIdx.y;
   const int tid = threadIdx.x, nt = blockDim.x;
 
   // the two DFT tables live in shared memory for the block's lifetime (they are re-read by every
   // item; from L1/L2 the inner loops were latency-bound: ncu long-scoreboard 20 cycles per issue).
   // Both are contiguous in HBM: two bulk async copies, in flight while phase 0 stages the image.
-  uint64_t* tbar = reinterpret_cast<uint64_t*>(tab + (tg ? 0 : hp * p.Kp + K * p.hp8));
+  uint64_t* tbar = reinterpret_cast<uint64_t*>(tab + (tg ? 0 : hp * p.Fp + F * p.hp8));
   pdl_launch_dependents();
   if (tid == 0 && !tg) {
     mbar_init(tbar, 1);
     mbar_init_fence();
-    const uint32_t b1 = (uint32_t)(hp * p.Kp) * 8u, b2 = (uint32_t)(K * p.hp8) * 8u;
+    const uint32_t b1 = (uint32_t)(hp * p.Fp) * 8u, b2 = (uint32_t)(F * p.hp8) * 8u;
     mbar_expect_tx(tbar, b1 + b2);
-    bulk_g2s(tab, p.t_hk, b1, tbar);
-    bulk_g2s(tab + hp * p.Kp, p.t_kh, b2, tbar);
+    bulk_g2s(tab, p.t_hf, b1, tbar);
+    bulk_g2s(tab + hp * p.Fp, p.t_fh, b2, tbar);
   }
   pdl_wait();      // the tables above are constant plan data; everything below reads the previous kernel's output
   // phase 0: stage the image's TL columns, all channels: bufA[h][a*TL + lt]
@@ -386,99 +418,118 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
   __syncthreads();          // also publishes the mbarrier init to the waiting threads
   if (!tg) mbar_wait(tbar, 0);
 
-  // phase 1: X[k][pa] = pre[l] * sum_h x[h][pa] * e^{-i phi_kh}, G1 kept rows per item
+  // phase 1: X[k][pa] = pre[l] * sum_h x[h][pa] * e^{-i phi_kh}, G1 frequencies (row pairs) per item
   constexpr int G = G1;
-  const int nkg = (K + G - 1) / G;
-  for (int idx = tid; idx < Pa * nkg; idx += nt) {
-    const int pa = idx % Pa, kg = idx / Pa;
-    float re[G], im[G];
+  const int nfg = (F + G - 1) / G;
+  for (int idx = tid; idx < Pa * nfg; idx += nt) {
+    const int pa = idx % Pa, fg = idx / Pa;
+    float ar[G], ai[G], br[G], bi[G];
 #pragma unroll
-    for (int j = 0; j < G; ++j) re[j] = im[j] = 0.f;
-    const float2* trow = s_hk + kg * G;
+    for (int j = 0; j < G; ++j) ar[j] = ai[j] = br[j] = bi[j] = 0.f;
+    const float2* trow = s_hf + fg * G;
 #pragma unroll 4
-    for (int h = 0; h < hp; ++h) cacc_rows<G>(bufA[h * Pa + pa], trow + (size_t)h * p.Kp, re, im, true);
+    for (int h = 0; h < hp; ++h) pacc_freqs<G>(bufA[h * Pa + pa], trow + (size_t)h * p.Fp, ar, ai, br, bi);
     const int a = pa / TL, lt = pa - a * TL, l = l0 + lt;
     const float sc = l < m2 ? __ldg(p.pre + l) : 0.f;
+    float2* so = (p.spec_out != nullptr && l < m2) ? p.spec_out + (size_t)(b * p.ca + a) * K * m2 + l : nullptr;
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-      const int k = kg * G + j;
-      if (k < K) {
-        const float2 v = make_float2(re[j] * sc, im[j] * sc);
-        bufX[k * Pa + pa] = v;
-        if (p.spec_out != nullptr && l < m2) p.spec_out[((size_t)(b * p.ca + a) * K + k) * m2 + l] = v;
+      const int f = fg * G + j;
+      if (f < p.m1) {
+        const float2 v = pair_lo(ar[j], ai[j], br[j], bi[j], sc);
+        bufX[f * Pa + pa] = v;
+        if (so != nullptr) so[(size_t)f * m2] = v;
+      }
+      if (f > 0 && f <= p.m1) {
+        const float2 v = pair_hi(ar[j], ai[j], br[j], bi[j], sc);
+        bufX[(K - f) * Pa + pa] = v;
+        if (so != nullptr) so[(size_t)(K - f) * m2] = v;
       }
     }
   }
   __syncthreads();
 
-  // phase 2: per-mode channel mix.  fwd: y_b = sum_a x_a W[a][b]; bwd: y_b = sum_a x_a conj(W[b][a])
+  // phase 2: per-mode channel mix of both rows of a frequency -> (P, Q).
+  // fwd: y_b = sum_a x_a W[a][b]; bwd: y_b = sum_a x_a conj(W[b][a])
   if (p.wt != nullptr) {
     // mode-major weights: the K*ci*co coefficients of one mode column are contiguous, so a block that owns
     // few columns reads them with full sectors (the parameter layout has the mode index innermost: one
     // 8-byte element per 32-byte sector for a single column)
     const int ci = BWD ? p.cb : p.ca, co = p.co_layer;
-    for (int idx = tid; idx < K * Pb; idx += nt) {
-      const int bc = idx % p.cb, k = (idx / p.cb) % K, lt = idx / (p.cb * K);
+    for (int idx = tid; idx < F * Pb; idx += nt) {
+      const int bc = idx % p.cb, f = (idx / p.cb) % F, lt = idx / (p.cb * F);
       const int l = l0 + lt;
-      float yr = 0.f, yi = 0.f;
+      float2 y[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       if (l < m2) {
-        const float2* wm = p.wt + ((size_t)l * K + k) * ci * co;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          if (r == 0 ? f >= p.m1 : f == 0) continue;
+          const int k = r == 0 ? f : K - f;
+          const float2* wm = p.wt + ((size_t)l * K + k) * ci * co;
+          float yr = 0.f, yi = 0.f;
 #pragma unroll 4
-        for (int a = 0; a < p.ca; ++a) {
-          const float2 x = bufX[k * Pa + a * TL + lt];
-          if (!BWD) {
-            const float2 w = __ldg(wm + a * co + bc);
-            yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
-            yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
-          } else {
-            const float2 w = __ldg(wm + bc * co + a);
-            yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
-            yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
+          for (int a = 0; a < p.ca; ++a) {
+            const float2 x = bufX[k * Pa + a * TL + lt];
+            if (!BWD) {
+              const float2 w = __ldg(wm + a * co + bc);
+              yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
+              yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
+            } else {
+              const float2 w = __ldg(wm + bc * co + a);
+              yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
+              yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
+            }
           }
+          y[r] = make_float2(yr, yi);
         }
       }
-      bufA[k * Pb + bc * TL + lt] = make_float2(yr, yi);
+      bufPQ[f * Pb + bc * TL + lt] = pair_pq(y[0], y[1]);
     }
   } else {
-    for (int idx = tid; idx < K * Pb; idx += nt) {
-      const int lt = idx % TL, k = (idx / TL) % K, bc = idx / (TL * K);
+    for (int idx = tid; idx < F * Pb; idx += nt) {
+      const int lt = idx % TL, f = (idx / TL) % F, bc = idx / (TL * F);
       const int l = l0 + lt;
-      float yr = 0.f, yi = 0.f;
+      float2 y[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       if (l < m2) {
-        const bool lo = k < p.m1;
-        const float2* wsel = lo ? p.w1 : p.w2;
-        const int kk = lo ? k : k - p.m1;
-        const size_t mode_off = (size_t)kk * m2 + l;
         const size_t cstride = (size_t)p.m1 * m2;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          if (r == 0 ? f >= p.m1 : f == 0) continue;
+          const int k = r == 0 ? f : K - f;
+          const float2* wsel = r == 0 ? p.w1 : p.w2;           // row k >= m1 is row k - m1 of weights2
+          const size_t mode_off = (size_t)(r == 0 ? f : p.m1 - f) * m2 + l;
+          float yr = 0.f, yi = 0.f;
 #pragma unroll 4
-        for (int a = 0; a < p.ca; ++a) {
-          const float2 x = bufX[k * Pa + a * TL + lt];
-          if (!BWD) {
-            const float2 w = __ldg(wsel + (size_t)(a * p.co_layer + bc) * cstride + mode_off);
-            yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
-            yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
-          } else {
-            const float2 w = __ldg(wsel + (size_t)(bc * p.co_layer + a) * cstride + mode_off);
-            yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
-            yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
+          for (int a = 0; a < p.ca; ++a) {
+            const float2 x = bufX[k * Pa + a * TL + lt];
+            if (!BWD) {
+              const float2 w = __ldg(wsel + (size_t)(a * p.co_layer + bc) * cstride + mode_off);
+              yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
+              yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
+            } else {
+              const float2 w = __ldg(wsel + (size_t)(bc * p.co_layer + a) * cstride + mode_off);
+              yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
+              yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
+            }
           }
+          y[r] = make_float2(yr, yi);
         }
       }
-      bufA[k * Pb + bc * TL + lt] = make_float2(yr, yi);
+      bufPQ[f * Pb + bc * TL + lt] = pair_pq(y[0], y[1]);
     }
   }
   __syncthreads();
 
-  // phase 3: Z[h][pb] = post[l] * sum_k y[k][pb] * e^{+i phi_kh}, G3 rows per item
+  // phase 3: Z[h][pb] = post[l] * sum_k y[k][pb] * e^{+i phi_kh} = post[l] * sum_f P cos + Q sin, G3 rows per item
   const int nhg = (hp + G3 - 1) / G3;
   for (int idx = tid; idx < Pb * nhg; idx += nt) {
     const int pb = idx % Pb, hg = idx / Pb;
     float re[G3], im[G3];
 #pragma unroll
     for (int j = 0; j < G3; ++j) re[j] = im[j] = 0.f;
-    const float2* trow = s_kh + hg * G3;
+    const float2* trow = s_fh + hg * G3;
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) cacc_rows<G3>(bufA[k * Pb + pb], trow + (size_t)k * p.hp8, re, im, false);
+    for (int f = 0; f < F; ++f) pacc_rows<G3>(bufPQ[f * Pb + pb], trow + (size_t)f * p.hp8, re, im);
     const int bc = pb / TL, lt = pb - bc * TL, l = l0 + lt;
     if (l >= m2) continue;
     const float sc = __ldg(p.post + l);
@@ -500,16 +551,16 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
 template <bool BWD, int G1, int G3>
 __global__ void __launch_bounds__(1024) core2d_stream_kernel(const CoreParams p, int images) {
   extern __shared__ __align__(16) float smem[];
-  const int K = p.K, hp = p.hp, m2 = p.m2, Pa = p.ca * m2, Pb = p.cb * m2;
+  const int K = p.K, F = p.F, hp = p.hp, m2 = p.m2, Pa = p.ca * m2, Pb = p.cb * m2;
   const int in_elems = p.ca * hp * m2;                      // float2 per image (even: m2*hp*ca*... padded below)
   const int in_pad = (in_elems + 1) & ~1;
   float2* in0 = reinterpret_cast<float2*>(smem);
   float2* in1 = in0 + in_pad;
   float2* bufX = in1 + in_pad;                              // [K][Pa]
-  float2* bufY = bufX + ((K * Pa + 1) & ~1);                // [K][Pb]
-  float2* s_hk = bufY + ((K * Pb + 1) & ~1);                // [hp][Kp]
-  float2* s_kh = s_hk + hp * p.Kp;                          // [K][hp8]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kh + K * p.hp8);   // [0],[1]: image stages, [2]: tables
+  float4* bufPQ = reinterpret_cast<float4*>(bufX + ((K * Pa + 1) & ~1));   // [F][Pb] (P, Q)
+  float2* s_hf = reinterpret_cast<float2*>(bufPQ + F * Pb); // [hp][Fp]
+  float2* s_fh = s_hf + hp * p.Fp;                          // [F][hp8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_fh + F * p.hp8);   // [0],[1]: image stages, [2]: tables
   const int tid = threadIdx.x, nt = blockDim.x;
   const uint32_t img_bytes = (uint32_t)in_elems * 8u;
 
@@ -519,10 +570,10 @@ __global__ void __launch_bounds__(1024) core2d_stream_kernel(const CoreParams p,
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
     mbar_init_fence();
-    const uint32_t b1 = (uint32_t)(hp * p.Kp) * 8u, b2 = (uint32_t)(K * p.hp8) * 8u;
+    const uint32_t b1 = (uint32_t)(hp * p.Fp) * 8u, b2 = (uint32_t)(F * p.hp8) * 8u;
     mbar_expect_tx(&bars[2], b1 + b2);
-    bulk_g2s(s_hk, p.t_hk, b1, &bars[2]);
-    bulk_g2s(s_kh, p.t_kh, b2, &bars[2]);
+    bulk_g2s(s_hf, p.t_hf, b1, &bars[2]);
+    bulk_g2s(s_fh, p.t_fh, b2, &bars[2]);
   }
   pdl_wait();
   __syncthreads();
@@ -541,67 +592,78 @@ __global__ void __launch_bounds__(1024) core2d_stream_kernel(const CoreParams p,
     mbar_wait(&bars[stage], (it >> 1) & 1);
     const float2* xin = stage ? in1 : in0;                  // [a][h][l]
 
-    // phase 1: X[k][(a,l)] = pre[l] * sum_h x[a][h][l] * e^{-i phi_kh}
-    const int nkg = (K + G1 - 1) / G1;
-    for (int idx = tid; idx < Pa * nkg; idx += nt) {
-      const int pa = idx % Pa, kg = idx / Pa;
+    // phase 1: X[k][(a,l)] = pre[l] * sum_h x[a][h][l] * e^{-i phi_kh}, by frequency (row pairs)
+    const int nfg = (F + G1 - 1) / G1;
+    for (int idx = tid; idx < Pa * nfg; idx += nt) {
+      const int pa = idx % Pa, fg = idx / Pa;
       const int a = pa / m2, l = pa - a * m2;
-      float re[G1], im[G1];
+      float ar[G1], ai[G1], br[G1], bi[G1];
 #pragma unroll
-      for (int j = 0; j < G1; ++j) re[j] = im[j] = 0.f;
-      const float2* trow = s_hk + kg * G1;
+      for (int j = 0; j < G1; ++j) ar[j] = ai[j] = br[j] = bi[j] = 0.f;
+      const float2* trow = s_hf + fg * G1;
       const float2* xcol = xin + (size_t)a * hp * m2 + l;
 #pragma unroll 4
-      for (int h = 0; h < hp; ++h) cacc_rows<G1>(xcol[h * m2], trow + (size_t)h * p.Kp, re, im, true);
+      for (int h = 0; h < hp; ++h) pacc_freqs<G1>(xcol[h * m2], trow + (size_t)h * p.Fp, ar, ai, br, bi);
       const float sc = __ldg(p.pre + l);
+      float2* so = p.spec_out != nullptr ? p.spec_out + (size_t)(b * p.ca + a) * K * m2 + l : nullptr;
 #pragma unroll
       for (int j = 0; j < G1; ++j) {
-        const int k = kg * G1 + j;
-        if (k < K) {
-          const float2 v = make_float2(re[j] * sc, im[j] * sc);
-          bufX[k * Pa + pa] = v;
-          if (p.spec_out != nullptr) p.spec_out[((size_t)(b * p.ca + a) * K + k) * m2 + l] = v;
+        const int f = fg * G1 + j;
+        if (f < p.m1) {
+          const float2 v = pair_lo(ar[j], ai[j], br[j], bi[j], sc);
+          bufX[f * Pa + pa] = v;
+          if (so != nullptr) so[(size_t)f * m2] = v;
+        }
+        if (f > 0 && f <= p.m1) {
+          const float2 v = pair_hi(ar[j], ai[j], br[j], bi[j], sc);
+          bufX[(K - f) * Pa + pa] = v;
+          if (so != nullptr) so[(size_t)(K - f) * m2] = v;
         }
       }
     }
     __syncthreads();
 
-    // phase 2: per-mode channel mix
-    for (int idx = tid; idx < K * Pb; idx += nt) {
-      const int l = idx % m2, k = (idx / m2) % K, bc = idx / (m2 * K);
-      const bool lo = k < p.m1;
-      const float2* wsel = lo ? p.w1 : p.w2;
-      const int kk = lo ? k : k - p.m1;
-      const size_t mode_off = (size_t)kk * m2 + l;
+    // phase 2: per-mode channel mix of both rows of a frequency -> (P, Q)
+    for (int idx = tid; idx < F * Pb; idx += nt) {
+      const int l = idx % m2, f = (idx / m2) % F, bc = idx / (m2 * F);
       const size_t cstride = (size_t)p.m1 * m2;
-      float yr = 0.f, yi = 0.f;
+      float2 y[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (r == 0 ? f >= p.m1 : f == 0) continue;
+        const int k = r == 0 ? f : K - f;
+        const float2* wsel = r == 0 ? p.w1 : p.w2;             // row k >= m1 is row k - m1 of weights2
+        const size_t mode_off = (size_t)(r == 0 ? f : p.m1 - f) * m2 + l;
+        float yr = 0.f, yi = 0.f;
 #pragma unroll 4
-      for (int a = 0; a < p.ca; ++a) {
-        const float2 x = bufX[k * Pa + a * m2 + l];
-        if (!BWD) {
-          const float2 w = __ldg(wsel + (size_t)(a * p.co_layer + bc) * cstride + mode_off);
-          yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
-          yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
-        } else {
-          const float2 w = __ldg(wsel + (size_t)(bc * p.co_layer + a) * cstride + mode_off);
-          yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
-          yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
+        for (int a = 0; a < p.ca; ++a) {
+          const float2 x = bufX[k * Pa + a * m2 + l];
+          if (!BWD) {
+            const float2 w = __ldg(wsel + (size_t)(a * p.co_layer + bc) * cstride + mode_off);
+            yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
+            yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
+          } else {
+            const float2 w = __ldg(wsel + (size_t)(bc * p.co_layer + a) * cstride + mode_off);
+            yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
+            yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
+          }
         }
+        y[r] = make_float2(yr, yi);
       }
-      bufY[k * Pb + bc * m2 + l] = make_float2(yr, yi);
+      bufPQ[f * Pb + bc * m2 + l] = pair_pq(y[0], y[1]);
     }
     __syncthreads();
 
-    // phase 3: Z[(bc)][h][l] = post[l] * sum_k y[k][(bc,l)] * e^{+i phi_kh}
+    // phase 3: Z[(bc)][h][l] = post[l] * sum_f P cos + Q sin
     const int nhg = (hp + G3 - 1) / G3;
     for (int idx = tid; idx < Pb * nhg; idx += nt) {
       const int pb = idx % Pb, hg = idx / Pb;
       float re[G3], im[G3];
 #pragma unroll
       for (int j = 0; j < G3; ++j) re[j] = im[j] = 0.f;
-      const float2* trow = s_kh + hg * G3;
+      const float2* trow = s_fh + hg * G3;
 #pragma unroll 4
-      for (int k = 0; k < K; ++k) cacc_rows<G3>(bufY[k * Pb + pb], trow + (size_t)k * p.hp8, re, im, false);
+      for (int f = 0; f < F; ++f) pacc_rows<G3>(bufPQ[f * Pb + pb], trow + (size_t)f * p.hp8, re, im);
       const int bc = pb / m2, l = pb - bc * m2;
       const float sc = __ldg(p.post + l);
 #pragma unroll
@@ -611,7 +673,7 @@ __global__ void __launch_bounds__(1024) core2d_stream_kernel(const CoreParams p,
       }
     }
     fence_proxy_async();
-    __syncthreads();          // bufX / bufY and this image stage are free again
+    __syncthreads();          // bufX / bufPQ and this image stage are free again
   }
 }
 
@@ -671,25 +733,25 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
   LaunchScope scope(bwd ? "core2d_bwd" : "core2d_fwd", st, co_layer);
   CoreParams p;
   p.in = in; p.out = out; p.spec_out = spec_out; p.w1 = w1; p.w2 = w2; p.wt = wt;
-  p.t_hk = pl->t_hk; p.t_kh = pl->t_kh;
+  p.t_hf = pl->t_hf; p.t_fh = pl->t_fh;
   p.pre = bwd ? pl->col_fwd : pl->col_dc;
   p.post = bwd ? pl->col_dc : pl->col_fwd;
   p.ca = bwd ? co_layer : ci_layer;
   p.cb = bwd ? ci_layer : co_layer;
   p.co_layer = co_layer;
-  p.hp = pl->hp; p.hp8 = pl->hp8; p.m1 = pl->m1; p.m2 = pl->m2; p.K = pl->K; p.Kp = pl->Kp;
-  const size_t table_f2 = (size_t)pl->hp * pl->Kp + (size_t)pl->K * pl->hp8;
-  p.tables_global = table_f2 * sizeof(float2) > 150 * 1024;    // e.g. 160 x 128 or 320 x 64: 327 KB of tables
-  // many images: persistent streaming kernel, whole images per block (G1 = 2 kept rows, G3 = 8 rows per item)
+  p.hp = pl->hp; p.hp8 = pl->hp8; p.m1 = pl->m1; p.m2 = pl->m2; p.K = pl->K; p.F = pl->F; p.Fp = pl->Fp;
+  const size_t table_f2 = (size_t)pl->hp * pl->Fp + (size_t)pl->F * pl->hp8;
+  p.tables_global = table_f2 * sizeof(float2) > 150 * 1024;    // e.g. 320 x 128: 337 KB of tables
+  // many images: persistent streaming kernel, whole images per block (G1 = 2 frequencies, G3 = 8 rows per item)
   {
     const size_t in_pad = ((size_t)p.ca * pl->hp * pl->m2 + 1) & ~(size_t)1;
-    const size_t nX = ((size_t)pl->K * p.ca * pl->m2 + 1) & ~(size_t)1, nY = ((size_t)pl->K * p.cb * pl->m2 + 1) & ~(size_t)1;
-    const size_t smem_s = (2 * in_pad + nX + nY + (size_t)pl->hp * pl->Kp + (size_t)pl->K * pl->hp8) * sizeof(float2) + 32;
+    const size_t nX = ((size_t)pl->K * p.ca * pl->m2 + 1) & ~(size_t)1, nPQ = 2 * (size_t)pl->F * p.cb * pl->m2;
+    const size_t smem_s = (2 * in_pad + nX + nPQ + (size_t)pl->hp * pl->Fp + (size_t)pl->F * pl->hp8) * sizeof(float2) + 32;
     const bool aligned = (((size_t)p.ca * pl->hp * pl->m2 * 8) & 15) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
     if (images >= 148 && smem_s <= 110 * 1024 && aligned) {
       p.TL = pl->m2;
       const int Pa_s = p.ca * pl->m2, Pb_s = p.cb * pl->m2;
-      const int items1 = Pa_s * ceil_div(pl->K, 2), items3 = Pb_s * ceil_div(pl->hp, 8);
+      const int items1 = Pa_s * ceil_div(pl->F, 2), items3 = Pb_s * ceil_div(pl->hp, 8);
       int threads = items1 > items3 ? items1 : items3;
       threads = ceil_div(threads, ceil_div(threads, 1024));
       threads = (threads + 31) & ~31;
@@ -705,7 +767,8 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
   // TL mode columns per block: the widest column tile that still leaves >= 2 blocks per SM and fits
   // shared memory (wide tiles read the W-transformed image with full 32-byte sectors)
   auto smem_of = [&](int t) {
-    size_t nA = (size_t)((pl->hp * p.ca > pl->K * p.cb) ? pl->hp * p.ca : pl->K * p.cb) * t;
+    const size_t a0 = (size_t)pl->hp * p.ca, a1 = 2 * (size_t)pl->F * p.cb;
+    size_t nA = (a0 > a1 ? a0 : a1) * t;
     nA = (nA + 1) & ~(size_t)1;
     const size_t nX = (size_t)pl->K * p.ca * t;
     return (nA + nX + (nX & 1) + (p.tables_global ? 0 : table_f2)) * sizeof(float2) + 16;
@@ -719,17 +782,17 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
   p.TL = tl;
   const size_t smem = smem_of(tl);
   dim3 grid(ceil_div(pl->m2, tl), images);
-  // Work items: phase 1 has Pa * ceil(K / G1), phase 3 has Pb * ceil(hp / G3).  With few images (the
+  // Work items: phase 1 has Pa * ceil(F / G1), phase 3 has Pb * ceil(hp / G3).  With few images (the
   // heads) every block should run as many threads as it has items (latency-bound); with many images
   // (the per-snapshot net) larger G gives more FMAs per shared-memory load.
   const int Pa = p.ca * tl, Pb = p.cb * tl;
   int g1 = 1, g3 = 1;
   const int target = 256;
   for (int cand = 4; cand >= 1; cand >>= 1)
-    if (Pa * ceil_div(pl->K, cand) >= target || cand == 1) { g1 = cand; break; }
+    if (Pa * ceil_div(pl->F, cand) >= target || cand == 1) { g1 = cand; break; }
   for (int cand = 8; cand >= 1; cand >>= 1)
     if (Pb * ceil_div(pl->hp, cand) >= target || cand == 1) { g3 = cand; break; }
-  const int items1 = Pa * ceil_div(pl->K, g1), items3 = Pb * ceil_div(pl->hp, g3);
+  const int items1 = Pa * ceil_div(pl->F, g1), items3 = Pb * ceil_div(pl->hp, g3);
   const int most = items1 > items3 ? items1 : items3;
   int threads = ceil_div(most, ceil_div(most, 1024));      // balanced rounds when one block cannot hold all items
   threads = (threads + 31) & ~31;

@@ -308,13 +308,19 @@ def test_default_shape_train_step_at_the_benchmarked_batch(prec):
 
 def test_default_shape_1d_gpe_nio_vs_oracle():
     """BASELINE.json configs[1] at the script's own constructor: NIOFP_schrodinger(1, 3, 100, 25, 3, 20, 40, 1), bags of
-    101 snapshots of 128 points (1d_GPE/train_nio_GPE.py:89-109,124), train mode.  The conv encoder + train-mode
-    BatchNorm run on cuDNN (summation order differs from the CPU's): outputs 5e-5, gradients 2e-3 as for the NIO
-    fixtures; the FNO head and the pooled tail are this library's kernels."""
+    101 snapshots of 128 points (1d_GPE/train_nio_GPE.py:89-109,124), train mode, against the oracle in fp32 (what the
+    reference computes on the CPU) and in fp64 (the truth both are measured against).
+
+    This library's kernels are the pooled tail (nio_tail) and the FNO head; the conv encoder + train-mode BatchNorm are
+    cuDNN calls.  Outputs: 5e-5.  Gradients of everything downstream of the encoder output -- the head, the trunk, b0 and
+    the gradient that ENTERS the encoder (d loss / d coefficients) -- by _grad_check at the NIO bound 2e-3.  The encoder's
+    own parameter gradients come out of cuDNN's backward kernels: they are checked against stock PyTorch on the same
+    GPU (same library kernels, its own incoming gradient: the NIO bound 2e-3) and, loosely (1e-2, measured ~2.5e-3 on conv1: cancelling
+    sums over 404 snapshots through seven train-mode BatchNorms), against fp64; both errors go to the parity report."""
     torch.manual_seed(5)
     model = nio.make_models("1d_GPE")["NIOFP_schrodinger"](1, 3, 100, 25, 3, 20, 40, 1, "cpu")
     params = {k: v.clone() for k, v in model.state_dict().items()}
-    heads = model.head_names
+    heads = tuple(model.head_names)
     model = model.to(DEV).train()
     g = torch.Generator().manual_seed(0)
     x, gy = torch.randn(4, 101, 128, generator=g).abs(), torch.randn(4, 128, 1, generator=g)
@@ -322,24 +328,63 @@ def test_default_shape_1d_gpe_nio_vs_oracle():
     np.random.seed(6)
     idx = O.draw_bag(101, True)
     np.random.seed(6)
+    seen = {}
+    hook = model.branch.register_forward_hook(lambda m, i, o: o.register_hook(lambda gr: seen.__setitem__("g_coeff", gr.detach().clone())))
     prev = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
         y = model(x.to(DEV), grid.to(DEV))
         y.backward(gy.to(DEV))
     finally:
+        hook.remove()
+
+    def oracle_run(dt, dev):
+        def cast(v):
+            if v.is_complex():
+                return v.to(torch.complex128 if dt == torch.float64 else torch.complex64).to(dev)
+            return (v.to(dt) if v.is_floating_point() else v).to(dev)
+        leaf = {k: (cast(v).clone().requires_grad_(True) if (v.is_floating_point() or v.is_complex())
+                    and not k.endswith(("running_mean", "running_var")) else cast(v).clone()) for k, v in params.items()}
+        xx, gg = x.to(dt).to(dev), grid.to(dt).to(dev)
+        coeff = O.encoder1d_forward(leaf, xx[:, torch.as_tensor(idx)], "branch.", True, True)
+        coeff.retain_grad()
+        basis = O.ffn_forward(leaf, gg, "trunk.", True)
+        lifted = O.bag_pool_lift(O.deeponet_forward(leaf, coeff, basis), gg, leaf["fc0.weight"], leaf["fc0.bias"])
+        outs = [O.fno1d_forward(leaf, lifted, prefix=h + ".") for h in heads]
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
+        out.backward(gy.to(dt).to(dev))
+        return out.detach(), leaf, coeff.grad
+
+    try:
+        y32, leaf32, gc32 = oracle_run(torch.float32, "cpu")
+        y64, leaf64, gc64 = oracle_run(torch.float64, "cpu")
+        _, leaf_cuda, _ = oracle_run(torch.float32, DEV)        # stock PyTorch on the same GPU (cuDNN encoder)
+    finally:
         torch.backends.cudnn.allow_tf32 = prev
-    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("running_mean", "running_var")) else v.clone())
-            for k, v in params.items()}
-    want = O.nio1d_forward(leaf, x, grid, heads=tuple(heads), training=True, idx=idx)
-    want.backward(gy)
-    assert rel_err(y, want) < 5e-5
+    assert rel_err(y, y32) < 5e-5 and rel_err(y, y64) < 5e-5
     got = dict(model.named_parameters())
+    gmax = _gmax({k: v.grad for k, v in leaf64.items() if torch.is_tensor(v) and v.requires_grad})
+    _grad_check("d loss / d branch coefficients", seen["g_coeff"], gc32, gc64, tol=2e-3, floor=1.2e-7 * gmax)
+    from tests.conftest import PARITY_RECORDS
     checked = 0
-    for k, v in leaf.items():
-        if torch.is_tensor(v) and v.requires_grad and v.grad is not None and k in got and got[k].grad is not None:
-            assert rel_err(got[k].grad, v.grad) < 2e-3, k
-            checked += 1
+    for k, v in leaf64.items():
+        if not (torch.is_tensor(v) and v.requires_grad and v.grad is not None and k in got and got[k].grad is not None):
+            continue
+        checked += 1
+        if not k.startswith("branch."):
+            _grad_check(k, got[k].grad, leaf32[k].grad, v.grad, tol=2e-3, floor=1.2e-7 * gmax)
+            continue
+        scale = v.grad.abs().max().item()
+        if scale < 1e3 * 1.2e-7 * gmax:      # conv biases in front of a train-mode BatchNorm: the true gradient is zero
+            continue
+        vs_cuda = (got[k].grad.cpu().double() - leaf_cuda[k].grad.cpu().double()).abs().max().item() / scale
+        vs_64 = (got[k].grad.cpu().double() - v.grad).abs().max().item() / scale
+        PARITY_RECORDS.append({"case": "test_default_shape_1d_gpe_nio_vs_oracle", "tensor": k, "rel_err": vs_64,
+                               "reference_fp32_rel_err": (leaf32[k].grad.double() - v.grad).abs().max().item() / scale,
+                               "scale": scale, "floor_rel": 0.0,
+                               "admitted_by": f"cuDNN encoder: vs stock PyTorch CUDA {vs_cuda:.2e} (2e-3), vs fp64 (1e-2)"})
+        assert vs_cuda < 2e-3, (k, vs_cuda)
+        assert vs_64 < 1e-2, (k, vs_64)
     assert checked > 20
 
 
