@@ -24,12 +24,14 @@ static std::atomic<long long> g_launches{0};
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+thread_local int pdl_few_images = 0;
+
 bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("BDN_PDL");      // opt-in: measured neutral under CUDA-graph replay (profiles/README.md)
-    return e && e[0] == '1';
+  static const int mode = [] {
+    const char* e = getenv("BDN_PDL");      // opt-in (profiles/README.md)
+    return e ? atoi(e) : 0;
   }();
-  return on;
+  return mode == 1 || (mode == 2 && !pdl_few_images);
 }
 
 int set_error(int code, const char* fmt, ...) {
@@ -547,6 +549,8 @@ int bdn_fno_forward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftIn
     return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
   auto zbuf = [&](int k) { return z_saved ? z_saved + (size_t)k * act : zping[k & 1]; };
   const bool tc = use_tc_layer(s, pl);
+  struct FewGuard { int prev; FewGuard(bool few) : prev(pdl_few_images) { pdl_few_images = few; } ~FewGuard() { pdl_few_images = prev; } }
+      few_guard(use_mode_major(s));
   float* abuf = nullptr;            // act(z_k) planes: written by kernel P, read by kernel Q's 1x1 conv
   if (tc && s->n_layers > 1 && !(abuf = (float*)cv.take(act * sizeof(float))))
     return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
@@ -630,6 +634,8 @@ int bdn_fno_backward(const BdnFnoShape* s, const BdnFnoParams* p, const BdnLiftI
   if (!G1 || !GZ || !gz[0] || !gz[1] || !GY) return set_error(BDN_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
 
   const bool tc = use_tc_layer(s, pl);
+  struct FewGuard { int prev; FewGuard(bool few) : prev(pdl_few_images) { pdl_few_images = few; } ~FewGuard() { pdl_few_images = prev; } }
+      few_guard(use_mode_major(s));
   const float2* wt = use_mode_major(s) && !tc ? (const float2*)(xs_saved + (size_t)s->n_layers * ksp) : nullptr;
   const size_t wt1 = wt_floats1(s) / 2;
   int cur = 0;

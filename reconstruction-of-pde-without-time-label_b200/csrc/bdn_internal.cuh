@@ -247,7 +247,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-bool pdl_enabled();
+bool pdl_enabled();      // BDN_PDL: 0 off, 1 every launch, 2 every launch except those of few-image nets (pdl_few_images)
+extern thread_local int pdl_few_images;      // set by the FNO entry points while they launch a few-image net (the heads)
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

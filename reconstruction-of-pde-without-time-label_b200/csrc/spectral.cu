@@ -8,6 +8,8 @@
 // FNO2d.forward :226-232 / FNO1d.forward :108-114.
 #include "bdn_internal.cuh"
 
+#include <cstdlib>
+
 #include <cstdio>
 #include <mutex>
 #include <set>
@@ -322,6 +324,8 @@ struct CoreParams {
   const float* pre; const float* post;
   int ca, cb, co_layer, hp, hp8, m1, m2, K, F, Fp, TL;
   int tables_global;     // large hp x F: the DFT tables do not fit shared memory and are read through L1/L2
+  int wstage;            // core2d_kernel with TL = 1: the block's column of wt is staged in shared memory
+  int onetab;            // core2d_kernel: the inverse transform reads the h-major table too (t_fh is not staged)
 };
 
 // G = frequencies (phase 1) / spatial rows (phase 3) accumulated per work item.  Small G gives more
@@ -379,6 +383,69 @@ __device__ __forceinline__ float4 pair_pq(const float2 y1, const float2 y2) {
   return make_float4(y1.x + y2.x, y1.y + y2.y, y2.y - y1.y, y1.x - y2.x);
 }
 
+// The three inner loops of the middle stage, on running pointers (every stride is a run-time value: indexing by
+// h * pitch costs an IMAD + LEA per load, ncu source view) and inlined once per address space so that the shared
+// memory tables are read with LDS (a pointer that may be global or shared compiles to generic LD).
+template <int G>
+__device__ __forceinline__ void h_forward_freqs(const float2* __restrict__ x, int xpitch, const float2* __restrict__ t, int tpitch,
+                                                int hp, float (&ar)[G], float (&ai)[G], float (&br)[G], float (&bi)[G]) {
+#pragma unroll 4
+  for (int h = 0; h < hp; ++h) {
+    pacc_freqs<G>(*x, t, ar, ai, br, bi);
+    x += xpitch;
+    t += tpitch;
+  }
+}
+
+template <int G>
+__device__ __forceinline__ void h_inverse_rows(const float4* __restrict__ pq, int ppitch, const float2* __restrict__ t, int tpitch,
+                                               int F, float (&re)[G], float (&im)[G]) {
+#pragma unroll 4
+  for (int f = 0; f < F; ++f) {
+    pacc_rows<G>(*pq, t, re, im);
+    pq += ppitch;
+    t += tpitch;
+  }
+}
+
+// the same from the h-major table: row j of the item is t[j] (one 8-byte load per row instead of 16 bytes per row pair)
+template <int G>
+__device__ __forceinline__ void h_inverse_rows_hmajor(const float4* __restrict__ pq, int ppitch, const float2* const (&t)[G],
+                                                      int F, float (&re)[G], float (&im)[G]) {
+#pragma unroll 4
+  for (int f = 0; f < F; ++f) {
+    const float4 v = *pq;
+    pq += ppitch;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const float2 cs = t[j][f];
+      re[j] = fmaf(v.x, cs.x, fmaf(v.z, cs.y, re[j]));
+      im[j] = fmaf(v.y, cs.x, fmaf(v.w, cs.y, im[j]));
+    }
+  }
+}
+
+// y = sum_a x_a W[a][b] (fwd) or sum_a x_a conj(W[b][a]) (bwd): x at stride xstride, W at stride wstride (float2 units)
+template <bool BWD>
+__device__ __forceinline__ float2 mix_row(const float2* __restrict__ x, int xstride, const float2* __restrict__ w, int wstride,
+                                          int ca) {
+  float yr = 0.f, yi = 0.f;
+#pragma unroll 6
+  for (int a = 0; a < ca; ++a) {
+    const float2 xv = *x, wv = *w;
+    x += xstride;
+    w += wstride;
+    if (!BWD) {
+      yr = fmaf(xv.x, wv.x, fmaf(-xv.y, wv.y, yr));
+      yi = fmaf(xv.x, wv.y, fmaf(xv.y, wv.x, yi));
+    } else {
+      yr = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, yr));
+      yi = fmaf(xv.y, wv.x, fmaf(-xv.x, wv.y, yi));
+    }
+  }
+  return make_float2(yr, yi);
+}
+
 template <bool BWD, int G1, int G3>   // frequencies per phase-1 item, spatial rows per phase-3 item
 __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -389,46 +456,70 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
   float2* bufX = bufA + nA;
   float2* tab = bufX + K * Pa + ((K * Pa) & 1);
   const bool tg = p.tables_global != 0;
-  const float2* s_hf = tg ? p.t_hf : tab;                  // [hp][Fp], 16-byte aligned rows
-  const float2* s_fh = tg ? p.t_fh : tab + hp * p.Fp;      // [F][hp8]
+  float2* tab_hf = tab;                                    // [hp][Fp], 16-byte aligned rows
+  float2* tab_fh = tab + hp * p.Fp;                        // [F][hp8]  (not with onetab)
+  const int fh_n = p.onetab ? 0 : F * p.hp8;
+  float2* wcol = tab + (tg ? 0 : hp * p.Fp + fh_n);        // [K][ci][co]: this block's column of the mode-major weights
+  const int wcol_n = p.wstage ? K * p.ca * p.cb : 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wcol + wcol_n);   // [0] t_hf, [1] t_fh, [2] weights
   const int l0 = blockIdx.x * TL, b = blockIdx.y;
   const int tid = threadIdx.x, nt = blockDim.x;
 
-  // the two DFT tables live in shared memory for the block's lifetime (they are re-read by every
-  // item; from L1/L2 the inner loops were latency-bound: ncu long-scoreboard 20 cycles per issue).
-  // Both are contiguous in HBM: two bulk async copies, in flight while phase 0 stages the image.
-  uint64_t* tbar = reinterpret_cast<uint64_t*>(tab + (tg ? 0 : hp * p.Fp + F * p.hp8));
+  // The two DFT tables live in shared memory for the block's lifetime (they are re-read by every item; from L1/L2 the
+  // inner loops were latency-bound: ncu long-scoreboard 20 cycles per issue), and with one mode column per block so
+  // does the column's slice of the mode-major weights (the mix was a chain of dependent L2 reads).  Each is contiguous
+  // in HBM: three bulk async copies, each with its own barrier, in flight while phase 0 stages the image; a phase
+  // waits only for the operand it reads.
   pdl_launch_dependents();
-  if (tid == 0 && !tg) {
-    mbar_init(tbar, 1);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     mbar_init_fence();
-    const uint32_t b1 = (uint32_t)(hp * p.Fp) * 8u, b2 = (uint32_t)(F * p.hp8) * 8u;
-    mbar_expect_tx(tbar, b1 + b2);
-    bulk_g2s(tab, p.t_hf, b1, tbar);
-    bulk_g2s(tab + hp * p.Fp, p.t_fh, b2, tbar);
+    if (!tg) {
+      const uint32_t b1 = (uint32_t)(hp * p.Fp) * 8u, b2 = (uint32_t)(F * p.hp8) * 8u;
+      mbar_expect_tx(&bars[0], b1);
+      bulk_g2s(tab_hf, p.t_hf, b1, &bars[0]);
+      if (!p.onetab) {
+        mbar_expect_tx(&bars[1], b2);
+        bulk_g2s(tab_fh, p.t_fh, b2, &bars[1]);
+      }
+    }
   }
   pdl_wait();      // the tables above are constant plan data; everything below reads the previous kernel's output
-  // phase 0: stage the image's TL columns, all channels: bufA[h][a*TL + lt]
-  for (int idx = tid; idx < p.ca * hp * TL; idx += nt) {
-    const int lt = idx % TL, h = (idx / TL) % hp, a = idx / (TL * hp);
-    const int l = l0 + lt;
-    bufA[h * Pa + a * TL + lt] =
-        l < m2 ? __ldg(p.in + ((size_t)(b * p.ca + a) * hp + h) * m2 + l) : make_float2(0.f, 0.f);
+  if (tid == 0 && p.wstage) {     // (the mode-major weights are written by a kernel earlier in the step)
+    const uint32_t bw = (uint32_t)wcol_n * 8u;
+    mbar_expect_tx(&bars[2], bw);
+    bulk_g2s(wcol, p.wt + (size_t)l0 * wcol_n, bw, &bars[2]);
   }
-  __syncthreads();          // also publishes the mbarrier init to the waiting threads
-  if (!tg) mbar_wait(tbar, 0);
+  // phase 0: stage the image's TL columns, all channels: bufA[h][a*TL + lt]
+  if (TL == 1) {
+    const float inv_hp = 1.0f / (float)hp;
+    for (int idx = tid; idx < p.ca * hp; idx += nt) {
+      const int a = __float2int_rz(((float)idx + 0.5f) * inv_hp), h = idx - a * hp;      // exact for these ranges
+      bufA[h * Pa + a] = __ldg(p.in + ((size_t)(b * p.ca + a) * hp + h) * m2 + l0);
+    }
+  } else {
+    for (int idx = tid; idx < p.ca * hp * TL; idx += nt) {
+      const int lt = idx % TL, h = (idx / TL) % hp, a = idx / (TL * hp);
+      const int l = l0 + lt;
+      bufA[h * Pa + a * TL + lt] =
+          l < m2 ? __ldg(p.in + ((size_t)(b * p.ca + a) * hp + h) * m2 + l) : make_float2(0.f, 0.f);
+    }
+  }
+  __syncthreads();          // also publishes the mbarrier inits to the waiting threads
+  if (!tg) mbar_wait(&bars[0], 0);
 
   // phase 1: X[k][pa] = pre[l] * sum_h x[h][pa] * e^{-i phi_kh}, G1 frequencies (row pairs) per item
   constexpr int G = G1;
   const int nfg = (F + G - 1) / G;
   for (int idx = tid; idx < Pa * nfg; idx += nt) {
-    const int pa = idx % Pa, fg = idx / Pa;
+    const int fg = idx / Pa, pa = idx - fg * Pa;
     float ar[G], ai[G], br[G], bi[G];
 #pragma unroll
     for (int j = 0; j < G; ++j) ar[j] = ai[j] = br[j] = bi[j] = 0.f;
-    const float2* trow = s_hf + fg * G;
-#pragma unroll 4
-    for (int h = 0; h < hp; ++h) pacc_freqs<G>(bufA[h * Pa + pa], trow + (size_t)h * p.Fp, ar, ai, br, bi);
+    if (tg) h_forward_freqs<G>(bufA + pa, Pa, p.t_hf + fg * G, p.Fp, hp, ar, ai, br, bi);
+    else h_forward_freqs<G>(bufA + pa, Pa, tab_hf + fg * G, p.Fp, hp, ar, ai, br, bi);
     const int a = pa / TL, lt = pa - a * TL, l = l0 + lt;
     const float sc = l < m2 ? __ldg(p.pre + l) : 0.f;
     float2* so = (p.spec_out != nullptr && l < m2) ? p.spec_out + (size_t)(b * p.ca + a) * K * m2 + l : nullptr;
@@ -456,6 +547,8 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
     // few columns reads them with full sectors (the parameter layout has the mode index innermost: one
     // 8-byte element per 32-byte sector for a single column)
     const int ci = BWD ? p.cb : p.ca, co = p.co_layer;
+    const int wa = BWD ? 1 : co, wb = BWD ? co : 1;        // strides of the summed / the produced channel
+    if (p.wstage) mbar_wait(&bars[2], 0);
     for (int idx = tid; idx < F * Pb; idx += nt) {
       const int bc = idx % p.cb, f = (idx / p.cb) % F, lt = idx / (p.cb * F);
       const int l = l0 + lt;
@@ -465,79 +558,59 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
         for (int r = 0; r < 2; ++r) {
           if (r == 0 ? f >= p.m1 : f == 0) continue;
           const int k = r == 0 ? f : K - f;
-          const float2* wm = p.wt + ((size_t)l * K + k) * ci * co;
-          float yr = 0.f, yi = 0.f;
-#pragma unroll 4
-          for (int a = 0; a < p.ca; ++a) {
-            const float2 x = bufX[k * Pa + a * TL + lt];
-            if (!BWD) {
-              const float2 w = __ldg(wm + a * co + bc);
-              yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
-              yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
-            } else {
-              const float2 w = __ldg(wm + bc * co + a);
-              yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
-              yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
-            }
-          }
-          y[r] = make_float2(yr, yi);
+          if (p.wstage) y[r] = mix_row<BWD>(bufX + k * Pa + lt, TL, wcol + (size_t)k * ci * co + bc * wb, wa, p.ca);
+          else y[r] = mix_row<BWD>(bufX + k * Pa + lt, TL, p.wt + ((size_t)l * K + k) * ci * co + bc * wb, wa, p.ca);
         }
       }
       bufPQ[f * Pb + bc * TL + lt] = pair_pq(y[0], y[1]);
     }
   } else {
+    const size_t cstride = (size_t)p.m1 * m2;
+    const int wa = (int)((BWD ? 1 : p.co_layer) * cstride), wb = (int)((BWD ? p.co_layer : 1) * cstride);
     for (int idx = tid; idx < F * Pb; idx += nt) {
       const int lt = idx % TL, f = (idx / TL) % F, bc = idx / (TL * F);
       const int l = l0 + lt;
       float2 y[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       if (l < m2) {
-        const size_t cstride = (size_t)p.m1 * m2;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           if (r == 0 ? f >= p.m1 : f == 0) continue;
           const int k = r == 0 ? f : K - f;
           const float2* wsel = r == 0 ? p.w1 : p.w2;           // row k >= m1 is row k - m1 of weights2
           const size_t mode_off = (size_t)(r == 0 ? f : p.m1 - f) * m2 + l;
-          float yr = 0.f, yi = 0.f;
-#pragma unroll 4
-          for (int a = 0; a < p.ca; ++a) {
-            const float2 x = bufX[k * Pa + a * TL + lt];
-            if (!BWD) {
-              const float2 w = __ldg(wsel + (size_t)(a * p.co_layer + bc) * cstride + mode_off);
-              yr = fmaf(x.x, w.x, fmaf(-x.y, w.y, yr));
-              yi = fmaf(x.x, w.y, fmaf(x.y, w.x, yi));
-            } else {
-              const float2 w = __ldg(wsel + (size_t)(bc * p.co_layer + a) * cstride + mode_off);
-              yr = fmaf(x.x, w.x, fmaf(x.y, w.y, yr));
-              yi = fmaf(x.y, w.x, fmaf(-x.x, w.y, yi));
-            }
-          }
-          y[r] = make_float2(yr, yi);
+          y[r] = mix_row<BWD>(bufX + k * Pa + lt, TL, wsel + (size_t)bc * wb + mode_off, wa, p.ca);
         }
       }
       bufPQ[f * Pb + bc * TL + lt] = pair_pq(y[0], y[1]);
     }
   }
   __syncthreads();
+  if (!tg && !p.onetab) mbar_wait(&bars[1], 0);
 
   // phase 3: Z[h][pb] = post[l] * sum_k y[k][pb] * e^{+i phi_kh} = post[l] * sum_f P cos + Q sin, G3 rows per item
   const int nhg = (hp + G3 - 1) / G3;
   for (int idx = tid; idx < Pb * nhg; idx += nt) {
-    const int pb = idx % Pb, hg = idx / Pb;
+    const int hg = idx / Pb, pb = idx - hg * Pb;
     float re[G3], im[G3];
 #pragma unroll
     for (int j = 0; j < G3; ++j) re[j] = im[j] = 0.f;
-    const float2* trow = s_fh + hg * G3;
-#pragma unroll 4
-    for (int f = 0; f < F; ++f) pacc_rows<G3>(bufPQ[f * Pb + pb], trow + (size_t)f * p.hp8, re, im);
+    if (tg) {
+      h_inverse_rows<G3>(bufPQ + pb, Pb, p.t_fh + hg * G3, p.hp8, F, re, im);
+    } else if (p.onetab) {
+      const float2* rows[G3];
+#pragma unroll
+      for (int j = 0; j < G3; ++j) rows[j] = tab_hf + min(hg * G3 + j, hp - 1) * p.Fp;
+      h_inverse_rows_hmajor<G3>(bufPQ + pb, Pb, rows, F, re, im);
+    } else {
+      h_inverse_rows<G3>(bufPQ + pb, Pb, tab_fh + hg * G3, p.hp8, F, re, im);
+    }
     const int bc = pb / TL, lt = pb - bc * TL, l = l0 + lt;
     if (l >= m2) continue;
     const float sc = __ldg(p.post + l);
+    float2* dst = p.out + ((size_t)(b * p.cb + bc) * hp + hg * G3) * m2 + l;
 #pragma unroll
-    for (int j = 0; j < G3; ++j) {
-      const int h = hg * G3 + j;
-      if (h < hp) p.out[((size_t)(b * p.cb + bc) * hp + h) * m2 + l] = make_float2(re[j] * sc, im[j] * sc);
-    }
+    for (int j = 0; j < G3; ++j)
+      if (hg * G3 + j < hp) dst[(size_t)j * m2] = make_float2(re[j] * sc, im[j] * sc);
   }
 }
 
@@ -750,6 +823,7 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
     const bool aligned = (((size_t)p.ca * pl->hp * pl->m2 * 8) & 15) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
     if (images >= 148 && smem_s <= 110 * 1024 && aligned) {
       p.TL = pl->m2;
+      p.wstage = 0; p.onetab = 0;
       const int Pa_s = p.ca * pl->m2, Pb_s = p.cb * pl->m2;
       const int items1 = Pa_s * ceil_div(pl->F, 2), items3 = Pb_s * ceil_div(pl->hp, 8);
       int threads = items1 > items3 ? items1 : items3;
@@ -766,12 +840,13 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
   }
   // TL mode columns per block: the widest column tile that still leaves >= 2 blocks per SM and fits
   // shared memory (wide tiles read the W-transformed image with full 32-byte sectors)
+  static const int onetab_knob = [] { const char* e = getenv("BDN_CORE_ONETAB"); return e ? atoi(e) : 1; }();   // (tuning knob)
   auto smem_of = [&](int t) {
     const size_t a0 = (size_t)pl->hp * p.ca, a1 = 2 * (size_t)pl->F * p.cb;
     size_t nA = (a0 > a1 ? a0 : a1) * t;
     nA = (nA + 1) & ~(size_t)1;
     const size_t nX = (size_t)pl->K * p.ca * t;
-    return (nA + nX + (nX & 1) + (p.tables_global ? 0 : table_f2)) * sizeof(float2) + 16;
+    return (nA + nX + (nX & 1) + (p.tables_global ? 0 : table_f2)) * sizeof(float2) + 32;
   };
   int tl = 1;
   for (int parts = 1; parts <= pl->m2; ++parts) {
@@ -780,7 +855,16 @@ void launch_core2d(const Plan* pl, const float2* in, float2* out, float2* spec_o
     if ((long)images * ceil_div(pl->m2, cand) >= 2 * 148 || cand == 1) { tl = cand; break; }
   }
   p.TL = tl;
-  const size_t smem = smem_of(tl);
+  size_t smem = smem_of(tl);
+  // one mode column per block: its K*ci*co slice of the mode-major weights is contiguous -> staged by one bulk copy
+  const size_t wcol_bytes = (size_t)pl->K * p.ca * p.cb * sizeof(float2);
+  static const int wstage_knob = [] { const char* e = getenv("BDN_CORE_WSTAGE"); return e ? atoi(e) : 1; }();   // (tuning knob)
+  p.wstage = wstage_knob && wt != nullptr && tl == 1 && smem + wcol_bytes <= 200 * 1024 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0;
+  if (p.wstage) smem += wcol_bytes;
+  // with the weights staged a block holds > 113 KB: dropping the f-major table (the inverse transform then reads the
+  // h-major one) lets two blocks -- one of each output head, which run side by side -- share an SM
+  p.onetab = onetab_knob && p.wstage && !p.tables_global && smem > 113 * 1024;
+  if (p.onetab) smem -= (size_t)pl->F * pl->hp8 * sizeof(float2);
   dim3 grid(ceil_div(pl->m2, tl), images);
   // Work items: phase 1 has Pa * ceil(F / G1), phase 3 has Pb * ceil(hp / G3).  With few images (the
   // heads) every block should run as many threads as it has items (latency-bound); with many images
