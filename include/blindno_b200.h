@@ -257,6 +257,20 @@ int bdn_nio_tail_backward(const float* g, const float* basis, const float* wbar_
                           int32_t npix, int32_t grid_dim, int32_t width, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Training loss in one launch: criterion(model(inputs, grid), outputs) with criterion = torch.nn.MSELoss()
+ *   2d_FPE/train_fno.py:116,146-147 (1d_FPE/train_fno.py, 1d_GPE/train_nio_GPE.py alike); the model's
+ *   torch.cat of its head outputs (2d_FPE/NIOModules.py:577-581) is folded into the addressing.
+ * outs: host array of n_heads (<= 4) device pointers, head k = [npix, c]; target: [npix, n_heads * c];
+ * loss: one float (device); scratch: 65 * 4 bytes of device memory, zero before the FIRST call (every call leaves
+ * its counter word zero again, so CUDA-graph replays need no reset).  The sum is deterministic.
+ * backward: g_outs[k] = (2 / (npix * n_heads * c)) * grad_loss[0] * (outs[k] - target_k)   (OVERWRITTEN)
+ * ------------------------------------------------------------------------- */
+int bdn_mse_heads_forward(const float* const* outs, int32_t n_heads, int32_t c, int64_t npix, const float* target,
+                          float* loss, void* scratch, void* stream);
+int bdn_mse_heads_backward(const float* const* outs, int32_t n_heads, int32_t c, int64_t npix, const float* target,
+                           const float* grad_loss, float* const* g_outs, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Optimiser step fused over a flat fp32 buffer (torch.optim.Adam semantics,
  * 2d_FPE/train_fno.py:117; eps added after the bias-corrected sqrt, no
  * weight decay / amsgrad).  step = 1-based step count.

@@ -919,6 +919,36 @@ int bdn_nio_tail_backward(const float* g, const float* basis, const float* wbar_
   return check_cuda("bdn_nio_tail_backward");
 }
 
+int bdn_mse_heads_forward(const float* const* outs, int32_t n_heads, int32_t c, int64_t npix, const float* target,
+                          float* loss, void* scratch, void* stream) {
+  if (n_heads < 1 || n_heads > MSE_MAX_HEADS || c < 1 || npix < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
+  if (!outs || !target || !loss || !scratch) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  MseHeadsArgs a{};
+  for (int k = 0; k < n_heads; ++k) {
+    if (!outs[k]) return set_error(BDN_ERR_INVALID, "null head output");
+    a.out[k] = outs[k];
+  }
+  a.target = target; a.n_heads = n_heads; a.c = c; a.npix = npix;
+  // scratch: [0] the block counter (zero before the first launch; every launch leaves it zero), [1 .. 64] partial sums
+  launch_mse_heads(a, loss, (float*)scratch + 1, (unsigned int*)scratch, (cudaStream_t)stream);
+  return check_cuda("bdn_mse_heads_forward");
+}
+
+int bdn_mse_heads_backward(const float* const* outs, int32_t n_heads, int32_t c, int64_t npix, const float* target,
+                           const float* grad_loss, float* const* g_outs, void* stream) {
+  if (n_heads < 1 || n_heads > MSE_MAX_HEADS || c < 1 || npix < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
+  if (!outs || !target || !grad_loss || !g_outs) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  MseHeadsArgs a{};
+  for (int k = 0; k < n_heads; ++k) {
+    if (!outs[k] || !g_outs[k]) return set_error(BDN_ERR_INVALID, "null head tensor");
+    a.out[k] = outs[k];
+    a.g[k] = g_outs[k];
+  }
+  a.target = target; a.n_heads = n_heads; a.c = c; a.npix = npix;
+  launch_mse_heads_bwd(a, grad_loss, (cudaStream_t)stream);
+  return check_cuda("bdn_mse_heads_backward");
+}
+
 int bdn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float grad_scale, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq) return set_error(BDN_ERR_INVALID, "null pointer argument");

@@ -156,6 +156,15 @@ void launch_nio_tail(const float* w, const float* basis, const float* b0, const 
                      float* out, float* wbar, int n_bags, int L, int p, int npix, int gd, int width, cudaStream_t st);
 void launch_nio_tail_bwd(const float* g, const float* basis, const float* wbar, const float* w0, float* g_wbar, float* g_basis,
                          float* g_b0, float* g_w, int n_bags, int L, int p, int npix, int gd, int width, cudaStream_t st);
+// MSE over the concatenated head outputs without the concatenation (forward: deterministic two-level sum; backward)
+constexpr int MSE_MAX_HEADS = 4;
+struct MseHeadsArgs {
+  const float* out[MSE_MAX_HEADS]; float* g[MSE_MAX_HEADS]; const float* target;
+  int n_heads, c; long npix;
+};
+int mse_heads_blocks(long total);
+void launch_mse_heads(const MseHeadsArgs& a, float* loss, float* partial, unsigned int* counter, cudaStream_t st);
+void launch_mse_heads_bwd(const MseHeadsArgs& a, const float* grad_loss, cudaStream_t st);
 void launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,
                  float eps, int step, float grad_scale, cudaStream_t st);
 

@@ -935,6 +935,81 @@ void launch_nio_tail_bwd(const float* g, const float* basis, const float* wbar, 
 }
 
 // ===========================================================================
+// Training loss of the bag models in one launch: MSE between the concatenated head outputs and the target
+// (criterion = torch.nn.MSELoss() on model(inputs, grid), 2d_FPE/train_fno.py:116,146-147), without forming the
+// concatenation.  Deterministic: per-block partial sums, the last block to finish adds them in block order.
+//   outs[k]: [npix, c] (head k), target: [npix, n_heads * c], loss = mean((cat_k outs[k] - target)^2)
+// backward: g[k] = (2 / total) * grad_loss * (outs[k] - target_k)
+// ===========================================================================
+constexpr int MSE_BLOCKS = 64;
+
+__global__ void __launch_bounds__(512) mse_heads_fwd_kernel(const MseHeadsArgs a, float* __restrict__ loss,
+                                                            float* __restrict__ partial, unsigned int* counter) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[16];
+  __shared__ bool last;
+  const int C = a.n_heads * a.c;
+  const long total = (long)a.npix * C;
+  float s = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / C;
+    const int ch = (int)(i - pix * C), k = ch / a.c, j = ch - k * a.c;
+    const float d = __ldg(a.out[k] + pix * a.c + j) - __ldg(a.target + i);
+    s = fmaf(d, d, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float t = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) t += *reinterpret_cast<volatile float*>(partial + b);
+    *loss = t / (float)total;
+    *counter = 0u;            // ready for the next launch (graph replays included)
+  }
+}
+
+__global__ void mse_heads_bwd_kernel(const MseHeadsArgs a, const float* __restrict__ grad_loss) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C = a.n_heads * a.c;
+  const long total = (long)a.npix * C;
+  const float scale = 2.0f / (float)total * __ldg(grad_loss);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / C;
+    const int ch = (int)(i - pix * C), k = ch / a.c, j = ch - k * a.c;
+    a.g[k][pix * a.c + j] = scale * (__ldg(a.out[k] + pix * a.c + j) - __ldg(a.target + i));
+  }
+}
+
+int mse_heads_blocks(long total) {
+  const long b = (total + 4095) / 4096;
+  return (int)(b < 1 ? 1 : (b > MSE_BLOCKS ? MSE_BLOCKS : b));
+}
+
+void launch_mse_heads(const MseHeadsArgs& a, float* loss, float* partial, unsigned int* counter, cudaStream_t st) {
+  LaunchScope scope("mse_heads", st);
+  const long total = (long)a.npix * a.n_heads * a.c;
+  launch_k(mse_heads_fwd_kernel, dim3(mse_heads_blocks(total)), dim3(512), 0, st, a, loss, partial, counter);
+}
+
+void launch_mse_heads_bwd(const MseHeadsArgs& a, const float* grad_loss, cudaStream_t st) {
+  LaunchScope scope("mse_heads_bwd", st);
+  const long total = (long)a.npix * a.n_heads * a.c;
+  const long b = (total + 1023) / 1024;
+  launch_k(mse_heads_bwd_kernel, dim3((unsigned)(b > 148 * 4 ? 148 * 4 : b)), dim3(256), 0, st, a, grad_loss);
+}
+
+// ===========================================================================
 // Adam over a flat buffer (torch.optim.Adam defaults: no weight decay, no amsgrad)
 // ===========================================================================
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,

@@ -21,6 +21,8 @@ FLOP runs in libblindno_b200.so.  There is no CPU implementation: the CPU dispat
     bag_project_pool_lift(z, n_keep, fc1.., grid, fc0..)     projection of every snapshot, then the above
     deeponet_pool_contract_lift(w, basis, b0, grid, fc0..)   DeepOnetNoBiasOrg.forward + bag mean + lift
                                                              DeepONetModules.py:142-151, 1d_GPE/NIOModules.py:209-219
+    heads_mse(outs, target)                                  criterion(model(inputs, grid), outputs), MSELoss over the
+                                                             concatenated head outputs      2d_FPE/train_fno.py:116,146-147
 
     *_forward / *_backward ops are the non-differentiable primitives the formulas above are made of.
 """
@@ -35,7 +37,7 @@ import torch
 from . import _lib
 from ._lib import FnoParams, FnoShape, LiftInput, PREC_FP32, PREC_TF32, PREC_TF32X3, SpectralShape, check, pad_amount
 
-__all__ = ["FnoSpec", "set_precision", "stage_wfwd", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat",
+__all__ = ["FnoSpec", "set_precision", "stage_wfwd", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat", "heads_mse",
            "kernel_launches", "fno_lift_pad", "fno_layer", "fno_project", "OP_NAMES",
            "PREC_FP32", "PREC_TF32", "PREC_TF32X3"]
 
@@ -1023,6 +1025,85 @@ _define_composite("bag_project_pool_lift",
 _define_composite("deeponet_pool_contract_lift",
                   "(Tensor w, Tensor basis, Tensor b0, Tensor grid, Tensor fc0_w, Tensor fc0_b) -> Tensor",
                   _deeponet_pool_contract_lift)
+
+
+# ---------------------------------------------------------------------------------------------
+# training loss: MSE over the (never formed) concatenation of the head outputs
+# ---------------------------------------------------------------------------------------------
+_MSE_SCRATCH = {}
+
+
+def _mse_scratch(dev):
+    """65 floats per (device, stream): the forward kernel's block counter (left at zero by every launch) and partials."""
+    key = (dev.index, _stream())
+    buf = _MSE_SCRATCH.get(key)
+    if buf is None:
+        buf = _MSE_SCRATCH[key] = torch.zeros(65, dtype=torch.float32, device=dev)
+    return buf
+
+
+def _mse_dims(outs, target):
+    n = len(outs)
+    if not 1 <= n <= 4:
+        raise RuntimeError(f"heads_mse takes 1 to 4 head outputs, got {n}")
+    c = outs[0].shape[-1]
+    npix = outs[0].numel() // max(c, 1)
+    for o in outs:
+        if o.shape != outs[0].shape:
+            raise RuntimeError("heads_mse: head outputs must have one shape")
+    if tuple(target.shape) != tuple(outs[0].shape[:-1]) + (n * c,):
+        raise RuntimeError(f"heads_mse: target {tuple(target.shape)} does not match {n} heads of {tuple(outs[0].shape)}")
+    return n, c, npix
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _heads_mse_forward_cuda(outs, target):
+    _need_cuda(*outs, target)
+    oc, tc = [_f32c(o) for o in outs], _f32c(target)
+    n, c, npix = _mse_dims(oc, tc)
+    loss = torch.empty((), dtype=torch.float32, device=tc.device)
+    with torch.cuda.device(tc.device):
+        check(_lib.lib().bdn_mse_heads_forward(_ptr_array(oc), n, c, npix, _ptr(tc), _ptr(loss), _ptr(_mse_scratch(tc.device)),
+                                               _stream()), "bdn_mse_heads_forward")
+    return loss
+
+
+def _heads_mse_backward_cuda(outs, target, grad_loss):
+    _need_cuda(*outs, target, grad_loss)
+    oc, tc, gl = [_f32c(o) for o in outs], _f32c(target), _f32c(grad_loss)
+    n, c, npix = _mse_dims(oc, tc)
+    gs = [torch.empty_like(o) for o in oc]
+    with torch.cuda.device(tc.device):
+        check(_lib.lib().bdn_mse_heads_backward(_ptr_array(oc), n, c, npix, _ptr(tc), _ptr(gl), _ptr_array(gs), _stream()),
+              "bdn_mse_heads_backward")
+    return gs
+
+
+_define("heads_mse", "(Tensor[] outs, Tensor target) -> Tensor", _heads_mse_forward_cuda,
+        lambda outs, target: (_mse_dims(outs, target), target.new_empty(()))[1])
+_define("heads_mse_backward", "(Tensor[] outs, Tensor target, Tensor grad_loss) -> Tensor[]", _heads_mse_backward_cuda,
+        lambda outs, target, grad_loss: [torch.empty_like(o) for o in outs])
+
+
+def _mse_setup(ctx, inputs, output):
+    outs, target = inputs
+    ctx.save_for_backward(target, *outs)
+
+
+def _mse_bwd(ctx, g):
+    target, *outs = ctx.saved_tensors
+    return _OPS.heads_mse_backward(list(outs), target, g), None      # the target gets no gradient
+
+
+torch.library.register_autograd(f"{NS}::heads_mse", _mse_bwd, setup_context=_mse_setup, lib=_LIB)
+
+
+def heads_mse(outs, target):
+    """``F.mse_loss(torch.cat(outs, -1), target)`` in one kernel (and one for its backward); the sum is deterministic."""
+    return _OPS.heads_mse(list(outs), target)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -63,6 +63,9 @@ class FlatTrainer:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.loss_fn = loss_fn or nn.functional.mse_loss
+        # the default criterion (MSELoss on the concatenated head outputs, train_fno.py:116,146) runs as one kernel that
+        # reads the head outputs where they are (ops.heads_mse); a caller-supplied loss_fn sees the usual tensor
+        self.fused_mse = loss_fn is None and hasattr(model, "_heads_as_list")
         self.step_count = 0
         self.adam_fn = ops.adam_step_flat
         # CUDA-graph replay of the device work of a step (see step()): one graph per bag size
@@ -239,14 +242,23 @@ class FlatTrainer:
         for lo, hi in (spans if spans is not None else [(0, self.numel)]):
             self._adam(lo, hi, self.step_count)
 
+    def _loss(self, run_model, target):
+        if not (self.fused_mse and target.is_cuda):
+            return self.loss_fn(run_model(), target)
+        self.model._heads_as_list = True
+        try:
+            outs = run_model()
+        finally:
+            self.model._heads_as_list = False
+        return ops.heads_mse(outs, target) if isinstance(outs, (list, tuple)) else self.loss_fn(outs, target)
+
     # -- the step --------------------------------------------------------------------------
     def step(self, x: torch.Tensor, grid: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """zero_grad -> forward -> loss -> backward -> all-reduce -> Adam.  Returns the (device) loss."""
         if self.use_graphs and (x.is_cuda or x.is_pinned()) and self.flat_param.is_cuda and getattr(self.model, "accepts_idx", False):
             return self._graph_step(x, grid, target)
         self.zero_grad()
-        pred = self.model(x, grid)
-        loss = self.loss_fn(pred, target)
+        loss = self._loss(lambda: self.model(x, grid), target)
         loss.backward()
         self.reduce_gradients()
         self.optimizer_step()
@@ -288,9 +300,8 @@ class FlatTrainer:
         def body_a():
             self.flat_grad.zero_()
             self.model._expose_lifted = split
-            pred = self.model(ent["x"], ent["grid"], idx=ent["idx"]) if ent["idx"] is not None else \
-                self.model(ent["x"], ent["grid"])
-            loss = self.loss_fn(pred, ent["target"])
+            loss = self._loss(lambda: self.model(ent["x"], ent["grid"], idx=ent["idx"]) if ent["idx"] is not None else
+                              self.model(ent["x"], ent["grid"]), ent["target"])
             if not split:
                 loss.backward()
                 return loss.detach(), None, None

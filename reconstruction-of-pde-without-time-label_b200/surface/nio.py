@@ -50,6 +50,7 @@ def _side_streams(device, n):
 class _BagModel(nn.Module):
     head_names: tuple = ()
     accepts_idx = False     # forward(x, grid, idx=<int32 device tensor>): the caller drew the bag (CUDA-graph replay)
+    _heads_as_list = False  # the trainer's fused loss (ops.heads_mse) reads the head outputs without the torch.cat
 
     def _heads(self, lifted):
         """The output FNO heads read the same lifted bag mean and are independent of each other; with only
@@ -59,6 +60,8 @@ class _BagModel(nn.Module):
         names = self.head_names
         if len(names) == 1 or not lifted.is_cuda:
             outs = [getattr(self, name)(lifted) for name in names]
+            if self._heads_as_list:
+                return outs
             return outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
         main = torch.cuda.current_stream(lifted.device)
         side = _side_streams(lifted.device, len(names) - 1)
@@ -75,7 +78,7 @@ class _BagModel(nn.Module):
             if not capturing:          # (a graph's private pool keeps its tensors alive by itself)
                 lifted.record_stream(side[k - 1])
                 outs[k].record_stream(main)
-        return torch.cat(outs, dim=-1)
+        return outs if self._heads_as_list else torch.cat(outs, dim=-1)
 
 
 class _NioFnoMixin(_BagModel):

@@ -150,6 +150,17 @@ def test_pooled_tails_detach_fc0_on_meta():
     assert w.grad.shape == w.shape and basis.grad.shape == basis.shape and b0.grad is not None and fc0_w.grad is None
 
 
+def test_heads_mse_on_meta():
+    outs = [torch.randn(2, 8, 8, 1, device=META, requires_grad=True) for _ in range(2)]
+    target = torch.randn(2, 8, 8, 2, device=META)
+    loss = ops.heads_mse(outs, target)
+    assert loss.shape == ()
+    loss.backward()
+    assert all(o.grad is not None and o.grad.shape == o.shape for o in outs)
+    with pytest.raises(RuntimeError, match="target"):
+        ops.heads_mse(outs, torch.randn(2, 8, 8, 3, device=META))
+
+
 def test_grad_sink_suppresses_autograd_parameter_grads_on_meta():
     m = fno.FNO2d(3, 4, 1, 3, 1).to(META)
     params = m._params()

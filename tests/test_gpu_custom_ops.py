@@ -166,6 +166,26 @@ def test_pooled_tails_vs_oracle():
         assert rel_err(a.grad, r.grad) < 1e-4      # TF32-free cuBLAS GEMM vs fp64; cancelling sums over n*n points
 
 
+@pytest.mark.parametrize("n_heads,c,shape", [(2, 1, (4, 61, 61)), (1, 1, (4, 128)), (2, 2, (3, 7, 5)), (3, 1, (40, 80, 80))])
+def test_heads_mse_matches_mse_loss_on_the_concatenation(n_heads, c, shape):
+    """criterion(model(inputs, grid), outputs) with MSELoss (2d_FPE/train_fno.py:116,146-147) without the torch.cat:
+    loss and the gradient of every head output, against F.mse_loss in fp64; deterministic across repeated launches."""
+    g = torch.Generator().manual_seed(n_heads * 10 + c)
+    outs = [torch.randn(*shape, c, generator=g) for _ in range(n_heads)]
+    target = torch.randn(*shape, n_heads * c, generator=g)
+    dev = [o.to(DEV).requires_grad_(True) for o in outs]
+    loss = ops.heads_mse(dev, target.to(DEV))
+    (3.0 * loss).backward()
+    ref = [o.double().requires_grad_(True) for o in outs]
+    want = F.mse_loss(torch.cat(ref, dim=-1), target.double())
+    (3.0 * want).backward()
+    assert abs(loss.item() - want.item()) <= 2e-6 * abs(want.item())
+    for a, r in zip(dev, ref):
+        assert rel_err(a.grad, r.grad) < TOL
+    again = [ops.heads_mse([d.detach() for d in dev], target.to(DEV)).item() for _ in range(3)]
+    assert all(v == loss.item() for v in again)
+
+
 def test_opcheck_schema_fake_and_autograd_registration():
     x = torch.randn(2, 3, 8, 8, device=DEV, requires_grad=True)
     w = (torch.rand(3, 3, 2, 2, 2, device=DEV) / 9).requires_grad_(True)

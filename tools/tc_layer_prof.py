@@ -8,7 +8,9 @@ from blindno_b200 import ops  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "snap"
 prec = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-images, c, hp, wp, m1, m2 = (300, 4, 76, 76, 12, 12) if which == "snap" else (4, 12, 76, 76, 32, 32)
+SHAPES = {"snap": (300, 4, 76, 76, 12, 12), "snap32": (2400, 4, 76, 76, 12, 12), "heads": (4, 12, 76, 76, 32, 32),
+          "heads32": (32, 12, 76, 76, 32, 32)}
+images, c, hp, wp, m1, m2 = SHAPES[which]
 g = torch.Generator().manual_seed(0)
 z = torch.randn(images, c, hp, wp, generator=g).cuda().requires_grad_(True)
 w1 = (torch.rand(c, c, m1, m2, 2, generator=g) / (c * c)).cuda().requires_grad_(True)
