@@ -261,12 +261,14 @@ int bdn_nio_tail_backward(const float* g, const float* basis, const float* wbar_
  *   2d_FPE/train_fno.py:116,146-147 (1d_FPE/train_fno.py, 1d_GPE/train_nio_GPE.py alike); the model's
  *   torch.cat of its head outputs (2d_FPE/NIOModules.py:577-581) is folded into the addressing.
  * outs: host array of n_heads (<= 4) device pointers, head k = [npix, c]; target: [npix, n_heads * c];
- * loss: one float (device); scratch: 65 * 4 bytes of device memory, zero before the FIRST call (every call leaves
+ * loss: one float (device); g_outs: null, or n_heads device pointers that receive d loss / d outs[k] =
+ * (2 / (npix * n_heads * c)) * (outs[k] - target_k) in the same launch (what backward gives for grad_loss = 1: the
+ * train step's case); scratch: 65 * 4 bytes of device memory, zero before the FIRST call (every call leaves
  * its counter word zero again, so CUDA-graph replays need no reset).  The sum is deterministic.
  * backward: g_outs[k] = (2 / (npix * n_heads * c)) * grad_loss[0] * (outs[k] - target_k)   (OVERWRITTEN)
  * ------------------------------------------------------------------------- */
 int bdn_mse_heads_forward(const float* const* outs, int32_t n_heads, int32_t c, int64_t npix, const float* target,
-                          float* loss, void* scratch, void* stream);
+                          float* loss, float* const* g_outs, void* scratch, void* stream);
 int bdn_mse_heads_backward(const float* const* outs, int32_t n_heads, int32_t c, int64_t npix, const float* target,
                            const float* grad_loss, float* const* g_outs, void* stream);
 

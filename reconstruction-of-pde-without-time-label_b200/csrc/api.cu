@@ -920,13 +920,15 @@ int bdn_nio_tail_backward(const float* g, const float* basis, const float* wbar_
 }
 
 int bdn_mse_heads_forward(const float* const* outs, int32_t n_heads, int32_t c, int64_t npix, const float* target,
-                          float* loss, void* scratch, void* stream) {
+                          float* loss, float* const* g_outs, void* scratch, void* stream) {
   if (n_heads < 1 || n_heads > MSE_MAX_HEADS || c < 1 || npix < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
+  if (npix * n_heads * c >= (1LL << 31)) return set_error(BDN_ERR_UNSUPPORTED, "more than 2^31 output elements");
   if (!outs || !target || !loss || !scratch) return set_error(BDN_ERR_INVALID, "null pointer argument");
   MseHeadsArgs a{};
   for (int k = 0; k < n_heads; ++k) {
-    if (!outs[k]) return set_error(BDN_ERR_INVALID, "null head output");
+    if (!outs[k] || (g_outs && !g_outs[k])) return set_error(BDN_ERR_INVALID, "null head tensor");
     a.out[k] = outs[k];
+    a.g[k] = g_outs ? g_outs[k] : nullptr;
   }
   a.target = target; a.n_heads = n_heads; a.c = c; a.npix = npix;
   // scratch: [0] the block counter (zero before the first launch; every launch leaves it zero), [1 .. 64] partial sums
@@ -937,6 +939,7 @@ int bdn_mse_heads_forward(const float* const* outs, int32_t n_heads, int32_t c, 
 int bdn_mse_heads_backward(const float* const* outs, int32_t n_heads, int32_t c, int64_t npix, const float* target,
                            const float* grad_loss, float* const* g_outs, void* stream) {
   if (n_heads < 1 || n_heads > MSE_MAX_HEADS || c < 1 || npix < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
+  if (npix * n_heads * c >= (1LL << 31)) return set_error(BDN_ERR_UNSUPPORTED, "more than 2^31 output elements");
   if (!outs || !target || !grad_loss || !g_outs) return set_error(BDN_ERR_INVALID, "null pointer argument");
   MseHeadsArgs a{};
   for (int k = 0; k < n_heads; ++k) {

@@ -740,7 +740,7 @@ static void launch_project_bwd_t(const ProjArgs& a, const float* g_out, int pool
                                  float* g_w1, float* g_b1, float* g_w2, float* g_b2, long total, cudaStream_t st) {
   constexpr int TILE = PROJ_THREADS / JS * PP;
   const long ntiles = (total + TILE - 1) / TILE;
-  static const long cap8 = [] { const char* e = getenv("BDN_PROJ_BWD_CAP8"); return e ? atol(e) : 148L * 4; }();   // (tuning knob)
+  static const long cap8 = [] { const char* e = getenv("BDN_PROJ_BWD_CAP8"); return e ? atol(e) : 148L * 2; }();   // (tuning knob; r2k: 4 blocks per SM 88.5, 2 per SM 78.8, 1 per SM 87.4 us per step)
   const long cap = JS == 1 ? 148L * 2 : cap8;
   const long rounds = (ntiles + cap - 1) / cap;
   const int grid = (int)((ntiles + rounds - 1) / rounds);      // balanced: every block runs `rounds` tiles
@@ -943,20 +943,25 @@ void launch_nio_tail_bwd(const float* g, const float* basis, const float* wbar, 
 // ===========================================================================
 constexpr int MSE_BLOCKS = 64;
 
+// (32-bit index arithmetic: the entry point bounds the element count)
 __global__ void __launch_bounds__(512) mse_heads_fwd_kernel(const MseHeadsArgs a, float* __restrict__ loss,
                                                             float* __restrict__ partial, unsigned int* counter) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[16];
   __shared__ bool last;
-  const int C = a.n_heads * a.c;
-  const long total = (long)a.npix * C;
+  const int C = a.n_heads * a.c, c = a.c;
+  const int total = (int)a.npix * C;
+  const bool with_g = a.g[0] != nullptr;          // also write d loss / d outs for grad_loss = 1 (the train step's case)
+  const float gscale = 2.0f / (float)total;
   float s = 0.f;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long pix = i / C;
-    const int ch = (int)(i - pix * C), k = ch / a.c, j = ch - k * a.c;
-    const float d = __ldg(a.out[k] + pix * a.c + j) - __ldg(a.target + i);
+  const int stride = gridDim.x * blockDim.x;
+#pragma unroll 4
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int pix = i / C, ch = i - pix * C, k = ch / c, j = ch - k * c;
+    const float d = __ldg(a.out[k] + pix * c + j) - __ldg(a.target + i);
     s = fmaf(d, d, s);
+    if (with_g) a.g[k][pix * c + j] = gscale * d;
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -964,35 +969,42 @@ __global__ void __launch_bounds__(512) mse_heads_fwd_kernel(const MseHeadsArgs a
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    partial[blockIdx.x] = t;
-    __threadfence();
-    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    if (gridDim.x == 1) {
+      *loss = t / (float)total;
+      last = false;
+    } else {
+      partial[blockIdx.x] = t;
+      __threadfence();
+      last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last && threadIdx.x < 32) {
     __threadfence();
-    float t = 0.f;
-    for (int b = 0; b < (int)gridDim.x; ++b) t += *reinterpret_cast<volatile float*>(partial + b);
-    *loss = t / (float)total;
-    *counter = 0u;            // ready for the next launch (graph replays included)
+    float t = 0.f;                                 // fixed order: lane l adds partials l, l + 32, ...; then the warp tree
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) t += *reinterpret_cast<volatile float*>(partial + b);
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      *loss = t / (float)total;
+      *counter = 0u;            // ready for the next launch (graph replays included)
+    }
   }
 }
 
 __global__ void mse_heads_bwd_kernel(const MseHeadsArgs a, const float* __restrict__ grad_loss) {
   pdl_launch_dependents();
   pdl_wait();
-  const int C = a.n_heads * a.c;
-  const long total = (long)a.npix * C;
+  const int C = a.n_heads * a.c, c = a.c;
+  const int total = (int)a.npix * C;
   const float scale = 2.0f / (float)total * __ldg(grad_loss);
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long pix = i / C;
-    const int ch = (int)(i - pix * C), k = ch / a.c, j = ch - k * a.c;
-    a.g[k][pix * a.c + j] = scale * (__ldg(a.out[k] + pix * a.c + j) - __ldg(a.target + i));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int pix = i / C, ch = i - pix * C, k = ch / c, j = ch - k * c;
+    a.g[k][pix * c + j] = scale * (__ldg(a.out[k] + pix * c + j) - __ldg(a.target + i));
   }
 }
 
 int mse_heads_blocks(long total) {
-  const long b = (total + 4095) / 4096;
+  const long b = (total + 8191) / 8192;            // 16 elements per thread; one block (no second level) up to 8192
   return (int)(b < 1 ? 1 : (b > MSE_BLOCKS ? MSE_BLOCKS : b));
 }
 

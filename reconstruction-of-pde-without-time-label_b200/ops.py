@@ -37,7 +37,7 @@ import torch
 from . import _lib
 from ._lib import FnoParams, FnoShape, LiftInput, PREC_FP32, PREC_TF32, PREC_TF32X3, SpectralShape, check, pad_amount
 
-__all__ = ["FnoSpec", "set_precision", "stage_wfwd", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat", "heads_mse",
+__all__ = ["FnoSpec", "set_precision", "stage_wfwd", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat", "heads_mse", "heads_mse_grads",
            "kernel_launches", "fno_lift_pad", "fno_layer", "fno_project", "OP_NAMES",
            "PREC_FP32", "PREC_TF32", "PREC_TF32X3"]
 
@@ -1060,15 +1060,25 @@ def _ptr_array(tensors):
     return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
-def _heads_mse_forward_cuda(outs, target):
+def _heads_mse_launch(outs, target, with_grads):
     _need_cuda(*outs, target)
     oc, tc = [_f32c(o) for o in outs], _f32c(target)
     n, c, npix = _mse_dims(oc, tc)
     loss = torch.empty((), dtype=torch.float32, device=tc.device)
+    gs = [torch.empty_like(o) for o in oc] if with_grads else []
     with torch.cuda.device(tc.device):
-        check(_lib.lib().bdn_mse_heads_forward(_ptr_array(oc), n, c, npix, _ptr(tc), _ptr(loss), _ptr(_mse_scratch(tc.device)),
+        check(_lib.lib().bdn_mse_heads_forward(_ptr_array(oc), n, c, npix, _ptr(tc), _ptr(loss),
+                                               _ptr_array(gs) if with_grads else None, _ptr(_mse_scratch(tc.device)),
                                                _stream()), "bdn_mse_heads_forward")
-    return loss
+    return loss, gs
+
+
+def _heads_mse_forward_cuda(outs, target):
+    return _heads_mse_launch(outs, target, False)[0]
+
+
+def _heads_mse_grads_cuda(outs, target):
+    return _heads_mse_launch(outs, target, True)
 
 
 def _heads_mse_backward_cuda(outs, target, grad_loss):
@@ -1084,6 +1094,8 @@ def _heads_mse_backward_cuda(outs, target, grad_loss):
 
 _define("heads_mse", "(Tensor[] outs, Tensor target) -> Tensor", _heads_mse_forward_cuda,
         lambda outs, target: (_mse_dims(outs, target), target.new_empty(()))[1])
+_define("heads_mse_grads", "(Tensor[] outs, Tensor target) -> (Tensor, Tensor[])", _heads_mse_grads_cuda,
+        lambda outs, target: ((_mse_dims(outs, target), target.new_empty(()))[1], [torch.empty_like(o) for o in outs]))
 _define("heads_mse_backward", "(Tensor[] outs, Tensor target, Tensor grad_loss) -> Tensor[]", _heads_mse_backward_cuda,
         lambda outs, target, grad_loss: [torch.empty_like(o) for o in outs])
 
@@ -1099,6 +1111,13 @@ def _mse_bwd(ctx, g):
 
 
 torch.library.register_autograd(f"{NS}::heads_mse", _mse_bwd, setup_context=_mse_setup, lib=_LIB)
+
+
+def heads_mse_grads(outs, target):
+    """(loss, [d loss / d out_k]) of ``F.mse_loss(torch.cat(outs, -1), target)`` in ONE kernel: what a train step needs
+    (its backward starts from grad_loss = 1); not differentiable -- feed the gradients to ``torch.autograd.backward``."""
+    loss, gs = _OPS.heads_mse_grads([o.detach() for o in outs], target)
+    return loss, list(gs)
 
 
 def heads_mse(outs, target):

@@ -243,14 +243,22 @@ class FlatTrainer:
             self._adam(lo, hi, self.step_count)
 
     def _loss(self, run_model, target):
-        if not (self.fused_mse and target.is_cuda):
-            return self.loss_fn(run_model(), target)
-        self.model._heads_as_list = True
-        try:
-            outs = run_model()
-        finally:
-            self.model._heads_as_list = False
-        return ops.heads_mse(outs, target) if isinstance(outs, (list, tuple)) else self.loss_fn(outs, target)
+        """Forward + criterion.  Returns (loss, roots, root_grads): backward starts from ``roots`` with ``root_grads``.
+        The default criterion on CUDA runs as one kernel that also produces d loss / d (head outputs)
+        (ops.heads_mse_grads): the autograd graph then starts at the head outputs, there is no loss node."""
+        if self.fused_mse and target.is_cuda:
+            self.model._heads_as_list = True
+            try:
+                outs = run_model()
+            finally:
+                self.model._heads_as_list = False
+            if isinstance(outs, (list, tuple)):
+                loss, grads = ops.heads_mse_grads(outs, target)
+                return loss, list(outs), grads
+            loss = self.loss_fn(outs, target)
+        else:
+            loss = self.loss_fn(run_model(), target)
+        return loss, [loss], [torch.ones_like(loss)]
 
     # -- the step --------------------------------------------------------------------------
     def step(self, x: torch.Tensor, grid: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
@@ -258,8 +266,8 @@ class FlatTrainer:
         if self.use_graphs and (x.is_cuda or x.is_pinned()) and self.flat_param.is_cuda and getattr(self.model, "accepts_idx", False):
             return self._graph_step(x, grid, target)
         self.zero_grad()
-        loss = self._loss(lambda: self.model(x, grid), target)
-        loss.backward()
+        loss, roots, root_grads = self._loss(lambda: self.model(x, grid), target)
+        torch.autograd.backward(roots, root_grads)
         self.reduce_gradients()
         self.optimizer_step()
         return loss.detach()
@@ -300,14 +308,16 @@ class FlatTrainer:
         def body_a():
             self.flat_grad.zero_()
             self.model._expose_lifted = split
-            loss = self._loss(lambda: self.model(ent["x"], ent["grid"], idx=ent["idx"]) if ent["idx"] is not None else
-                              self.model(ent["x"], ent["grid"]), ent["target"])
+            loss, roots, root_grads = self._loss(
+                lambda: self.model(ent["x"], ent["grid"], idx=ent["idx"]) if ent["idx"] is not None else
+                self.model(ent["x"], ent["grid"]), ent["target"])
             if not split:
-                loss.backward()
+                torch.autograd.backward(roots, root_grads)
                 return loss.detach(), None, None
             lifted = self.model._lifted
             self.model._lifted = None
-            (g_lifted,) = torch.autograd.grad(loss, [lifted])     # runs the heads' backward (gradients -> flat buffer)
+            # runs the heads' backward (gradients -> flat buffer)
+            (g_lifted,) = torch.autograd.grad(roots, [lifted], grad_outputs=root_grads)
             return loss.detach(), lifted, g_lifted
 
         def body_b(lifted, g_lifted):

@@ -184,6 +184,11 @@ def test_heads_mse_matches_mse_loss_on_the_concatenation(n_heads, c, shape):
         assert rel_err(a.grad, r.grad) < TOL
     again = [ops.heads_mse([d.detach() for d in dev], target.to(DEV)).item() for _ in range(3)]
     assert all(v == loss.item() for v in again)
+    # the train step's form: loss and d loss / d outs (grad_loss = 1) from one launch
+    loss1, grads1 = ops.heads_mse_grads(dev, target.to(DEV))
+    assert loss1.item() == loss.item()
+    for gk, r in zip(grads1, ref):
+        assert rel_err(gk, r.grad / 3.0) < TOL
 
 
 def test_opcheck_schema_fake_and_autograd_registration():
