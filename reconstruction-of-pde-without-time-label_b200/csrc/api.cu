@@ -137,6 +137,15 @@ const Plan* get_plan(int ndim, int hp, int wp, int m1, int m2) {
       t_sin[(size_t)l * pl->wp4 + w] = s;
     }
   pl->t_wl = upload(t_wl);
+  pl->wl_nh = wp / 2 + 1;
+  pl->wl_nh4 = round_up(pl->wl_nh, 4);
+  pl->wl_m2p = round_up(m2, 4);
+  {
+    std::vector<float2> half((size_t)pl->wl_nh4 * pl->wl_m2p, make_float2(0.f, 0.f));
+    for (int w = 0; w < pl->wl_nh; ++w)
+      for (int l = 0; l < m2; ++l) half[(size_t)w * pl->wl_m2p + l] = t_wl[(size_t)w * m2 + l];
+    pl->t_wl_half = upload(half);      // optional: without it the unfolded kernel runs
+  }
   pl->t_lw_cos = upload(t_cos);
   pl->t_lw_sin = upload(t_sin);
 

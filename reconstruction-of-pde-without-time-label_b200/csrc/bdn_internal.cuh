@@ -20,6 +20,8 @@ struct Plan {
   int hp8;      // hp rounded up to 8 (table row pitch of t_fh)
   int wp4;      // wp rounded up to 4 (row pitch of t_lw_cos / t_lw_sin)
   float2* t_wl;      // [wp][m2]   (cos theta, sin theta)      forward W transform
+  float2* t_wl_half; // [wl_nh4][wl_m2p] the same for w = 0..wp/2 only (rows / modes zero padded to multiples of 4): the
+  int wl_nh, wl_nh4, wl_m2p;   // folded W-forward kernel pairs x[w] with x[wp - w], which share cos and differ in the sign of sin
   float* t_lw_cos;   // [m2][wp4]  cos theta                   inverse W transform
   float* t_lw_sin;   // [m2][wp4]  sin theta
   float2* t_hf;      // [hp][Fp]   (cos phi, sin phi), phi = 2*pi*f*h/hp     forward H transform (h-major)
@@ -162,7 +164,7 @@ struct MseHeadsArgs {
   const float* out[MSE_MAX_HEADS]; float* g[MSE_MAX_HEADS]; const float* target;
   int n_heads, c; long npix;
 };
-int mse_heads_blocks(long total);
+int mse_heads_blocks(long npix);
 void launch_mse_heads(const MseHeadsArgs& a, float* loss, float* partial, unsigned int* counter, cudaStream_t st);
 void launch_mse_heads_bwd(const MseHeadsArgs& a, const float* grad_loss, cudaStream_t st);
 void launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,

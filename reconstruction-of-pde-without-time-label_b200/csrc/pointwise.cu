@@ -943,39 +943,59 @@ void launch_nio_tail_bwd(const float* g, const float* basis, const float* wbar, 
 // ===========================================================================
 constexpr int MSE_BLOCKS = 64;
 
-// (32-bit index arithmetic: the entry point bounds the element count)
-__global__ void __launch_bounds__(512) mse_heads_fwd_kernel(const MseHeadsArgs a, float* __restrict__ loss,
-                                                            float* __restrict__ partial, unsigned int* counter) {
+// Thread = pixel, static loops over the heads (constant indices into the pointer arrays of the argument struct: a
+// run-time head index would copy the struct to local memory) -- no index divisions.  32-bit arithmetic: the entry
+// point bounds the element count.
+template <bool WITH_G>
+__device__ __forceinline__ float mse_pixel(const MseHeadsArgs& a, int pix, int c, int C, float gscale) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MSE_MAX_HEADS; ++k) {
+    if (k < a.n_heads) {
+      for (int j = 0; j < c; ++j) {
+        const float d = __ldg(a.out[k] + pix * c + j) - __ldg(a.target + pix * C + k * c + j);
+        s = fmaf(d, d, s);
+        if (WITH_G) a.g[k][pix * c + j] = gscale * d;
+      }
+    }
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(1024) mse_heads_fwd_kernel(const MseHeadsArgs a, float* __restrict__ loss,
+                                                             float* __restrict__ partial, unsigned int* counter) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float red[16];
+  __shared__ float red[32];
   __shared__ bool last;
-  const int C = a.n_heads * a.c, c = a.c;
-  const int total = (int)a.npix * C;
+  const int C = a.n_heads * a.c, c = a.c, npix = (int)a.npix;
+  const float total = (float)npix * (float)C;
   const bool with_g = a.g[0] != nullptr;          // also write d loss / d outs for grad_loss = 1 (the train step's case)
-  const float gscale = 2.0f / (float)total;
+  const float gscale = 2.0f / total;
   float s = 0.f;
   const int stride = gridDim.x * blockDim.x;
+  if (with_g) {
 #pragma unroll 4
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int pix = i / C, ch = i - pix * C, k = ch / c, j = ch - k * c;
-    const float d = __ldg(a.out[k] + pix * c + j) - __ldg(a.target + i);
-    s = fmaf(d, d, s);
-    if (with_g) a.g[k][pix * c + j] = gscale * d;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += stride) s += mse_pixel<true>(a, pix, c, C, gscale);
+  } else {
+#pragma unroll 4
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += stride) s += mse_pixel<false>(a, pix, c, C, gscale);
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    if (gridDim.x == 1) {
-      *loss = t / (float)total;
-      last = false;
-    } else {
-      partial[blockIdx.x] = t;
-      __threadfence();
-      last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      if (gridDim.x == 1) {
+        *loss = t / total;
+        last = false;
+      } else {
+        partial[blockIdx.x] = t;
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+      }
     }
   }
   __syncthreads();
@@ -985,7 +1005,7 @@ __global__ void __launch_bounds__(512) mse_heads_fwd_kernel(const MseHeadsArgs a
     for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) t += *reinterpret_cast<volatile float*>(partial + b);
     t = warp_sum(t);
     if (threadIdx.x == 0) {
-      *loss = t / (float)total;
+      *loss = t / total;
       *counter = 0u;            // ready for the next launch (graph replays included)
     }
   }
@@ -994,30 +1014,31 @@ __global__ void __launch_bounds__(512) mse_heads_fwd_kernel(const MseHeadsArgs a
 __global__ void mse_heads_bwd_kernel(const MseHeadsArgs a, const float* __restrict__ grad_loss) {
   pdl_launch_dependents();
   pdl_wait();
-  const int C = a.n_heads * a.c, c = a.c;
-  const int total = (int)a.npix * C;
-  const float scale = 2.0f / (float)total * __ldg(grad_loss);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int pix = i / C, ch = i - pix * C, k = ch / c, j = ch - k * c;
-    a.g[k][pix * c + j] = scale * (__ldg(a.out[k] + pix * c + j) - __ldg(a.target + i));
+  const int C = a.n_heads * a.c, c = a.c, npix = (int)a.npix;
+  const float scale = 2.0f / ((float)npix * (float)C) * __ldg(grad_loss);
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < MSE_MAX_HEADS; ++k)
+      if (k < a.n_heads)
+        for (int j = 0; j < c; ++j)
+          a.g[k][pix * c + j] = scale * (__ldg(a.out[k] + pix * c + j) - __ldg(a.target + pix * C + k * c + j));
   }
 }
 
-int mse_heads_blocks(long total) {
-  const long b = (total + 8191) / 8192;            // 16 elements per thread; one block (no second level) up to 8192
-  return (int)(b < 1 ? 1 : (b > MSE_BLOCKS ? MSE_BLOCKS : b));
+int mse_heads_blocks(long npix) {
+  if (npix <= 32768) return 1;                     // one block: no second level, no atomics
+  const long b = (npix + 8191) / 8192;
+  return (int)(b > MSE_BLOCKS ? MSE_BLOCKS : b);
 }
 
 void launch_mse_heads(const MseHeadsArgs& a, float* loss, float* partial, unsigned int* counter, cudaStream_t st) {
   LaunchScope scope("mse_heads", st);
-  const long total = (long)a.npix * a.n_heads * a.c;
-  launch_k(mse_heads_fwd_kernel, dim3(mse_heads_blocks(total)), dim3(512), 0, st, a, loss, partial, counter);
+  launch_k(mse_heads_fwd_kernel, dim3(mse_heads_blocks(a.npix)), dim3(1024), 0, st, a, loss, partial, counter);
 }
 
 void launch_mse_heads_bwd(const MseHeadsArgs& a, const float* grad_loss, cudaStream_t st) {
   LaunchScope scope("mse_heads_bwd", st);
-  const long total = (long)a.npix * a.n_heads * a.c;
-  const long b = (total + 1023) / 1024;
+  const long b = (a.npix + 255) / 256;
   launch_k(mse_heads_bwd_kernel, dim3((unsigned)(b > 148 * 4 ? 148 * 4 : b)), dim3(256), 0, st, a, grad_loss);
 }
 

@@ -250,6 +250,133 @@ __global__ void __launch_bounds__(256) wfwd_pipe_kernel(const WfwdParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// W-forward, folded: cos(theta_{l, wp-w}) = cos(theta_{l, w}) and sin(theta_{l, wp-w}) = -sin(theta_{l, w}), so with
+//   e[w] = x[w] + x[wp-w],  o[w] = x[w] - x[wp-w]     (w = 1 .. ceil(wp/2)-1;  e = x, o = 0 at w = 0 and w = wp/2)
+// the pruned DFT is  Re X[l] = sum_{w <= wp/2} e[w] cos,  Im X[l] = -sum o[w] sin: half the multiply-adds and half the
+// table.  Same thread mapping as wfwd_pipe_kernel (warp = (row group, 4 modes), lane = RT rows, 128-bit row-strided
+// shared loads).  The raw tile lands by one bulk copy; a fold pass (which also applies the GELU of layers > 0) writes
+// the (e | o) tile; the raw buffer is then free, so the next tile's copy runs under this tile's multiply-adds.
+// ---------------------------------------------------------------------------
+struct WfoldParams {
+  const float* x; float2* out; const float2* t_half;
+  int rows, wp, m2, act, nh, nh4, fpitch, nrg, nmg, m2p, ntiles;
+};
+
+template <int RT>
+__global__ void __launch_bounds__(256) wfwd_fold_kernel(const WfoldParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int BR = 32 * RT * p.nrg;
+  const int wp = p.wp, m2 = p.m2, m2p = p.m2p, nh = p.nh, nh4 = p.nh4, fpitch = p.fpitch;
+  float* raw = smem;                                          // [BR][wp]
+  float* F = raw + BR * wp;                                   // [BR][fpitch]: e at 0 .. nh4-1, o at nh4 .. 2*nh4-1
+  float2* ts = reinterpret_cast<float2*>(F + BR * fpitch);    // [nh4][m2p]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ts + (size_t)nh4 * m2p);   // [0] raw tile, [1] table
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+
+  pdl_launch_dependents();
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init_fence();
+    const uint32_t tb = (uint32_t)(nh4 * m2p) * 8u;           // constant plan data: staged before the dependency wait
+    mbar_expect_tx(&bars[1], tb);
+    bulk_g2s(ts, p.t_half, tb, &bars[1]);
+  }
+  __syncthreads();
+  pdl_wait();
+  auto issue = [&](int tile) {   // thread 0
+    const int row0 = tile * BR;
+    const uint32_t bytes = (uint32_t)min(BR, p.rows - row0) * (uint32_t)wp * 4u;
+    fence_proxy_async();
+    mbar_expect_tx(&bars[0], bytes);
+    bulk_g2s(raw, p.x + (size_t)row0 * wp, bytes, &bars[0]);
+  };
+  if (tid == 0 && (int)blockIdx.x < p.ntiles) issue(blockIdx.x);
+  mbar_wait(&bars[1], 0);
+
+  const int rg = warp % p.nrg, mg0 = warp / p.nrg, mgstep = (nt >> 5) / p.nrg;
+  const float inv_nh4 = 1.0f / (float)nh4;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    mbar_wait(&bars[0], it & 1);
+    const int row0 = tile * BR, nrows = min(BR, p.rows - row0);
+    for (int idx = tid; idx < BR * nh4; idx += nt) {
+      const int r = __float2int_rz(((float)idx + 0.5f) * inv_nh4), j = idx - r * nh4;     // exact for these ranges
+      float e = 0.f, o = 0.f;
+      if (r < nrows && j < nh) {
+        float a = raw[r * wp + j];
+        if (p.act) a = gelu_fast(a);
+        e = a;
+        const int jm = wp - j;
+        if (j > 0 && jm > j) {
+          float b = raw[r * wp + jm];
+          if (p.act) b = gelu_fast(b);
+          e = a + b;
+          o = a - b;
+        }
+      }
+      F[r * fpitch + j] = e;
+      F[r * fpitch + nh4 + j] = o;
+    }
+    fence_proxy_async();   // generic-proxy reads of the raw tile are ordered before the async refill
+    __syncthreads();       // the raw tile is free, the folded tile complete
+    const int next = tile + gridDim.x;
+    if (tid == 0 && next < p.ntiles) issue(next);
+
+    for (int mg = mg0; mg < p.nmg; mg += mgstep) {
+      float ar[RT][4], ai[RT][4];
+#pragma unroll
+      for (int j = 0; j < RT; ++j)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) ar[j][m] = ai[j][m] = 0.f;
+      const float* xrow = F + (rg * 32 * RT + lane) * fpitch;
+      const float4* tb = reinterpret_cast<const float4*>(ts + mg * 4);
+      const int tpitch4 = m2p >> 1;   // float4 per table row
+#pragma unroll 2
+      for (int w4 = 0; w4 < (nh4 >> 2); ++w4) {
+        float ev[RT][4], ov[RT][4];
+#pragma unroll
+        for (int j = 0; j < RT; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(xrow + j * 32 * fpitch + 4 * w4);
+          const float4 u = *reinterpret_cast<const float4*>(xrow + j * 32 * fpitch + nh4 + 4 * w4);
+          ev[j][0] = v.x; ev[j][1] = v.y; ev[j][2] = v.z; ev[j][3] = v.w;
+          ov[j][0] = u.x; ov[j][1] = u.y; ov[j][2] = u.z; ov[j][3] = u.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t01 = tb[(4 * w4 + i) * tpitch4];
+          const float4 t23 = tb[(4 * w4 + i) * tpitch4 + 1];
+          const float tc[4] = {t01.x, t01.z, t23.x, t23.z};
+          const float tsn[4] = {t01.y, t01.w, t23.y, t23.w};
+#pragma unroll
+          for (int j = 0; j < RT; ++j)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              ar[j][m] = fmaf(ev[j][i], tc[m], ar[j][m]);
+              ai[j][m] = fmaf(-ov[j][i], tsn[m], ai[j][m]);
+            }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < RT; ++j) {
+        const int row = row0 + rg * 32 * RT + j * 32 + lane;
+        if (row >= p.rows) continue;
+        float2* o = p.out + (size_t)row * m2 + mg * 4;
+        if ((m2 & 3) == 0) {
+          reinterpret_cast<float4*>(o)[0] = make_float4(ar[j][0], ai[j][0], ar[j][1], ai[j][1]);
+          reinterpret_cast<float4*>(o)[1] = make_float4(ar[j][2], ai[j][2], ar[j][3], ai[j][3]);
+        } else {
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            if (mg * 4 + m < m2) o[m] = make_float2(ar[j][m], ai[j][m]);
+        }
+      }
+    }
+    __syncthreads();       // the folded tile is free before the next fold pass
+  }
+}
+
 bool wfwd_uses_tensor_cores(const Plan* pl, const float* x, int rows, int prec) {
   return (prec == 1 || prec == 2) && rows >= 128 && tc_wfwd_supported(pl, x, prec == 2);
 }
@@ -273,6 +400,38 @@ bool launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act,
   if ((wp & 3) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) {   // bulk copies need 16-byte rows
     launch_wfwd_generic(pl, x, out, rows, act, st);
     return false;
+  }
+  static const int fold_knob = [] { const char* e = getenv("BDN_WFWD_FOLD"); return e ? atoi(e) : 1; }();   // (tuning knob)
+  // folding pays where the multiply-adds dominate the fold pass: measured (r2r) 13 % faster at 32 modes (the heads),
+  // 10 % slower at 12 modes (the per-snapshot net: 24 FMAs per element become 12, the fold pass adds ~8 instructions)
+  if (fold_knob && pl->t_wl_half != nullptr && (m2 >= 20 || fold_knob == 2)) {
+    WfoldParams f;
+    f.x = x; f.out = out; f.t_half = pl->t_wl_half; f.rows = rows; f.wp = wp; f.m2 = m2; f.act = act;
+    f.nh = pl->wl_nh; f.nh4 = pl->wl_nh4; f.m2p = pl->wl_m2p;
+    f.nmg = f.m2p >> 2;
+    f.fpitch = 2 * f.nh4 + ((((2 * f.nh4) >> 2) & 1) ? 0 : 4);      // (pitch / 4) odd: conflict-free 128-bit row-strided loads
+    f.nrg = f.nmg <= 2 ? 4 : (f.nmg <= 4 ? 2 : 1);
+    const int nwarps = f.nrg * (f.nmg < 8 / f.nrg ? f.nmg : 8 / f.nrg);
+    auto smem_of = [&](int r) {
+      return (size_t)32 * r * f.nrg * (wp + f.fpitch) * 4 + (size_t)f.nh4 * f.m2p * 8 + 16;
+    };
+    int rt = 4;
+    while (rt > 1 && (ceil_div(rows, 32 * rt * f.nrg) < 2 * 148 || smem_of(rt) > 100 * 1024)) rt >>= 1;
+    if (smem_of(rt) <= 200 * 1024) {
+      f.ntiles = ceil_div(rows, 32 * rt * f.nrg);
+      const size_t smem = smem_of(rt);
+      const int per_sm = (int)((220 * 1024) / (smem + 1024));
+      const int cap = 148 * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+      const int grid = f.ntiles < cap ? f.ntiles : cap;
+#define BDN_WFOLD(RT)                                                                                    \
+  {                                                                                                      \
+    cudaFuncSetAttribute(wfwd_fold_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    launch_k(wfwd_fold_kernel<RT>, dim3(grid), dim3(32 * nwarps), smem, st, f);                          \
+  }
+      if (rt == 4) BDN_WFOLD(4) else if (rt == 2) BDN_WFOLD(2) else BDN_WFOLD(1)
+#undef BDN_WFOLD
+      return false;
+    }
   }
   WfwdParams p;
   p.x = x; p.out = out; p.t_wl = pl->t_wl; p.rows = rows; p.wp = wp; p.m2 = m2; p.act = act;
