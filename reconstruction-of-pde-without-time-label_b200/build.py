@@ -44,24 +44,45 @@ def _fingerprint() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile if the sources changed since the last build.  Returns the .so path."""
+    """Compile if the sources changed since the last build.  Returns the .so path.
+
+    Safe under concurrent callers (one process per GPU under torchrun all import the package at once): the check and
+    the compile run under an exclusive file lock, nvcc writes to a private temporary file, and the library is put in
+    place with an atomic rename -- a process never sees a half-written .so."""
+    import fcntl
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.stamp")
     fp = _fingerprint()
-    if not force and os.path.exists(LIBPATH) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
+
+    def current() -> bool:
+        return os.path.exists(LIBPATH) and os.path.exists(stamp) and open(stamp).read().strip() == fp
+
+    if not force and current():
         return LIBPATH
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-o", LIBPATH, *srcs]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr, file=sys.stderr)
-    with open(stamp, "w") as fh:
-        fh.write(fp)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and current():          # another process built it while this one waited for the lock
+                return LIBPATH
+            srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+            tmp = f"{LIBPATH}.tmp.{os.getpid()}"
+            cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-o", tmp, *srcs]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), file=sys.stderr)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            if verbose:
+                print(res.stderr, file=sys.stderr)
+            os.replace(tmp, LIBPATH)
+            with open(stamp + ".tmp", "w") as fh:
+                fh.write(fp)
+            os.replace(stamp + ".tmp", stamp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIBPATH
 
 

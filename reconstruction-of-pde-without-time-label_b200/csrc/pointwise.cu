@@ -105,21 +105,27 @@ void launch_lift(const LiftArgs& a, float* z0, cudaStream_t st) {
   const LiftParams p = make_lift_params(a);
   const int plane = a.hp * a.wp;
   const int block = 256;
-  int gx = (plane + 4 * block - 1) / (4 * block);
+  // few pixels in all (the heads: 4 images): one pixel per thread, 4x the blocks (24 blocks were latency-bound at 9 us)
+  const int px = (long)a.images * plane < 148L * block * 4 ? 1 : 4;
+  int gx = (plane + px * block - 1) / (px * block);
   // 1-D nets have tiny planes and many images: fold several images' worth of blocks only through grid.y
   dim3 grid(gx, a.images < 65535 ? a.images : 65535);
   const int cp = (a.width + 3) & ~3;
   const size_t smem = (size_t)(a.c_in * cp + cp) * sizeof(float);
-#define BDN_LIFT(CPV, PXV) launch_k(lift_kernel<CPV, PXV>, grid, dim3(block), smem, st, p, z0)
+#define BDN_LIFT(CPV)                                                                   \
+  {                                                                                     \
+    if (px == 1) launch_k(lift_kernel<CPV, 1>, grid, dim3(block), smem, st, p, z0);     \
+    else launch_k(lift_kernel<CPV, 4>, grid, dim3(block), smem, st, p, z0);             \
+  }
   switch (cp) {
-    case 4: BDN_LIFT(4, 4); break;
-    case 8: BDN_LIFT(8, 4); break;
-    case 12: BDN_LIFT(12, 4); break;
-    case 16: BDN_LIFT(16, 4); break;
-    case 20: BDN_LIFT(20, 4); break;
-    case 24: BDN_LIFT(24, 4); break;
-    case 28: BDN_LIFT(28, 4); break;
-    default: BDN_LIFT(32, 4); break;
+    case 4: BDN_LIFT(4) break;
+    case 8: BDN_LIFT(8) break;
+    case 12: BDN_LIFT(12) break;
+    case 16: BDN_LIFT(16) break;
+    case 20: BDN_LIFT(20) break;
+    case 24: BDN_LIFT(24) break;
+    case 28: BDN_LIFT(28) break;
+    default: BDN_LIFT(32) break;
   }
 #undef BDN_LIFT
 }

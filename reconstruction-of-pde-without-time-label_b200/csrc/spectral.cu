@@ -1145,9 +1145,99 @@ __global__ void gw_reduce_kernel(const float2* __restrict__ xs, const float2* __
   }
 }
 
+// Register-tiled form for channel counts that are multiples of 4: a thread owns one mode (k, l) and a 4 x 4 block of
+// (input, output) channel pairs, so an image costs 8 loads for 16 complex multiply-adds (the plain kernel: 2 loads for
+// one, every spectrum value re-read co times through L1/L2 -- 80 us per launch for the heads at batch 32).
+__global__ void __launch_bounds__(128) gw_reduce_tiled_kernel(const float2* __restrict__ xs, const float2* __restrict__ gys,
+                                                              float2* gw1, float2* gw2, int images, int ci, int co, int K,
+                                                              int m1, int m2, int bchunk) {
+  // block = 32 mode tiles (threadIdx.x) x 4 image sub-chunks (threadIdx.y): the sub-chunks' partial sums are joined in
+  // shared memory, so a block issues one (atomic) update per output instead of four
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float part[4][32][33];
+  const int nog = co >> 2, nig = ci >> 2;
+  const long total = (long)nig * nog * K * m2;
+  const long idx = blockIdx.x * 32L + threadIdx.x;
+  const bool live = idx < total;
+  const long id = live ? idx : 0;
+  const int l = id % m2, k = (id / m2) % K, og = (id / ((long)m2 * K)) % nog, ig = id / ((long)m2 * K * nog);
+  const int sub = threadIdx.y;
+  const int b0 = blockIdx.y * bchunk, b1 = min(images, b0 + bchunk);
+  const size_t plane = (size_t)K * m2;
+  const float2* xp = xs + ((size_t)(b0 + sub) * ci + ig * 4) * plane + (size_t)k * m2 + l;
+  const float2* gp = gys + ((size_t)(b0 + sub) * co + og * 4) * plane + (size_t)k * m2 + l;
+  float re[4][4], im[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) re[a][c] = im[a][c] = 0.f;
+  if (live) {
+#pragma unroll 2
+    for (int b = b0 + sub; b < b1; b += 4) {
+      float2 x[4], g[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        x[a] = __ldg(xp + a * plane);
+        g[a] = __ldg(gp + a * plane);
+      }
+      xp += 4 * (size_t)ci * plane;
+      gp += 4 * (size_t)co * plane;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          re[a][c] = fmaf(x[a].x, g[c].x, fmaf(x[a].y, g[c].y, re[a][c]));
+          im[a][c] = fmaf(x[a].x, g[c].y, fmaf(-x[a].y, g[c].x, im[a][c]));
+        }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      part[sub][threadIdx.x][(a * 4 + c) * 2] = re[a][c];
+      part[sub][threadIdx.x][(a * 4 + c) * 2 + 1] = im[a][c];
+    }
+  __syncthreads();
+  if (!live) return;
+  const bool lo = (m1 == 0) || k < m1;
+  const int kk = lo ? k : k - m1;
+  const int mrows = m1 == 0 ? 1 : m1;
+  float2* base = lo ? gw1 : gw2;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {            // this thread finishes (a, c) pairs sub * 4 + q
+    const int pr = sub * 4 + q, a = pr >> 2, c = pr & 3;
+    const float vr = (part[0][threadIdx.x][2 * pr] + part[1][threadIdx.x][2 * pr]) +
+                     (part[2][threadIdx.x][2 * pr] + part[3][threadIdx.x][2 * pr]);
+    const float vi = (part[0][threadIdx.x][2 * pr + 1] + part[1][threadIdx.x][2 * pr + 1]) +
+                     (part[2][threadIdx.x][2 * pr + 1] + part[3][threadIdx.x][2 * pr + 1]);
+    float* dst = reinterpret_cast<float*>(base + ((size_t)((ig * 4 + a) * co + og * 4 + c) * mrows + kk) * m2 + l);
+    if (gridDim.y == 1) {
+      dst[0] += vr; dst[1] += vi;
+    } else {
+      atomicAdd(dst, vr); atomicAdd(dst + 1, vi);
+    }
+  }
+}
+
 void launch_gw_reduce(const Plan* pl, const float2* xs, const float2* gys, float2* gw1, float2* gw2, int images,
                       int ci, int co, cudaStream_t st) {
   LaunchScope scope("gw_reduce", st, co);
+  static const int tiled_knob = [] { const char* e = getenv("BDN_GW_TILED"); return e ? atoi(e) : 1; }();   // (tuning knob)
+  if (tiled_knob && (ci & 3) == 0 && (co & 3) == 0) {
+    const long total = (long)(ci >> 2) * (co >> 2) * pl->K * pl->m2;
+    const int gx = (int)((total + 31) / 32);
+    // split the image loop further over blocks (atomic accumulation) when the modes alone do not fill the GPU:
+    // >= 16 images per block (4 per sub-chunk)
+    int chunks = 1;
+    while (chunks < images && (long)gx * chunks < 2 * 148 && images / (chunks * 2) >= 16) chunks *= 2;
+    const int bchunk = ceil_div(images, chunks);
+    dim3 grid(gx, ceil_div(images, bchunk));
+    launch_k(gw_reduce_tiled_kernel, dim3(grid), dim3(32, 4), 0, st, xs, gys, gw1, gw2, images, ci, co, pl->K, pl->m1, pl->m2,
+             bchunk);
+    return;
+  }
   const long total = (long)ci * co * pl->K * pl->m2;
   const int block = 128;
   const int gx = (int)((total + block - 1) / block);
@@ -1171,6 +1261,7 @@ struct WinvParams {
   const float* pw_w; const float* pw_b; float* g_pw_w; float* g_pw_b;
   const float* t_cos; const float* t_sin;
   int lines, c, hp, wp, wp4, m2, act_in, HT, WCH;
+  int table_bulk, bar_off;      // tables by bulk copy (WCH == wp4); float offset of the mbarrier in shared memory
 };
 
 template <int MODE, int CG>   // CG = channels accumulated per work item (4, 2 or 1)
@@ -1188,6 +1279,7 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
   float* pws = as + (MODE >= 1 ? c * npx : 0);             // [cpad][c] + bias[cpad]
   float* zact = pws + (MODE >= 1 ? cpad * c + cpad : 0);   // [c][HT][WCH] act(z_in)   (MODE == 2)
   float* gsm = zact + (MODE == 2 ? c * npx : 0);           // [c][HT][WCH] act'(z_in)  (MODE == 2)
+  uint64_t* tbar = reinterpret_cast<uint64_t*>(smem + p.bar_off);   // completion of the table copies (bulk path)
 
   // Staging.  Every index split below is a multiply by a precomputed reciprocal (exact for these
   // ranges): ncu showed the integer divisions of the element-wise staging loops to be 45 % of this
@@ -1197,7 +1289,18 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
               inv_m2 = 1.0f / (float)m2;
   auto fdiv = [](int n, float inv) { return __float2int_rz(((float)n + 0.5f) * inv); };
   pdl_launch_dependents();
-  for (int idx = tid; idx < m2 * nwq; idx += nt) {      // constant plan data: staged before the dependency wait
+  // constant plan data, staged before the dependency wait: when the block covers whole table rows (one w chunk) the
+  // two tables are contiguous -> two bulk async copies that land while the spectrum and the activations are staged
+  const bool tbulk = p.table_bulk != 0;
+  if (tbulk && tid == 0) {
+    mbar_init(tbar, 1);
+    mbar_init_fence();
+    const uint32_t tb = (uint32_t)(m2 * WCH) * 4u;
+    mbar_expect_tx(tbar, 2u * tb);
+    bulk_g2s(tc, p.t_cos, tb, tbar);
+    bulk_g2s(tsn, p.t_sin, tb, tbar);
+  }
+  for (int idx = tid; idx < (tbulk ? 0 : m2 * nwq); idx += nt) {
     const int l = fdiv(idx, inv_nwq), q = idx - l * nwq;
     const int w = wc0 + 4 * q;     // wp4 is a multiple of 4: a float4 is inside the table row or fully outside
     float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), sv = cv;
@@ -1278,7 +1381,8 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
     for (int idx = tid; idx < cpad; idx += nt)
       pws[cpad * c + idx] = (MODE == 1 && idx < c) ? __ldg(p.pw_b + idx) : 0.f;
   }
-  __syncthreads();
+  __syncthreads();          // (also publishes the mbarrier init)
+  if (tbulk) mbar_wait(tbar, 0);
 
   const int nwg = WCH >> 2, nog = cpad / CG;
   for (int idx = tid; idx < nog * HT * nwg; idx += nt) {
@@ -1439,7 +1543,11 @@ void launch_winv(const Plan* pl, int mode, const WinvArgs& a, cudaStream_t st) {
         if (score > best) { best = score; best_ht = ht; best_cg = cg; }
       }
   p.HT = best_ht; p.WCH = wch;
-  const size_t smem = smem_of(best_ht, wch);
+  size_t smem = smem_of(best_ht, wch);
+  smem = (smem + 15) & ~(size_t)15;
+  p.bar_off = (int)(smem / sizeof(float));
+  p.table_bulk = nch == 1 && wch == pl->wp4;
+  smem += 16;
   dim3 grid(ceil_div(p.lines, best_ht), ceil_div(pl->wp4, wch));
 #define BDN_WINV(M)                                                        \
   {                                                                        \
