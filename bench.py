@@ -641,9 +641,18 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that dies must not leave the others in a collective for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     try:
         run_b200(args, wl, rank, world, local_rank)
+    except BaseException:
+        if world > 1:
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)          # do not wait in destroy_process_group / atexit for peers that are blocked in a collective
+        raise
     finally:
         if world > 1:
             import torch.distributed as dist
