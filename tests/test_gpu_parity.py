@@ -175,6 +175,30 @@ def test_fno_golden(name, ndim, fn):
         _grad_check(k, got[k].grad, g, g64[k], floor=1.2e-7 * _gmax(g64))
 
 
+@pytest.mark.parametrize("images,n,width,modes,layers", [(3, 57, 12, 32, 2), (2, 45, 8, 20, 1), (5, 61, 12, 32, 1)])
+def test_few_image_heads_at_odd_padded_sizes_vs_oracle(images, n, width, modes, layers):
+    """The few-image kernels of an output head at shapes that exercise their tails: an odd padded plane (57 -> 71: the
+    last row pair of the inverse H transform has one row, read from the h-major table), the staged weight column, the
+    folded W-forward (modes >= 20) with an odd number of folded columns, the register-tiled weight-gradient reduction
+    (width 8 / 12), one-pixel-per-thread lift."""
+    torch.manual_seed(images * 100 + n)
+    net = fno.FNO2d(modes=modes, width=width, n_layers=layers, input_dim=width, output_dim=1)
+    params = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(n)
+    x, gy = torch.randn(images, n, n, width, generator=g), torch.randn(images, n, n, 1, generator=g)
+    net = net.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    y = net(xd)
+    y.backward(gy.to(DEV))
+    (y32, g32, gx32), (y64, g64, gx64) = _oracle_grads(O.fno2d_forward, params, x, gy)
+    assert rel_err(y, y64) < TOL
+    _grad_check("gx", xd.grad, gx32, gx64, floor=1.2e-7 * _gmax(g64))
+    got = dict(net.named_parameters())
+    for k, gref in g64.items():
+        if gref is not None and k in got and got[k].grad is not None:
+            _grad_check(k, got[k].grad, g32[k], gref, floor=1.2e-7 * _gmax(g64))
+
+
 # ---------------------------------------------------------------------------------------------
 # whole NIO-FNO models vs golden + oracle
 # ---------------------------------------------------------------------------------------------
