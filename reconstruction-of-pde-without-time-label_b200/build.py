@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
-]
+] + os.environ.get("BDN_NVCC_EXTRA", "").split()      # (experiments, e.g. -DBDN_PDL_LATE=1; part of the build fingerprint)
 
 
 def _nvcc() -> str:

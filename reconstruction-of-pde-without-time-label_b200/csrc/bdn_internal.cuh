@@ -255,7 +255,16 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // launches without the attribute.  Opt-in with BDN_PDL=1 in the environment (off by default: it measured
 // neutral once the step is replayed from a CUDA graph, 1.402 ms vs 1.381 ms per step).
 // ---------------------------------------------------------------------------
+// Build with -DBDN_PDL_LATE=1 (BDN_NVCC_EXTRA in the environment of build.py) to move the trigger from the top of every
+// kernel to a point late in its work (pdl_trigger_late): with the trigger at the top a whole chain of future kernels
+// pre-launches and their waiting blocks hold shared memory (one head alone: 252 -> 317 us).
+#ifdef BDN_PDL_LATE
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void pdl_trigger_late() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger_late() {}
+#endif
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool pdl_enabled();      // BDN_PDL: 0 off, 1 every launch, 2 every launch except those of few-image nets (pdl_few_images)

@@ -91,6 +91,61 @@ __global__ void __launch_bounds__(256) lift_kernel(const LiftParams p, float* __
   }
 }
 
+// Bags form of the per-snapshot net (width <= 4, grid_dim 1 or 2): a thread owns 4 consecutive padded columns of one row
+// and writes one float4 per channel; the generic kernel above spends ~700 instructions per 4 pixels on its run-time
+// loops over input features (ncu r1n: 7.7 M warp-instructions for 240 images, 16 us for 28 MB of stores).
+template <int GD>
+__global__ void __launch_bounds__(256) lift_bags4_kernel(const LiftParams p, float* __restrict__ z0) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float ws[(GD + 1) * 4], bs[4];       // ws[i * 4 + c] = W0[c][i]
+  if (threadIdx.x < (GD + 1) * 4) {
+    const int i = threadIdx.x >> 2, c = threadIdx.x & 3;
+    ws[threadIdx.x] = c < p.width ? __ldg(p.w0 + c * (GD + 1) + i) : 0.f;
+  }
+  if (threadIdx.x < 4) bs[threadIdx.x] = (int)threadIdx.x < p.width ? __ldg(p.b0 + threadIdx.x) : 0.f;
+  __syncthreads();
+  const int wq = p.wp >> 2, per_img = p.hp * wq;
+  const float inv_wq = 1.0f / (float)wq;
+  const size_t plane = (size_t)p.hp * p.wp;
+  for (int img = blockIdx.y; img < p.images; img += gridDim.y) {
+    const int b = img / p.n_keep, l = img - b * p.n_keep;
+    const int snap = p.idx != nullptr ? __ldg(p.idx + l) : l;
+    const float* src0 = p.bags + ((size_t)b * p.bag_len + snap) * p.h * p.w;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per_img; t += gridDim.x * blockDim.x) {
+      const int hh = __float2int_rz(((float)t + 0.5f) * inv_wq), ww = (t - hh * wq) * 4;     // exact for these ranges
+      float o[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[c][j] = 0.f;
+      if (hh < p.h && ww < p.w) {
+        const int pix0 = hh * p.w + ww;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (ww + j < p.w) {
+            const float v = __ldg(src0 + pix0 + j);
+            float g[GD];
+#pragma unroll
+            for (int d = 0; d < GD; ++d) g[d] = __ldg(p.grid + (size_t)(pix0 + j) * GD + d);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float acc = fmaf(ws[c], v, bs[c]);
+#pragma unroll
+              for (int d = 0; d < GD; ++d) acc = fmaf(ws[(1 + d) * 4 + c], g[d], acc);
+              o[c][j] = acc;
+            }
+          }
+        }
+      }
+      float* dst = z0 + (size_t)img * p.width * plane + (size_t)hh * p.wp + ww;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < p.width) *reinterpret_cast<float4*>(dst + c * plane) = make_float4(o[c][0], o[c][1], o[c][2], o[c][3]);
+    }
+  }
+}
+
 static LiftParams make_lift_params(const LiftArgs& a) {
   LiftParams p;
   p.x_cl = a.x_cl; p.bags = a.bags; p.idx = a.idx; p.grid = a.grid;
@@ -105,6 +160,15 @@ void launch_lift(const LiftArgs& a, float* z0, cudaStream_t st) {
   const LiftParams p = make_lift_params(a);
   const int plane = a.hp * a.wp;
   const int block = 256;
+  static const int bags4_knob = [] { const char* e = getenv("BDN_LIFT_BAGS4"); return e ? atoi(e) : 1; }();   // (tuning knob)
+  if (bags4_knob && a.x_cl == nullptr && a.width <= 4 && (a.wp & 3) == 0 && (a.grid_dim == 1 || a.grid_dim == 2) &&
+      a.c_in == a.grid_dim + 1 && (reinterpret_cast<uintptr_t>(z0) & 15) == 0) {
+    const int per_img = a.hp * (a.wp >> 2);
+    dim3 grid((per_img + block - 1) / block, a.images < 65535 ? a.images : 65535);
+    if (a.grid_dim == 1) launch_k(lift_bags4_kernel<1>, grid, dim3(block), 0, st, p, z0);
+    else launch_k(lift_bags4_kernel<2>, grid, dim3(block), 0, st, p, z0);
+    return;
+  }
   // few pixels in all (the heads: 4 images): one pixel per thread, 4x the blocks (24 blocks were latency-bound at 9 us)
   const int px = (long)a.images * plane < 148L * block * 4 ? 1 : 4;
   int gx = (plane + px * block - 1) / (px * block);
@@ -393,6 +457,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjArgs a,
   const long ntiles = (total + TILE - 1) / TILE;
 
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (tile + gridDim.x >= ntiles) pdl_trigger_late();      // the block's last tile
     float z[PP][CP], o[PP][NOUT];
     long t[PP];
 #pragma unroll
@@ -546,6 +611,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_bwd_kernel(const ProjArg
   const float gscale = pooled_g ? 1.0f / (float)n_keep : 1.0f;
 
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (tile + gridDim.x >= ntiles) pdl_trigger_late();      // the block's last tile
     float z[PP][CP], g[PP][NOUT], gzr[PP][CP];
     size_t zoff[PP];
     bool live[PP];
@@ -766,11 +832,16 @@ void launch_project_bwd(const ProjArgs& a, const float* g_out, int pooled_g, int
   cudaMemsetAsync(gz, 0, act_bytes, st);
   const long total = (long)a.images * a.out_h * a.out_w;
   const bool many = proj_many_pixels(total);
+  // few pixels: pixels per thread between two reductions of the weight-gradient partials (tuning knob)
+  // (r2x, heads: 1 pixel 38.2 us per launch, 2 pixels 27.1 us)
+  static const int pp8 = [] { const char* e = getenv("BDN_PROJ_BWD_PP8"); return e ? atoi(e) : 2; }();
   dispatch_cp(a.width, [&](auto cp) {
     constexpr int CP = decltype(cp)::value;
     constexpr int PPM = CP <= 4 ? 8 : (CP <= 12 ? 4 : 2);
     if (a.c_out == 1) {
       if (many) launch_project_bwd_t<CP, 1, 1, PPM>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, total, st);
+      else if (pp8 == 2) launch_project_bwd_t<CP, 1, 8, 2>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, total, st);
+      else if (pp8 == 4) launch_project_bwd_t<CP, 1, 8, 4>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, total, st);
       else launch_project_bwd_t<CP, 1, 8, 1>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, total, st);
     } else {
       if (many) launch_project_bwd_t<CP, PROJ_MAX_OUT, 1, 2>(a, g_out, pooled_g, n_keep, gz, g_w1, g_b1, g_w2, g_b2, total, st);
@@ -981,20 +1052,21 @@ __global__ void __launch_bounds__(1024) mse_heads_fwd_kernel(const MseHeadsArgs 
   float s = 0.f;
   const int stride = gridDim.x * blockDim.x;
   if (c == 1) {
-    // one channel per head (every model of the reference): 4 pixels per pass, all loads before the first store -- the
+    // one channel per head (every model of the reference): 8 pixels per pass, all loads before the first store -- the
     // gradient stores may alias the inputs as far as the compiler knows, so a store between two loads serialises them
     // (the straightforward loop ran 15 dependent round trips to L2: 19 us for 30 k elements)
-    for (int pix0 = blockIdx.x * blockDim.x + threadIdx.x; pix0 < npix; pix0 += 4 * stride) {
-      float d[4][MSE_MAX_HEADS];
+    constexpr int U = 8;
+    for (int pix0 = blockIdx.x * blockDim.x + threadIdx.x; pix0 < npix; pix0 += U * stride) {
+      float d[U][MSE_MAX_HEADS];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int pix = pix0 + u * stride;
 #pragma unroll
         for (int k = 0; k < MSE_MAX_HEADS; ++k)
           d[u][k] = (pix < npix && k < a.n_heads) ? __ldg(a.out[k] + pix) - __ldg(a.target + pix * C + k) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int pix = pix0 + u * stride;
 #pragma unroll
         for (int k = 0; k < MSE_MAX_HEADS; ++k) {
@@ -1055,9 +1127,9 @@ __global__ void mse_heads_bwd_kernel(const MseHeadsArgs a, const float* __restri
 }
 
 int mse_heads_blocks(long npix) {
-  if (npix <= 32768) return 1;                     // one block: no second level, no atomics
-  const long b = (npix + 8191) / 8192;
-  return (int)(b > MSE_BLOCKS ? MSE_BLOCKS : b);
+  static const long per_block = [] { const char* e = getenv("BDN_MSE_PIX_PER_BLOCK"); return e ? atol(e) : 1024L; }();   // (tuning knob)
+  const long b = (npix + per_block - 1) / per_block;      // one pixel per thread: a single round of loads, then two-level sum
+  return (int)(b < 1 ? 1 : (b > MSE_BLOCKS ? MSE_BLOCKS : b));
 }
 
 void launch_mse_heads(const MseHeadsArgs& a, float* loss, float* partial, unsigned int* counter, cudaStream_t st) {

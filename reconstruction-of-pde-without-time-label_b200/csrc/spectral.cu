@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(256) wfwd_pipe_kernel(const WfwdParams p) {
     const int stage = it & 1;
     const int next = tile + gridDim.x;
     if (warp == 0 && next < p.ntiles) issue(next, stage ^ 1);
+    if (next >= p.ntiles) pdl_trigger_late();
     mbar_wait(&bars[stage], (it >> 1) & 1);
     float* xs = stage ? stage1 : stage0;
     const int row0 = tile * BR;
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(256) wfwd_fold_kernel(const WfoldParams p) {
     __syncthreads();       // the raw tile is free, the folded tile complete
     const int next = tile + gridDim.x;
     if (tid == 0 && next < p.ntiles) issue(next);
+    if (next >= p.ntiles) pdl_trigger_late();      // the block's last tile: only its multiply-adds and stores remain
 
     for (int mg = mg0; mg < p.nmg; mg += mgstep) {
       float ar[RT][4], ai[RT][4];
@@ -698,6 +700,7 @@ __global__ void __launch_bounds__(1024) core2d_kernel(const CoreParams p) {
     }
   }
   __syncthreads();
+  pdl_trigger_late();
 
   // phase 2: per-mode channel mix of both rows of a frequency -> (P, Q).
   // fwd: y_b = sum_a x_a W[a][b]; bwd: y_b = sum_a x_a conj(W[b][a])
@@ -822,6 +825,7 @@ __global__ void __launch_bounds__(1024) core2d_stream_kernel(const CoreParams p,
     const int stage = it & 1;
     if (tid == 0 && b + (int)gridDim.x < images) issue(b + gridDim.x, stage ^ 1);
     mbar_wait(&bars[stage], (it >> 1) & 1);
+    if (b + (int)gridDim.x >= images) pdl_trigger_late();
     const float2* xin = stage ? in1 : in0;                  // [a][h][l]
 
     // phase 1: X[k][(a,l)] = pre[l] * sum_h x[a][h][l] * e^{-i phi_kh}, by frequency (row pairs)
@@ -1192,6 +1196,7 @@ __global__ void __launch_bounds__(128) gw_reduce_tiled_kernel(const float2* __re
         }
     }
   }
+  pdl_trigger_late();
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -1382,6 +1387,7 @@ __global__ void __launch_bounds__(256) winv_kernel(const WinvParams p) {
       pws[cpad * c + idx] = (MODE == 1 && idx < c) ? __ldg(p.pw_b + idx) : 0.f;
   }
   __syncthreads();          // (also publishes the mbarrier init)
+  pdl_trigger_late();
   if (tbulk) mbar_wait(tbar, 0);
 
   const int nwg = WCH >> 2, nog = cpad / CG;
@@ -1542,6 +1548,14 @@ void launch_winv(const Plan* pl, int mode, const WinvArgs& a, cudaStream_t st) {
         const double score = util * dens * (pass == 1 && ht > 1 ? 0.0 : 1.0);
         if (score > best) { best = score; best_ht = ht; best_cg = cg; }
       }
+  {   // (tuning knobs for the many-image regime: "ht,cg" applied when lines >= 4096)
+    static const char* knob = getenv("BDN_WINV_TILE");
+    int kh = 0, kc = 0;
+    if (knob && p.lines >= 4096 && sscanf(knob, "%d,%d", &kh, &kc) == 2 && kh >= 1 && (kc == 1 || kc == 2 || kc == 4) &&
+        smem_of(kh, wch) <= 64 * 1024) {
+      best_ht = kh; best_cg = kc;
+    }
+  }
   p.HT = best_ht; p.WCH = wch;
   size_t smem = smem_of(best_ht, wch);
   smem = (smem + 15) & ~(size_t)15;
