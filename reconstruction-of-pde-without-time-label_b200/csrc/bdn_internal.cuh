@@ -194,10 +194,19 @@ __device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
   cdf = x >= 0.f ? 1.0f - q : q;
   pdf = e;
 }
+// gelu(x) = x Phi(x) without forming Phi: x (1 - q) for x >= 0 and x q for x < 0 are both max(x, 0) - |x| q
+// (one FMNMX + one FFMA instead of a compare, a predicated subtraction and a multiply: 13 instead of 14 instructions)
 __device__ __forceinline__ float gelu_fast(float x) {
-  float cdf, pdf;
-  gelu_cdf_pdf(x, cdf, pdf);
-  return x * cdf;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(fabsf(x), 0.2316418882663604f, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(x * x, -0.72134752044448170368f, -1.3257480647361592f)));
+  float p = 1.3302745f;
+  p = fmaf(p, t, -1.8212559f);
+  p = fmaf(p, t, 1.7814779f);
+  p = fmaf(p, t, -0.35656378f);
+  p = fmaf(p, t, 0.31938154f);
+  const float q = p * t * e;
+  return fmaf(-fabsf(x), q, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float gelu_exact(float x) { return gelu_fast(x); }
 __device__ __forceinline__ float gelu_grad(float x) {

@@ -116,4 +116,7 @@ def test_gelu_formula_accuracy_in_fp32():
     ref = np.array([0.5 * (1.0 + math.erf(v / math.sqrt(2.0))) for v in xd[::40]])
     assert np.abs(cdf[::40] - ref).max() <= 3.5e-7
     assert np.abs(xd[::40] * cdf[::40] - xd[::40] * ref).max() <= 5e-7
+    # the forward-only form gelu = max(x, 0) - |x| q (no Phi): same bound
+    gelu = (np.maximum(x, f(0)) - (np.abs(x) * q).astype(f)).astype(np.float64)
+    assert np.abs(gelu[::40] - xd[::40] * ref).max() <= 5e-7
     assert np.abs(e.astype(np.float64) - np.exp(-0.5 * xd * xd) / math.sqrt(2 * math.pi)).max() <= 1e-7
