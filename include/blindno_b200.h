@@ -257,6 +257,24 @@ int bdn_nio_tail_backward(const float* g, const float* basis, const float* wbar_
                           int32_t npix, int32_t grid_dim, int32_t width, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Bag attention + bag mean of the BlinDNO models, without [n_keep, dim] intermediates:
+ *   TemporalSelfAttention.forward  2d_FPE/NIOModules.py:1063-1083  softmax(X X^T / sqrt(dim)) X + X, LayerNorm(dim)
+ *   followed by .mean(dim=1)       2d_FPE/NIOModules.py:1153-1170  (1d_FPE/NIOModules.py, 1d_GPE/NIOModules.py alike)
+ * x: [n_bags, n_keep, dim] tokens (flattened feature maps), n_keep <= 128; ln_w, ln_b: [dim] (LayerNorm affine);
+ * out: [n_bags, dim]; saved: bdn_bag_attention_saved_floats() floats (row statistics, centered Gram matrix, attention
+ * weights: what backward needs besides x).  backward: g [n_bags, dim] -> g_x [n_bags, n_keep, dim] (OVERWRITTEN),
+ * g_ln_w_per_bag [n_bags, dim] (OVERWRITTEN; the caller sums over bags; d loss / d ln_b is the sum of g over bags);
+ * ws: bdn_bag_attention_workspace_floats() floats.
+ * ------------------------------------------------------------------------- */
+size_t bdn_bag_attention_saved_floats(int32_t n_bags, int32_t n_keep);
+size_t bdn_bag_attention_workspace_floats(int32_t n_bags, int32_t n_keep);
+int bdn_bag_attention_mean_forward(const float* x, const float* ln_w, const float* ln_b, float* out, float* saved,
+                                   int32_t n_bags, int32_t n_keep, int32_t dim, float eps, void* stream);
+int bdn_bag_attention_mean_backward(const float* x, const float* g, const float* ln_w, const float* saved, float* g_x,
+                                    float* g_ln_w_per_bag, float* ws, int32_t n_bags, int32_t n_keep, int32_t dim,
+                                    void* stream);
+
+/* ---------------------------------------------------------------------------
  * Training loss in one launch: criterion(model(inputs, grid), outputs) with criterion = torch.nn.MSELoss()
  *   2d_FPE/train_fno.py:116,146-147 (1d_FPE/train_fno.py, 1d_GPE/train_nio_GPE.py alike); the model's
  *   torch.cat of its head outputs (2d_FPE/NIOModules.py:577-581) is folded into the addressing.

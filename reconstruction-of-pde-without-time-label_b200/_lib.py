@@ -82,6 +82,10 @@ EXPORTS = {
     "bdn_bag_pool_lift_backward": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "bdn_nio_tail_forward": (C.c_int, [_fp] * 8 + [C.c_int32] * 6 + [_fp]),
     "bdn_nio_tail_backward": (C.c_int, [_fp] * 8 + [C.c_int32] * 6 + [_fp]),
+    "bdn_bag_attention_saved_floats": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "bdn_bag_attention_workspace_floats": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "bdn_bag_attention_mean_forward": (C.c_int, [_fp] * 5 + [C.c_int32] * 3 + [C.c_float, _fp]),
+    "bdn_bag_attention_mean_backward": (C.c_int, [_fp] * 7 + [C.c_int32] * 3 + [_fp]),
     "bdn_mse_heads_forward": (C.c_int, [C.POINTER(_fp), C.c_int32, C.c_int32, C.c_int64, _fp, _fp, C.POINTER(_fp), _fp, _fp]),
     "bdn_mse_heads_backward": (C.c_int, [C.POINTER(_fp), C.c_int32, C.c_int32, C.c_int64, _fp, _fp, C.POINTER(_fp), _fp]),
     "bdn_adam_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libblindno_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["spectral.cu", "pointwise.cu", "fused1d.cu", "tc_gemm.cu", "tc_layer.cu", "api.cu"]
+SOURCES = ["spectral.cu", "pointwise.cu", "fused1d.cu", "tc_gemm.cu", "tc_layer.cu", "bagattn.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

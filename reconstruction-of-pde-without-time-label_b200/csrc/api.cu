@@ -928,6 +928,40 @@ int bdn_nio_tail_backward(const float* g, const float* basis, const float* wbar_
   return check_cuda("bdn_nio_tail_backward");
 }
 
+size_t bdn_bag_attention_saved_floats(int32_t n_bags, int32_t n_keep) {
+  return (n_bags < 1 || n_keep < 1 || n_keep > 128) ? 0 : bagattn_saved_floats(n_bags, n_keep);
+}
+size_t bdn_bag_attention_workspace_floats(int32_t n_bags, int32_t n_keep) {
+  return (n_bags < 1 || n_keep < 1 || n_keep > 128) ? 0 : bagattn_backward_ws_floats(n_bags, n_keep);
+}
+
+static int check_bag_attention(int32_t n_bags, int32_t n_keep, int32_t dim) {
+  if (n_bags < 0 || n_keep < 1 || dim < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
+  if (n_keep > 128) return set_error(BDN_ERR_UNSUPPORTED, "bag of %d snapshots > 128 not built", n_keep);
+  return BDN_OK;
+}
+
+int bdn_bag_attention_mean_forward(const float* x, const float* ln_w, const float* ln_b, float* out, float* saved,
+                                   int32_t n_bags, int32_t n_keep, int32_t dim, float eps, void* stream) {
+  int rc = check_bag_attention(n_bags, n_keep, dim);
+  if (rc != BDN_OK) return rc;
+  if (n_bags == 0) return BDN_OK;
+  if (!x || !ln_w || !ln_b || !out || !saved) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  launch_bagattn_forward(x, ln_w, ln_b, out, saved, n_bags, n_keep, dim, eps, (cudaStream_t)stream);
+  return check_cuda("bdn_bag_attention_mean_forward");
+}
+
+int bdn_bag_attention_mean_backward(const float* x, const float* g, const float* ln_w, const float* saved, float* g_x,
+                                    float* g_ln_w_per_bag, float* ws, int32_t n_bags, int32_t n_keep, int32_t dim,
+                                    void* stream) {
+  int rc = check_bag_attention(n_bags, n_keep, dim);
+  if (rc != BDN_OK) return rc;
+  if (n_bags == 0) return BDN_OK;
+  if (!x || !g || !ln_w || !saved || !g_x || !g_ln_w_per_bag || !ws) return set_error(BDN_ERR_INVALID, "null pointer argument");
+  launch_bagattn_backward(x, g, ln_w, saved, g_x, g_ln_w_per_bag, ws, n_bags, n_keep, dim, (cudaStream_t)stream);
+  return check_cuda("bdn_bag_attention_mean_backward");
+}
+
 int bdn_mse_heads_forward(const float* const* outs, int32_t n_heads, int32_t c, int64_t npix, const float* target,
                           float* loss, float* const* g_outs, void* scratch, void* stream) {
   if (n_heads < 1 || n_heads > MSE_MAX_HEADS || c < 1 || npix < 1) return set_error(BDN_ERR_INVALID, "bad sizes");

@@ -1,0 +1,476 @@
+// Bag attention + bag mean of the BlinDNO models in a handful of small launches per U-Net level, without ever forming
+// an [L, D] intermediate:
+//
+//   TemporalSelfAttention.forward  2d_FPE/NIOModules.py:1063-1083   (tokens = flattened feature maps, no projections)
+//       S = X X^T / sqrt(D),  A = softmax(S),  O = A X + X,  Y = LayerNorm_D(O)
+//   followed by  .mean(dim=1)      2d_FPE/NIOModules.py:1153-1170   (PermInvUNet_attn.forward: h_att.mean, skip_att.mean)
+//
+// X is [L, D] per bag (L <= 128 snapshots, D = C*H*W up to a few thousand).  Everything between the two passes over X
+// lives in L x L matrices: with M = A + I, m_l = mean_d X_ld and the CENTERED Gram matrix Gc = (X - m 1^T)(X - m 1^T)^T
+//   S        = (Gc + D m m^T) / sqrt(D)
+//   mu_l     = (M m)_l                       row means of O
+//   var_l    = (M Gc M^T)_ll / D             row variances of O (a sum of squares: no cancellation)
+//   r_l      = 1 / sqrt(var_l + eps)
+//   out_d    = gamma_d / L * (sum_l' v_l' X_l'd - c) + beta_d,     v = M^T r,  c = sum_l r_l mu_l
+// so the forward is: row means -> centered Gram (one pass over X) -> L x L algebra (one block per bag) -> weighted
+// column sum (one pass over X).  Backward, with h_d = g_d gamma_d / L, hbar = mean_d h, w' = X h:
+//   p_l   = r_l / D * ((M w')_l - mu_l sum_d h_d),   a_l = r_l^2 p_l,   w = w' - hbar D m
+//   dA    = r w^T - diag(a) (M Gc),   dS = A .* (dA - rowsum(A .* dA))
+//   dX    = K X + v (h - hbar)^T + z 1^T,   K = -M^T diag(a) M + (dS + dS^T) / sqrt(D),   z = M^T (a .* mu)
+// i.e. one pass for w' (and the LayerNorm parameter gradients), L x L algebra, one pass for dX.
+#include "bdn_internal.cuh"
+
+#include <cmath>
+
+namespace bdn {
+
+constexpr int BA_MAXL = 128;
+constexpr int BA_DC = 64;        // columns of X per shared-memory chunk
+
+// ---------------------------------------------------------------------------
+// row means: m[b, l] = mean_d x[b, l, d]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ba_rowmean_kernel(const float* __restrict__ x, float* __restrict__ m, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8];
+  const float* row = x + (size_t)blockIdx.x * D;
+  float s = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) s += __ldg(row + d);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    m[blockIdx.x] = t / (float)D;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// centered Gram matrix: Gc[b, l, l'] += sum_d (x_ld - m_l)(x_l'd - m_l')   (Gc zeroed by the caller)
+// grid (blocks per bag, bags); a block loops over its column chunks, a thread owns 4 x 4 tiles of (l, l')
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ba_gram_kernel(const float* __restrict__ x, const float* __restrict__ m,
+                                                      float* __restrict__ gc, int L, int LP, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) float smem[];
+  float* xt = smem;                       // [BA_DC][LP]  centered, transposed: 4 consecutive l are one float4
+  float* ms = xt + BA_DC * LP;            // [LP]
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const float* xb = x + (size_t)b * L * D;
+  for (int l = tid; l < LP; l += blockDim.x) ms[l] = l < L ? __ldg(m + b * L + l) : 0.f;
+  const int nt4 = LP >> 2, ntiles = nt4 * nt4;
+  constexpr int MAXT = (BA_MAXL / 4) * (BA_MAXL / 4) / 256;      // tiles per thread at L = 128
+  float acc[MAXT][4][4];
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+  const int nchunk = (D + BA_DC - 1) / BA_DC;
+  for (int ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    __syncthreads();                      // ms staged / previous chunk consumed
+    const int d0 = ch * BA_DC;
+    for (int i = tid; i < LP * BA_DC; i += blockDim.x) {
+      const int l = i / BA_DC, k = i - l * BA_DC;
+      const int d = d0 + k;
+      xt[k * LP + l] = (l < L && d < D) ? __ldg(xb + (size_t)l * D + d) - ms[l] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+      const int tile = tid + t * 256;
+      if (tile < ntiles) {
+        const int ti = tile / nt4, tj = tile - ti * nt4;
+#pragma unroll 4
+        for (int k = 0; k < BA_DC; ++k) {
+          const float4 a = *reinterpret_cast<const float4*>(xt + k * LP + 4 * ti);
+          const float4 c = *reinterpret_cast<const float4*>(xt + k * LP + 4 * tj);
+          const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[t][i][j] = fmaf(av[i], cv[j], acc[t][i][j]);
+        }
+      }
+    }
+  }
+  float* g = gc + (size_t)b * L * L;
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) {
+    const int tile = tid + t * 256;
+    if (tile < ntiles) {
+      const int ti = tile / nt4, tj = tile - ti * nt4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int l = 4 * ti + i, lp = 4 * tj + j;
+          if (l < L && lp < L) atomicAdd(g + l * L + lp, acc[t][i][j]);
+        }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// L x L algebra of the forward: one block per bag
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) ba_small_fwd_kernel(const float* __restrict__ gc, const float* __restrict__ m,
+                                                           float* __restrict__ a_out, float* __restrict__ r_out,
+                                                           float* __restrict__ mu_out, float* __restrict__ v_out,
+                                                           float* __restrict__ c_out, int L, int LP, int D, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) float smem[];
+  float* G = smem;                 // [L][LP] centered Gram
+  float* M = G + L * LP;           // [L][LP] A, then A + I
+  float* ms = M + L * LP;          // [LP]
+  float* rs = ms + LP;             // [LP]
+  float* mus = rs + LP;            // [LP]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const float* g = gc + (size_t)b * L * L;
+  for (int i = tid; i < L * L; i += blockDim.x) {
+    const int l = i / L, lp = i - l * L;
+    G[l * LP + lp] = __ldg(g + i);
+  }
+  for (int l = tid; l < LP; l += blockDim.x) ms[l] = l < L ? __ldg(m + b * L + l) : 0.f;
+  __syncthreads();
+  const float inv_sqrt_d = rsqrtf((float)D), fd = (float)D;
+  // softmax rows (warp per row), M = A + I, mu = M m
+  for (int l = warp; l < L; l += nw) {
+    float mx = -INFINITY;
+    for (int lp = lane; lp < L; lp += 32) {
+      const float s = (G[l * LP + lp] + fd * ms[l] * ms[lp]) * inv_sqrt_d;
+      M[l * LP + lp] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int lp = lane; lp < L; lp += 32) {
+      const float e = expf(M[l * LP + lp] - mx);
+      M[l * LP + lp] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    float mu = 0.f;
+    for (int lp = lane; lp < L; lp += 32) {
+      const float a = M[l * LP + lp] * inv;
+      a_out[((size_t)b * L + l) * L + lp] = a;
+      const float mm = a + (lp == l ? 1.0f : 0.f);
+      M[l * LP + lp] = mm;
+      mu = fmaf(mm, ms[lp], mu);
+    }
+    mu = warp_sum(mu);
+    if (lane == 0) mus[l] = mu;
+  }
+  __syncthreads();
+  // var_l = (M Gc M^T)_ll / D: t_j = sum_k M_lk Gc_kj (lane owns columns j), then dot with M_l.
+  for (int l = warp; l < L; l += nw) {
+    float q = 0.f;
+    for (int j = lane; j < L; j += 32) {
+      float t = 0.f;
+      for (int k = 0; k < L; ++k) t = fmaf(M[l * LP + k], G[k * LP + j], t);
+      q = fmaf(t, M[l * LP + j], q);
+    }
+    q = warp_sum(q);
+    if (lane == 0) rs[l] = rsqrtf(fmaxf(q, 0.f) / fd + eps);
+  }
+  __syncthreads();
+  for (int lp = tid; lp < L; lp += blockDim.x) {
+    float v = 0.f;
+    for (int l = 0; l < L; ++l) v = fmaf(rs[l], M[l * LP + lp], v);
+    v_out[b * L + lp] = v;
+    r_out[b * L + lp] = rs[lp];
+    mu_out[b * L + lp] = mus[lp];
+  }
+  if (warp == 0) {
+    float c = 0.f;
+    for (int l = lane; l < L; l += 32) c = fmaf(rs[l], mus[l], c);
+    c = warp_sum(c);
+    if (lane == 0) c_out[b] = c;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// out[b, d] = gamma_d / L * (sum_l v_l x_ld - c) + beta_d
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ba_out_kernel(const float* __restrict__ x, const float* __restrict__ v,
+                                                     const float* __restrict__ c, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float* __restrict__ out, int L, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float vs[BA_MAXL];
+  const int b = blockIdx.y;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) vs[l] = __ldg(v + b * L + l);
+  __syncthreads();
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float* xb = x + (size_t)b * L * D + d;
+  float s = 0.f;
+#pragma unroll 4
+  for (int l = 0; l < L; ++l) s = fmaf(vs[l], __ldg(xb + (size_t)l * D), s);
+  out[(size_t)b * D + d] = fmaf(__ldg(gamma + d) / (float)L, s - __ldg(c + b), __ldg(beta + d));
+}
+
+// ---------------------------------------------------------------------------
+// backward pass 1: w'[b, l] += sum_d x_ld h_d, hsum[b] += sum_d h_d, dgamma[b, d] = g_d u_d   (w', hsum zeroed by the caller)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ba_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                         const float* __restrict__ v, const float* __restrict__ c,
+                                                         const float* __restrict__ gamma, float* __restrict__ wp,
+                                                         float* __restrict__ hsum, float* __restrict__ dgamma, int L, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float vs[BA_MAXL], wacc[BA_MAXL];
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) { vs[l] = __ldg(v + b * L + l); wacc[l] = 0.f; }
+  __syncthreads();
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = d < D;
+  const float* xb = x + (size_t)b * L * D + (live ? d : 0);
+  const float gd = live ? __ldg(g + (size_t)b * D + d) : 0.f;
+  const float h = live ? gd * __ldg(gamma + d) / (float)L : 0.f;
+  float s = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const float xv = live ? __ldg(xb + (size_t)l * D) : 0.f;
+    s = fmaf(vs[l], xv, s);
+    const float t = warp_sum(xv * h);
+    if (lane == 0) atomicAdd(&wacc[l], t);
+  }
+  if (live) dgamma[(size_t)b * D + d] = gd * (s - __ldg(c + b)) / (float)L;
+  const float hs = warp_sum(h);
+  if (lane == 0) atomicAdd(hsum + b, hs);
+  __syncthreads();
+  for (int l = threadIdx.x; l < L; l += blockDim.x) atomicAdd(wp + b * L + l, wacc[l]);
+}
+
+// ---------------------------------------------------------------------------
+// L x L algebra of the backward: one block per bag.  Outputs K^T ([l'][l], for the dX pass), z, hbar.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) ba_small_bwd_kernel(const float* __restrict__ gc, const float* __restrict__ a_in,
+                                                           const float* __restrict__ m, const float* __restrict__ r,
+                                                           const float* __restrict__ mu, const float* __restrict__ wp,
+                                                           const float* __restrict__ hsum, float* __restrict__ kt_out,
+                                                           float* __restrict__ z_out, float* __restrict__ hbar_out, int L,
+                                                           int LP, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) float smem[];
+  float* G = smem;                 // [L][LP] centered Gram
+  float* M = G + L * LP;           // [L][LP] A + I
+  float* T = M + L * LP;           // [L][LP] M Gc -> dA -> dS
+  float* ms = T + L * LP;          // [LP]
+  float* rs = ms + LP;
+  float* mus = rs + LP;
+  float* ws = mus + LP;            // w = w' - hbar D m
+  float* as = ws + LP;             // a_l = r_l^2 p_l
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const float fd = (float)D, inv_sqrt_d = rsqrtf(fd);
+  for (int i = tid; i < L * L; i += blockDim.x) {
+    const int l = i / L, lp = i - l * L;
+    G[l * LP + lp] = __ldg(gc + (size_t)b * L * L + i);
+    M[l * LP + lp] = __ldg(a_in + (size_t)b * L * L + i) + (l == lp ? 1.0f : 0.f);
+  }
+  const float hs = __ldg(hsum + b), hbar = hs / fd;
+  for (int l = tid; l < L; l += blockDim.x) {
+    ms[l] = __ldg(m + b * L + l);
+    rs[l] = __ldg(r + b * L + l);
+    mus[l] = __ldg(mu + b * L + l);
+    ws[l] = __ldg(wp + b * L + l);          // w' for now
+  }
+  __syncthreads();
+  // p_l = r_l / D ((M w')_l - mu_l hsum);  a_l = r_l^2 p_l
+  for (int l = warp; l < L; l += nw) {
+    float s = 0.f;
+    for (int k = lane; k < L; k += 32) s = fmaf(M[l * LP + k], ws[k], s);
+    s = warp_sum(s);
+    if (lane == 0) as[l] = rs[l] * rs[l] * rs[l] / fd * (s - mus[l] * hs);
+  }
+  __syncthreads();
+  for (int l = tid; l < L; l += blockDim.x) ws[l] -= hbar * fd * ms[l];
+  // T = M Gc (row l by warp, lane owns columns)
+  for (int l = warp; l < L; l += nw)
+    for (int j = lane; j < L; j += 32) {
+      float t = 0.f;
+      for (int k = 0; k < L; ++k) t = fmaf(M[l * LP + k], G[k * LP + j], t);
+      T[l * LP + j] = t;
+    }
+  __syncthreads();
+  // dA = r w^T - diag(a) T;  dS = A .* (dA - rowsum(A .* dA))    (A = M - I)
+  for (int l = warp; l < L; l += nw) {
+    float dot = 0.f;
+    for (int j = lane; j < L; j += 32) {
+      const float da = rs[l] * ws[j] - as[l] * T[l * LP + j];
+      const float a = M[l * LP + j] - (j == l ? 1.0f : 0.f);
+      T[l * LP + j] = da;
+      dot = fmaf(a, da, dot);
+    }
+    dot = warp_sum(dot);
+    for (int j = lane; j < L; j += 32) {
+      const float a = M[l * LP + j] - (j == l ? 1.0f : 0.f);
+      T[l * LP + j] = a * (T[l * LP + j] - dot);
+    }
+  }
+  __syncthreads();
+  // K_{ij} = -sum_l a_l M_li M_lj + (dS_ij + dS_ji) / sqrt(D);  stored transposed: kt[j][i] = K_ij
+  for (int idx = tid; idx < L * L; idx += blockDim.x) {
+    const int i = idx / L, j = idx - i * L;
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s = fmaf(as[l] * M[l * LP + i], M[l * LP + j], s);
+    kt_out[((size_t)b * L + j) * L + i] = (T[i * LP + j] + T[j * LP + i]) * inv_sqrt_d - s;
+  }
+  for (int i = tid; i < L; i += blockDim.x) {
+    float z = 0.f;
+    for (int l = 0; l < L; ++l) z = fmaf(M[l * LP + i], as[l] * mus[l], z);
+    z_out[b * L + i] = z;
+  }
+  if (tid == 0) hbar_out[b] = hbar;
+}
+
+// ---------------------------------------------------------------------------
+// backward pass 2: dx[b, l, d] = sum_l' K_ll' x_l'd + v_l (h_d - hbar) + z_l
+// block = 64 columns x 4 row groups; K^T and the X chunk in shared memory
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ba_dx_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                    const float* __restrict__ gamma, const float* __restrict__ kt,
+                                                    const float* __restrict__ v, const float* __restrict__ z,
+                                                    const float* __restrict__ hbar, float* __restrict__ dx, int L, int LP, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) float smem[];
+  float* KT = smem;                // [L][LP]: KT[l'][l] = K_ll'
+  float* xs = KT + L * LP;         // [L][BA_DC]
+  float* vs = xs + L * BA_DC;      // [LP]
+  float* zs = vs + LP;             // [LP]
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < L * LP; i += blockDim.x) {
+    const int lp = i / LP, l = i - lp * LP;
+    KT[i] = l < L ? __ldg(kt + ((size_t)b * L + lp) * L + l) : 0.f;
+  }
+  for (int l = tid; l < LP; l += blockDim.x) {
+    vs[l] = l < L ? __ldg(v + b * L + l) : 0.f;
+    zs[l] = l < L ? __ldg(z + b * L + l) : 0.f;
+  }
+  const int d0 = blockIdx.x * BA_DC;
+  const float* xb = x + (size_t)b * L * D;
+  for (int i = tid; i < L * BA_DC; i += blockDim.x) {
+    const int l = i / BA_DC, k = i - l * BA_DC;
+    xs[i] = d0 + k < D ? __ldg(xb + (size_t)l * D + d0 + k) : 0.f;
+  }
+  __syncthreads();
+  const int k = tid & (BA_DC - 1), grp = tid / BA_DC;        // column, row group (4 groups)
+  const int d = d0 + k;
+  const float hd = d < D ? __ldg(g + (size_t)b * D + d) * __ldg(gamma + d) / (float)L - __ldg(hbar + b) : 0.f;
+  const int nt4 = LP >> 2;
+  for (int t = grp; t < nt4; t += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int lp = 0; lp < L; ++lp) {
+      const float4 kk = *reinterpret_cast<const float4*>(KT + lp * LP + 4 * t);
+      const float xv = xs[lp * BA_DC + k];
+      acc[0] = fmaf(kk.x, xv, acc[0]);
+      acc[1] = fmaf(kk.y, xv, acc[1]);
+      acc[2] = fmaf(kk.z, xv, acc[2]);
+      acc[3] = fmaf(kk.w, xv, acc[3]);
+    }
+    if (d < D) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int l = 4 * t + i;
+        if (l < L) dx[((size_t)b * L + l) * D + d] = acc[i] + fmaf(vs[l], hd, zs[l]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+static int ba_lp(int L) { return (L + 3) & ~3; }
+
+size_t bagattn_saved_floats(int n_bags, int L) {      // m, r, mu, v [L] each, c [1 padded to 4], Gc, A [L, L] per bag
+  return (size_t)n_bags * ((size_t)4 * L + 4 + 2 * (size_t)L * L);
+}
+
+void launch_bagattn_forward(const float* x, const float* gamma, const float* beta, float* out, float* saved, int n_bags, int L,
+                            int D, float eps, cudaStream_t st) {
+  const int LP = ba_lp(L);
+  float* m = saved;
+  float* r = m + (size_t)n_bags * L;
+  float* mu = r + (size_t)n_bags * L;
+  float* v = mu + (size_t)n_bags * L;
+  float* c = v + (size_t)n_bags * L;
+  float* gc = c + (size_t)n_bags * 4;
+  float* a = gc + (size_t)n_bags * L * L;
+  cudaMemsetAsync(gc, 0, (size_t)n_bags * L * L * sizeof(float), st);
+  {
+    LaunchScope scope("bagattn_rowmean", st);
+    launch_k(ba_rowmean_kernel, dim3(n_bags * L), dim3(256), 0, st, x, m, D);
+  }
+  {
+    LaunchScope scope("bagattn_gram", st);
+    const int nchunk = ceil_div(D, BA_DC);
+    const int per_bag = nchunk < 16 ? nchunk : 16;
+    const size_t smem = (size_t)(BA_DC * LP + LP) * sizeof(float);
+    cudaFuncSetAttribute(ba_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    launch_k(ba_gram_kernel, dim3(per_bag, n_bags), dim3(256), smem, st, x, (const float*)m, gc, L, LP, D);
+  }
+  {
+    LaunchScope scope("bagattn_small_fwd", st);
+    const size_t smem = (size_t)(2 * L * LP + 3 * LP) * sizeof(float);
+    cudaFuncSetAttribute(ba_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    launch_k(ba_small_fwd_kernel, dim3(n_bags), dim3(512), smem, st, (const float*)gc, (const float*)m, a, r, mu, v, c, L, LP, D, eps);
+  }
+  {
+    LaunchScope scope("bagattn_out", st);
+    launch_k(ba_out_kernel, dim3(ceil_div(D, 256), n_bags), dim3(256), 0, st, x, (const float*)v, (const float*)c, gamma, beta, out,
+             L, D);
+  }
+}
+
+size_t bagattn_backward_ws_floats(int n_bags, int L) {   // w' [L], z [L], hsum, hbar (padded), K^T [L, L] per bag
+  return (size_t)n_bags * ((size_t)2 * L + 8 + (size_t)L * L);
+}
+
+void launch_bagattn_backward(const float* x, const float* g, const float* gamma, const float* saved, float* dx, float* dgamma,
+                             float* ws, int n_bags, int L, int D, cudaStream_t st) {
+  const int LP = ba_lp(L);
+  const float* m = saved;
+  const float* r = m + (size_t)n_bags * L;
+  const float* mu = r + (size_t)n_bags * L;
+  const float* v = mu + (size_t)n_bags * L;
+  const float* c = v + (size_t)n_bags * L;
+  const float* gc = c + (size_t)n_bags * 4;
+  const float* a = gc + (size_t)n_bags * L * L;
+  float* wp = ws;
+  float* z = wp + (size_t)n_bags * L;
+  float* hsum = z + (size_t)n_bags * L;
+  float* hbar = hsum + (size_t)n_bags * 4;
+  float* kt = hbar + (size_t)n_bags * 4;
+  cudaMemsetAsync(ws, 0, ((size_t)n_bags * 2 * L + (size_t)n_bags * 8) * sizeof(float), st);
+  {
+    LaunchScope scope("bagattn_bwd_vec", st);
+    launch_k(ba_bwd_vec_kernel, dim3(ceil_div(D, 256), n_bags), dim3(256), 0, st, x, g, v, c, gamma, wp, hsum, dgamma, L, D);
+  }
+  {
+    LaunchScope scope("bagattn_small_bwd", st);
+    const size_t smem = (size_t)(3 * L * LP + 5 * LP) * sizeof(float);
+    cudaFuncSetAttribute(ba_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    launch_k(ba_small_bwd_kernel, dim3(n_bags), dim3(512), smem, st, gc, a, m, r, mu, (const float*)wp, (const float*)hsum, kt, z,
+             hbar, L, LP, D);
+  }
+  {
+    LaunchScope scope("bagattn_dx", st);
+    const size_t smem = (size_t)(L * LP + L * BA_DC + 2 * LP) * sizeof(float);
+    cudaFuncSetAttribute(ba_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    launch_k(ba_dx_kernel, dim3(ceil_div(D, BA_DC), n_bags), dim3(256), smem, st, x, g, gamma, (const float*)kt, v, (const float*)z,
+             (const float*)hbar, dx, L, LP, D);
+  }
+}
+
+}  // namespace bdn

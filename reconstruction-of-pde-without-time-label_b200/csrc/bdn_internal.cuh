@@ -158,6 +158,13 @@ void launch_nio_tail(const float* w, const float* basis, const float* b0, const 
                      float* out, float* wbar, int n_bags, int L, int p, int npix, int gd, int width, cudaStream_t st);
 void launch_nio_tail_bwd(const float* g, const float* basis, const float* wbar, const float* w0, float* g_wbar, float* g_basis,
                          float* g_b0, float* g_w, int n_bags, int L, int p, int npix, int gd, int width, cudaStream_t st);
+// bag attention + bag mean (bagattn.cu): TemporalSelfAttention + .mean(dim=1) of the BlinDNO models
+size_t bagattn_saved_floats(int n_bags, int L);
+size_t bagattn_backward_ws_floats(int n_bags, int L);
+void launch_bagattn_forward(const float* x, const float* gamma, const float* beta, float* out, float* saved, int n_bags, int L,
+                            int D, float eps, cudaStream_t st);
+void launch_bagattn_backward(const float* x, const float* g, const float* gamma, const float* saved, float* dx, float* dgamma,
+                             float* ws, int n_bags, int L, int D, cudaStream_t st);
 // MSE over the concatenated head outputs without the concatenation (forward: deterministic two-level sum; backward)
 constexpr int MSE_MAX_HEADS = 4;
 struct MseHeadsArgs {

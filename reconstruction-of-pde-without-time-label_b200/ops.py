@@ -21,6 +21,8 @@ FLOP runs in libblindno_b200.so.  There is no CPU implementation: the CPU dispat
     bag_project_pool_lift(z, n_keep, fc1.., grid, fc0..)     projection of every snapshot, then the above
     deeponet_pool_contract_lift(w, basis, b0, grid, fc0..)   DeepOnetNoBiasOrg.forward + bag mean + lift
                                                              DeepONetModules.py:142-151, 1d_GPE/NIOModules.py:209-219
+    bag_attention_mean(x, ln_w, ln_b, eps)                   TemporalSelfAttention.forward + .mean(dim=1)
+                                                             2d_FPE/NIOModules.py:1063-1083, :1153-1170
     heads_mse(outs, target)                                  criterion(model(inputs, grid), outputs), MSELoss over the
                                                              concatenated head outputs      2d_FPE/train_fno.py:116,146-147
 
@@ -37,7 +39,7 @@ import torch
 from . import _lib
 from ._lib import FnoParams, FnoShape, LiftInput, PREC_FP32, PREC_TF32, PREC_TF32X3, SpectralShape, check, pad_amount
 
-__all__ = ["FnoSpec", "set_precision", "stage_wfwd", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat", "heads_mse", "heads_mse_grads",
+__all__ = ["FnoSpec", "set_precision", "stage_wfwd", "fno_apply", "spectral_conv", "bag_pool_lift", "adam_step_flat", "heads_mse", "heads_mse_grads", "bag_attention_mean",
            "kernel_launches", "fno_lift_pad", "fno_layer", "fno_project", "OP_NAMES",
            "PREC_FP32", "PREC_TF32", "PREC_TF32X3"]
 
@@ -1025,6 +1027,85 @@ _define_composite("bag_project_pool_lift",
 _define_composite("deeponet_pool_contract_lift",
                   "(Tensor w, Tensor basis, Tensor b0, Tensor grid, Tensor fc0_w, Tensor fc0_b) -> Tensor",
                   _deeponet_pool_contract_lift)
+
+
+# ---------------------------------------------------------------------------------------------
+# bag attention + bag mean of the BlinDNO models (no [L, D] intermediates)
+# ---------------------------------------------------------------------------------------------
+BAG_ATTENTION_MAX_KEEP = 128
+
+
+def _bag_attention_dims(x, ln_w, ln_b):
+    if x.dim() != 3:
+        raise RuntimeError(f"bag_attention_mean expects tokens [bags, keep, dim], got {tuple(x.shape)}")
+    n_bags, n_keep, dim = x.shape
+    if ln_w.shape != (dim,) or ln_b.shape != (dim,):
+        raise RuntimeError("bag_attention_mean: LayerNorm weight / bias must have one entry per token feature")
+    if n_keep > BAG_ATTENTION_MAX_KEEP:
+        raise RuntimeError(f"bag_attention_mean: bags of more than {BAG_ATTENTION_MAX_KEEP} snapshots are not built")
+    return n_bags, n_keep, dim
+
+
+def _bag_attention_forward_cuda(x, ln_w, ln_b, eps):
+    _need_cuda(x, ln_w, ln_b)
+    xc, wc, bc = _f32c(x), _f32c(ln_w), _f32c(ln_b)
+    n_bags, n_keep, dim = _bag_attention_dims(xc, wc, bc)
+    L = _lib.lib()
+    out = torch.empty(n_bags, dim, dtype=torch.float32, device=xc.device)
+    saved = torch.empty(L.bdn_bag_attention_saved_floats(max(n_bags, 1), n_keep), dtype=torch.float32, device=xc.device)
+    with torch.cuda.device(xc.device):
+        check(L.bdn_bag_attention_mean_forward(_ptr(xc), _ptr(wc), _ptr(bc), _ptr(out), _ptr(saved), n_bags, n_keep, dim,
+                                               float(eps), _stream()), "bdn_bag_attention_mean_forward")
+    return out, saved
+
+
+def _bag_attention_backward_cuda(g, x, ln_w, saved):
+    _need_cuda(g, x, ln_w, saved)
+    gc, xc, wc = _f32c(g), _f32c(x), _f32c(ln_w)
+    n_bags, n_keep, dim = xc.shape
+    L = _lib.lib()
+    gx = torch.empty_like(xc)
+    gw_bag = torch.empty(n_bags, dim, dtype=torch.float32, device=xc.device)
+    ws = torch.empty(L.bdn_bag_attention_workspace_floats(max(n_bags, 1), n_keep), dtype=torch.float32, device=xc.device)
+    with torch.cuda.device(xc.device):
+        check(L.bdn_bag_attention_mean_backward(_ptr(xc), _ptr(gc), _ptr(wc), _ptr(saved), _ptr(gx), _ptr(gw_bag), _ptr(ws),
+                                                n_bags, n_keep, dim, _stream()), "bdn_bag_attention_mean_backward")
+    return gx, gw_bag
+
+
+def _bag_attention_fake(x, ln_w, ln_b, eps):
+    n_bags, n_keep, dim = _bag_attention_dims(x, ln_w, ln_b)
+    return x.new_empty(n_bags, dim), x.new_empty(n_bags * (4 * n_keep + 4 + 2 * n_keep * n_keep))
+
+
+_define("bag_attention_mean_forward", "(Tensor x, Tensor ln_w, Tensor ln_b, float eps) -> (Tensor, Tensor)",
+        _bag_attention_forward_cuda, _bag_attention_fake)
+_define("bag_attention_mean_backward", "(Tensor g, Tensor x, Tensor ln_w, Tensor saved) -> (Tensor, Tensor)",
+        _bag_attention_backward_cuda, lambda g, x, ln_w, saved: (torch.empty_like(x), x.new_empty(x.shape[0], x.shape[2])))
+
+
+def _bag_attention_setup(ctx, inputs, output):
+    x, ln_w, ln_b, eps = inputs
+    ctx.save_for_backward(x, ln_w, output[1])
+    ctx.mark_non_differentiable(output[1])
+
+
+def _bag_attention_bwd(ctx, g, _g_saved):
+    x, ln_w, saved = ctx.saved_tensors
+    gx, gw_bag = _OPS.bag_attention_mean_backward(g, x, ln_w, saved)
+    need = ctx.needs_input_grad
+    return (gx if need[0] else None, gw_bag.sum(dim=0) if need[1] else None, g.sum(dim=0) if need[2] else None, None)
+
+
+torch.library.register_autograd(f"{NS}::bag_attention_mean_forward", _bag_attention_bwd, setup_context=_bag_attention_setup,
+                                lib=_LIB)
+
+
+def bag_attention_mean(x, ln_w, ln_b, eps: float = 1e-5):
+    """``LayerNorm(softmax(x x^T / sqrt(D)) x + x).mean(dim=1)`` for tokens x [bags, keep, D] (TemporalSelfAttention followed
+    by the bag mean, 2d_FPE/NIOModules.py:1063-1083, :1153-1170) -> [bags, D]; everything between the two passes over x is
+    keep x keep algebra (csrc/bagattn.cu)."""
+    return _OPS.bag_attention_mean_forward(x, ln_w, ln_b, eps)[0]
 
 
 # ---------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@ import math
 import torch
 import torch.nn as nn
 
+from .. import ops
 from .fno import FNO1d, FNO2d
 from .nio import _BagModel, _idx_tensor, draw_bag
 
@@ -102,9 +103,15 @@ class _PermInvUNet(_BagModel):
                 FNO1d(modes=modes, width=width, n_layers=3, input_dim=width, output_dim=1, device=device)
             setattr(self, name, head)
 
+    fused_attention = True      # CUDA: attention + bag mean through ops.bag_attention_mean (bags of <= 128 snapshots)
+
     def _bag_mean(self, level: int, maps, n_bags: int):
         seq = maps.reshape(n_bags, -1, *maps.shape[1:])
-        return self.temp_atts[level](seq).mean(dim=1)
+        att = self.temp_atts[level]
+        if self.fused_attention and seq.is_cuda and seq.shape[1] <= ops.BAG_ATTENTION_MAX_KEEP:
+            out = ops.bag_attention_mean(seq.reshape(n_bags, seq.shape[1], att.D), att.norm.weight, att.norm.bias, att.norm.eps)
+            return out.reshape(n_bags, *maps.shape[1:])
+        return att(seq).mean(dim=1)
 
     accepts_idx = True
 

@@ -150,6 +150,18 @@ def test_pooled_tails_detach_fc0_on_meta():
     assert w.grad.shape == w.shape and basis.grad.shape == basis.shape and b0.grad is not None and fc0_w.grad is None
 
 
+def test_bag_attention_mean_on_meta():
+    x = torch.randn(2, 9, 40, device=META, requires_grad=True)
+    w = torch.ones(40, device=META, requires_grad=True)
+    b = torch.zeros(40, device=META, requires_grad=True)
+    y = ops.bag_attention_mean(x, w, b)
+    assert y.shape == (2, 40)
+    y.sum().backward()
+    assert x.grad.shape == x.shape and w.grad.shape == w.shape and b.grad.shape == b.shape
+    with pytest.raises(RuntimeError, match="128"):
+        ops.bag_attention_mean(torch.randn(1, 200, 8, device=META), torch.ones(8, device=META), torch.zeros(8, device=META))
+
+
 def test_heads_mse_on_meta():
     outs = [torch.randn(2, 8, 8, 1, device=META, requires_grad=True) for _ in range(2)]
     target = torch.randn(2, 8, 8, 2, device=META)

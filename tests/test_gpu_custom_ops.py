@@ -191,6 +191,30 @@ def test_heads_mse_matches_mse_loss_on_the_concatenation(n_heads, c, shape):
         assert rel_err(gk, r.grad / 3.0) < TOL
 
 
+@pytest.mark.parametrize("n_bags,n_keep,dim,shift", [(4, 75, 3721, 0.0), (2, 100, 900, 0.5), (3, 51, 144, 0.0), (1, 7, 37, 2.0),
+                                                     (2, 128, 392, 0.0)])
+def test_bag_attention_mean_vs_the_reference_formulation(n_bags, n_keep, dim, shift):
+    """TemporalSelfAttention + .mean(dim=1) (2d_FPE/NIOModules.py:1063-1083, :1153-1170) as the reference writes it, in
+    fp64, against the fused op: outputs and the gradients of the tokens and of the LayerNorm affine.  ``shift`` moves
+    the token means away from zero (the row variances come from the CENTERED Gram matrix)."""
+    g = torch.Generator().manual_seed(n_keep * 7 + dim)
+    x = torch.randn(n_bags, n_keep, dim, generator=g) * 0.7 + shift
+    ln_w = 1.0 + 0.3 * torch.randn(dim, generator=g)
+    ln_b = 0.2 * torch.randn(dim, generator=g)
+    gy = torch.randn(n_bags, dim, generator=g)
+    dev = [t.to(DEV).requires_grad_(True) for t in (x, ln_w, ln_b)]
+    got = ops.bag_attention_mean(*dev, 1e-5)
+    got.backward(gy.to(DEV))
+    ref = [t.double().requires_grad_(True) for t in (x, ln_w, ln_b)]
+    xf = ref[0]
+    attn = torch.softmax(torch.matmul(xf, xf.transpose(1, 2)) / dim ** 0.5, dim=-1)
+    want = F.layer_norm(torch.matmul(attn, xf) + xf, (dim,), ref[1], ref[2], 1e-5).mean(dim=1)
+    want.backward(gy.double())
+    assert rel_err(got, want) < TOL
+    for a, r in zip(dev, ref):
+        assert rel_err(a.grad, r.grad) < 2e-5
+
+
 def test_opcheck_schema_fake_and_autograd_registration():
     x = torch.randn(2, 3, 8, 8, device=DEV, requires_grad=True)
     w = (torch.rand(3, 3, 2, 2, 2, device=DEV) / 9).requires_grad_(True)
