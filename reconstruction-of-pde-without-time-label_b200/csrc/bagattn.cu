@@ -116,21 +116,20 @@ __global__ void __launch_bounds__(256) ba_gram_kernel(const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
-// L x L algebra of the forward: one block per bag
+// L x L algebra of the forward.  The rows of A, mu and r are independent of each other: grid (row groups, bags), a
+// block handles rows blockIdx.x, blockIdx.x + gridDim.x, ... (one warp per row) with the whole centered Gram matrix
+// in shared memory.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) ba_small_fwd_kernel(const float* __restrict__ gc, const float* __restrict__ m,
+__global__ void __launch_bounds__(256) ba_small_fwd_kernel(const float* __restrict__ gc, const float* __restrict__ m,
                                                            float* __restrict__ a_out, float* __restrict__ r_out,
-                                                           float* __restrict__ mu_out, float* __restrict__ v_out,
-                                                           float* __restrict__ c_out, int L, int LP, int D, float eps) {
+                                                           float* __restrict__ mu_out, int L, int LP, int D, float eps) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) float smem[];
   float* G = smem;                 // [L][LP] centered Gram
-  float* M = G + L * LP;           // [L][LP] A, then A + I
-  float* ms = M + L * LP;          // [LP]
-  float* rs = ms + LP;             // [LP]
-  float* mus = rs + LP;            // [LP]
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  float* ms = G + L * LP;          // [LP]
+  float* Mrow = ms + LP;           // [warps][LP]: row l of A, then of A + I
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const float* g = gc + (size_t)b * L * L;
   for (int i = tid; i < L * L; i += blockDim.x) {
     const int l = i / L, lp = i - l * L;
@@ -139,82 +138,91 @@ __global__ void __launch_bounds__(512) ba_small_fwd_kernel(const float* __restri
   for (int l = tid; l < LP; l += blockDim.x) ms[l] = l < L ? __ldg(m + b * L + l) : 0.f;
   __syncthreads();
   const float inv_sqrt_d = rsqrtf((float)D), fd = (float)D;
-  // softmax rows (warp per row), M = A + I, mu = M m
-  for (int l = warp; l < L; l += nw) {
+  float* M = Mrow + warp * LP;
+  for (int l = blockIdx.x * nw + warp; l < L; l += gridDim.x * nw) {
+    // softmax of row l, M = A + I, mu = M m
     float mx = -INFINITY;
     for (int lp = lane; lp < L; lp += 32) {
-      const float s = (G[l * LP + lp] + fd * ms[l] * ms[lp]) * inv_sqrt_d;
-      M[l * LP + lp] = s;
-      mx = fmaxf(mx, s);
+      const float sv = (G[l * LP + lp] + fd * ms[l] * ms[lp]) * inv_sqrt_d;
+      M[lp] = sv;
+      mx = fmaxf(mx, sv);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
     for (int lp = lane; lp < L; lp += 32) {
-      const float e = expf(M[l * LP + lp] - mx);
-      M[l * LP + lp] = e;
+      const float e = expf(M[lp] - mx);
+      M[lp] = e;
       sum += e;
     }
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
     float mu = 0.f;
     for (int lp = lane; lp < L; lp += 32) {
-      const float a = M[l * LP + lp] * inv;
-      a_out[((size_t)b * L + l) * L + lp] = a;
-      const float mm = a + (lp == l ? 1.0f : 0.f);
-      M[l * LP + lp] = mm;
+      const float av = M[lp] * inv;
+      a_out[((size_t)b * L + l) * L + lp] = av;
+      const float mm = av + (lp == l ? 1.0f : 0.f);
+      M[lp] = mm;
       mu = fmaf(mm, ms[lp], mu);
     }
     mu = warp_sum(mu);
-    if (lane == 0) mus[l] = mu;
-  }
-  __syncthreads();
-  // var_l = (M Gc M^T)_ll / D: t_j = sum_k M_lk Gc_kj (lane owns columns j), then dot with M_l.
-  for (int l = warp; l < L; l += nw) {
+    __syncwarp();
+    // var_l = (M Gc M^T)_ll / D: t_j = sum_k M_lk Gc_kj (lane owns columns j), then the dot with M_l.
     float q = 0.f;
     for (int j = lane; j < L; j += 32) {
       float t = 0.f;
-      for (int k = 0; k < L; ++k) t = fmaf(M[l * LP + k], G[k * LP + j], t);
-      q = fmaf(t, M[l * LP + j], q);
+      for (int k = 0; k < L; ++k) t = fmaf(M[k], G[k * LP + j], t);
+      q = fmaf(t, M[j], q);
     }
     q = warp_sum(q);
-    if (lane == 0) rs[l] = rsqrtf(fmaxf(q, 0.f) / fd + eps);
-  }
-  __syncthreads();
-  for (int lp = tid; lp < L; lp += blockDim.x) {
-    float v = 0.f;
-    for (int l = 0; l < L; ++l) v = fmaf(rs[l], M[l * LP + lp], v);
-    v_out[b * L + lp] = v;
-    r_out[b * L + lp] = rs[lp];
-    mu_out[b * L + lp] = mus[lp];
-  }
-  if (warp == 0) {
-    float c = 0.f;
-    for (int l = lane; l < L; l += 32) c = fmaf(rs[l], mus[l], c);
-    c = warp_sum(c);
-    if (lane == 0) c_out[b] = c;
+    if (lane == 0) {
+      r_out[b * L + l] = rsqrtf(fmaxf(q, 0.f) / fd + eps);
+      mu_out[b * L + l] = mu;
+    }
+    __syncwarp();
   }
 }
 
 // ---------------------------------------------------------------------------
-// out[b, d] = gamma_d / L * (sum_l v_l x_ld - c) + beta_d
+// out[b, d] = gamma_d / L * (sum_l v_l x_ld - c) + beta_d,  v = M^T r,  c = sum_l r_l mu_l  (every block forms v and c
+// from A, r, mu: L^2 multiply-adds; block (0, b) also saves them for the backward)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ba_out_kernel(const float* __restrict__ x, const float* __restrict__ v,
-                                                     const float* __restrict__ c, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, float* __restrict__ out, int L, int D) {
+__global__ void __launch_bounds__(256) ba_out_kernel(const float* __restrict__ x, const float* __restrict__ a_in,
+                                                     const float* __restrict__ r, const float* __restrict__ mu,
+                                                     float* __restrict__ v_out, float* __restrict__ c_out,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     float* __restrict__ out, int L, int D) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float vs[BA_MAXL];
-  const int b = blockIdx.y;
-  for (int l = threadIdx.x; l < L; l += blockDim.x) vs[l] = __ldg(v + b * L + l);
+  __shared__ float vs[BA_MAXL], rs[BA_MAXL], cs;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int l = tid; l < L; l += blockDim.x) rs[l] = __ldg(r + b * L + l);
   __syncthreads();
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int lp = tid; lp < L; lp += blockDim.x) {
+    float v = rs[lp];                                  // the + I of M = A + I
+    const float* col = a_in + (size_t)b * L * L + lp;
+#pragma unroll 8
+    for (int l = 0; l < L; ++l) v = fmaf(rs[l], __ldg(col + (size_t)l * L), v);      // (independent loads: keep 8 in flight)
+    vs[lp] = v;
+    if (blockIdx.x == 0) v_out[b * L + lp] = v;
+  }
+  if (tid < 32) {
+    float c = 0.f;
+    for (int l = tid; l < L; l += 32) c = fmaf(rs[l], __ldg(mu + b * L + l), c);
+    c = warp_sum(c);
+    if (tid == 0) {
+      cs = c;
+      if (blockIdx.x == 0) c_out[b] = c;
+    }
+  }
+  __syncthreads();
+  const int d = blockIdx.x * blockDim.x + tid;
   if (d >= D) return;
   const float* xb = x + (size_t)b * L * D + d;
   float s = 0.f;
 #pragma unroll 4
   for (int l = 0; l < L; ++l) s = fmaf(vs[l], __ldg(xb + (size_t)l * D), s);
-  out[(size_t)b * D + d] = fmaf(__ldg(gamma + d) / (float)L, s - __ldg(c + b), __ldg(beta + d));
+  out[(size_t)b * D + d] = fmaf(__ldg(gamma + d) / (float)L, s - cs, __ldg(beta + d));
 }
 
 // ---------------------------------------------------------------------------
@@ -236,11 +244,32 @@ __global__ void __launch_bounds__(256) ba_bwd_vec_kernel(const float* __restrict
   const float gd = live ? __ldg(g + (size_t)b * D + d) : 0.f;
   const float h = live ? gd * __ldg(gamma + d) / (float)L : 0.f;
   float s = 0.f;
-  for (int l = 0; l < L; ++l) {
-    const float xv = live ? __ldg(xb + (size_t)l * D) : 0.f;
-    s = fmaf(vs[l], xv, s);
-    const float t = warp_sum(xv * h);
-    if (lane == 0) atomicAdd(&wacc[l], t);
+  // 32 rows at a time: a lane holds its column's 32 products, a butterfly of 31 shuffles leaves the total of row
+  // l0 + lane on every lane (a warp_sum per row would be 160 shuffles)
+  for (int l0 = 0; l0 < L; l0 += 32) {
+    float pr[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int l = l0 + i;
+      const float xv = (live && l < L) ? __ldg(xb + (size_t)l * D) : 0.f;
+      s = fmaf(l < L ? vs[l] : 0.f, xv, s);
+      pr[i] = xv * h;
+    }
+    int n = 32;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool up = (lane & off) != 0;
+      n >>= 1;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < n) {
+          const float send = up ? pr[i] : pr[i + n];
+          const float keep = up ? pr[i + n] : pr[i];
+          pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+    }
+    if (l0 + lane < L) atomicAdd(&wacc[l0 + lane], pr[0]);
   }
   if (live) dgamma[(size_t)b * D + d] = gd * (s - __ldg(c + b)) / (float)L;
   const float hs = warp_sum(h);
@@ -250,86 +279,110 @@ __global__ void __launch_bounds__(256) ba_bwd_vec_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------
-// L x L algebra of the backward: one block per bag.  Outputs K^T ([l'][l], for the dX pass), z, hbar.
+// L x L algebra of the backward, part 1 (rows independent: grid (row groups, bags), one warp per row):
+//   a_l = r_l^3 / D ((M w')_l - mu_l hsum),  T_l. = (M Gc)_l.,  dA_l. = r_l w^T - a_l T_l.,  dS_l. = A_l. .* (dA_l. - <A_l., dA_l.>)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) ba_small_bwd_kernel(const float* __restrict__ gc, const float* __restrict__ a_in,
-                                                           const float* __restrict__ m, const float* __restrict__ r,
-                                                           const float* __restrict__ mu, const float* __restrict__ wp,
-                                                           const float* __restrict__ hsum, float* __restrict__ kt_out,
-                                                           float* __restrict__ z_out, float* __restrict__ hbar_out, int L,
-                                                           int LP, int D) {
+__global__ void __launch_bounds__(256) ba_small_bwd_rows_kernel(const float* __restrict__ gc, const float* __restrict__ a_in,
+                                                                const float* __restrict__ m, const float* __restrict__ r,
+                                                                const float* __restrict__ mu, const float* __restrict__ wp,
+                                                                const float* __restrict__ hsum, float* __restrict__ ds_out,
+                                                                float* __restrict__ as_out, int L, int LP, int D) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) float smem[];
   float* G = smem;                 // [L][LP] centered Gram
-  float* M = G + L * LP;           // [L][LP] A + I
-  float* T = M + L * LP;           // [L][LP] M Gc -> dA -> dS
-  float* ms = T + L * LP;          // [LP]
-  float* rs = ms + LP;
-  float* mus = rs + LP;
-  float* ws = mus + LP;            // w = w' - hbar D m
-  float* as = ws + LP;             // a_l = r_l^2 p_l
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const float fd = (float)D, inv_sqrt_d = rsqrtf(fd);
+  float* wps = G + L * LP;         // [LP] w'
+  float* ws = wps + LP;            // [LP] w = w' - hbar D m
+  float* Mrow = ws + LP;           // [warps][LP]
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const float fd = (float)D;
   for (int i = tid; i < L * L; i += blockDim.x) {
     const int l = i / L, lp = i - l * L;
     G[l * LP + lp] = __ldg(gc + (size_t)b * L * L + i);
-    M[l * LP + lp] = __ldg(a_in + (size_t)b * L * L + i) + (l == lp ? 1.0f : 0.f);
   }
   const float hs = __ldg(hsum + b), hbar = hs / fd;
   for (int l = tid; l < L; l += blockDim.x) {
-    ms[l] = __ldg(m + b * L + l);
-    rs[l] = __ldg(r + b * L + l);
-    mus[l] = __ldg(mu + b * L + l);
-    ws[l] = __ldg(wp + b * L + l);          // w' for now
+    const float w = __ldg(wp + b * L + l);
+    wps[l] = w;
+    ws[l] = w - hbar * fd * __ldg(m + b * L + l);
   }
   __syncthreads();
-  // p_l = r_l / D ((M w')_l - mu_l hsum);  a_l = r_l^2 p_l
-  for (int l = warp; l < L; l += nw) {
+  float* M = Mrow + warp * LP;
+  for (int l = blockIdx.x * nw + warp; l < L; l += gridDim.x * nw) {
     float s = 0.f;
-    for (int k = lane; k < L; k += 32) s = fmaf(M[l * LP + k], ws[k], s);
-    s = warp_sum(s);
-    if (lane == 0) as[l] = rs[l] * rs[l] * rs[l] / fd * (s - mus[l] * hs);
-  }
-  __syncthreads();
-  for (int l = tid; l < L; l += blockDim.x) ws[l] -= hbar * fd * ms[l];
-  // T = M Gc (row l by warp, lane owns columns)
-  for (int l = warp; l < L; l += nw)
-    for (int j = lane; j < L; j += 32) {
-      float t = 0.f;
-      for (int k = 0; k < L; ++k) t = fmaf(M[l * LP + k], G[k * LP + j], t);
-      T[l * LP + j] = t;
+    for (int k = lane; k < L; k += 32) {
+      const float mm = __ldg(a_in + ((size_t)b * L + l) * L + k) + (k == l ? 1.0f : 0.f);
+      M[k] = mm;
+      s = fmaf(mm, wps[k], s);
     }
-  __syncthreads();
-  // dA = r w^T - diag(a) T;  dS = A .* (dA - rowsum(A .* dA))    (A = M - I)
-  for (int l = warp; l < L; l += nw) {
+    s = warp_sum(s);
+    const float rl = __ldg(r + b * L + l);
+    const float al = rl * rl * rl / fd * (s - __ldg(mu + b * L + l) * hs);
+    if (lane == 0) as_out[b * L + l] = al;
+    __syncwarp();
+    float dav[BA_MAXL / 32];
     float dot = 0.f;
-    for (int j = lane; j < L; j += 32) {
-      const float da = rs[l] * ws[j] - as[l] * T[l * LP + j];
-      const float a = M[l * LP + j] - (j == l ? 1.0f : 0.f);
-      T[l * LP + j] = da;
-      dot = fmaf(a, da, dot);
+#pragma unroll
+    for (int jj = 0; jj < BA_MAXL / 32; ++jj) {
+      const int j = lane + 32 * jj;
+      dav[jj] = 0.f;
+      if (j < L) {
+        float t = 0.f;
+        for (int k = 0; k < L; ++k) t = fmaf(M[k], G[k * LP + j], t);
+        const float da = rl * ws[j] - al * t;
+        dav[jj] = da;
+        dot = fmaf(M[j] - (j == l ? 1.0f : 0.f), da, dot);
+      }
     }
     dot = warp_sum(dot);
-    for (int j = lane; j < L; j += 32) {
-      const float a = M[l * LP + j] - (j == l ? 1.0f : 0.f);
-      T[l * LP + j] = a * (T[l * LP + j] - dot);
+#pragma unroll
+    for (int jj = 0; jj < BA_MAXL / 32; ++jj) {
+      const int j = lane + 32 * jj;
+      if (j < L) ds_out[((size_t)b * L + l) * L + j] = (M[j] - (j == l ? 1.0f : 0.f)) * (dav[jj] - dot);
     }
+    __syncwarp();
   }
+}
+
+// ---------------------------------------------------------------------------
+// part 2: K_ij = -sum_l a_l M_li M_lj + (dS_ij + dS_ji) / sqrt(D), stored transposed (kt[j][i] = K_ij) for the dX pass;
+// z_i = sum_l M_li a_l mu_l.  grid (row groups, bags): a block handles rows i = blockIdx.x, blockIdx.x + gridDim.x, ...
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ba_small_bwd_k_kernel(const float* __restrict__ a_in, const float* __restrict__ ds,
+                                                             const float* __restrict__ as_in, const float* __restrict__ mu,
+                                                             const float* __restrict__ hsum, float* __restrict__ kt_out,
+                                                             float* __restrict__ z_out, float* __restrict__ hbar_out, int L,
+                                                             int LP, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) float smem[];
+  float* M = smem;                 // [L][LP] A + I
+  float* as = M + L * LP;          // [LP]
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < L * L; i += blockDim.x) {
+    const int l = i / L, lp = i - l * L;
+    M[l * LP + lp] = __ldg(a_in + (size_t)b * L * L + i) + (l == lp ? 1.0f : 0.f);
+  }
+  for (int l = tid; l < L; l += blockDim.x) as[l] = __ldg(as_in + b * L + l);
   __syncthreads();
-  // K_{ij} = -sum_l a_l M_li M_lj + (dS_ij + dS_ji) / sqrt(D);  stored transposed: kt[j][i] = K_ij
-  for (int idx = tid; idx < L * L; idx += blockDim.x) {
-    const int i = idx / L, j = idx - i * L;
+  const float inv_sqrt_d = rsqrtf((float)D);
+  const float* dsb = ds + (size_t)b * L * L;
+  const int nrows = (L - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // rows blockIdx.x, + gridDim.x, ...
+  for (int idx = tid; idx < nrows * L; idx += blockDim.x) {
+    const int ri = idx / L, j = idx - ri * L, i = blockIdx.x + ri * gridDim.x;
     float s = 0.f;
+#pragma unroll 4
     for (int l = 0; l < L; ++l) s = fmaf(as[l] * M[l * LP + i], M[l * LP + j], s);
-    kt_out[((size_t)b * L + j) * L + i] = (T[i * LP + j] + T[j * LP + i]) * inv_sqrt_d - s;
+    kt_out[((size_t)b * L + j) * L + i] = (__ldg(dsb + (size_t)i * L + j) + __ldg(dsb + (size_t)j * L + i)) * inv_sqrt_d - s;
   }
-  for (int i = tid; i < L; i += blockDim.x) {
+  for (int ri = tid >> 5; ri < nrows; ri += (int)(blockDim.x >> 5)) {
+    const int i = blockIdx.x + ri * gridDim.x, lane = tid & 31;
     float z = 0.f;
-    for (int l = 0; l < L; ++l) z = fmaf(M[l * LP + i], as[l] * mus[l], z);
-    z_out[b * L + i] = z;
+    for (int l = lane; l < L; l += 32) z = fmaf(M[l * LP + i], as[l] * __ldg(mu + b * L + l), z);
+    z = warp_sum(z);
+    if (lane == 0) z_out[b * L + i] = z;
   }
-  if (tid == 0) hbar_out[b] = hbar;
+  if (blockIdx.x == 0 && tid == 0) hbar_out[b] = __ldg(hsum + b) / (float)D;
 }
 
 // ---------------------------------------------------------------------------
@@ -420,21 +473,23 @@ void launch_bagattn_forward(const float* x, const float* gamma, const float* bet
     cudaFuncSetAttribute(ba_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     launch_k(ba_gram_kernel, dim3(per_bag, n_bags), dim3(256), smem, st, x, (const float*)m, gc, L, LP, D);
   }
+  const int rgroups = 8;           // row groups of the L x L kernels: 8 blocks of 8 warps per bag
   {
     LaunchScope scope("bagattn_small_fwd", st);
-    const size_t smem = (size_t)(2 * L * LP + 3 * LP) * sizeof(float);
-    cudaFuncSetAttribute(ba_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    launch_k(ba_small_fwd_kernel, dim3(n_bags), dim3(512), smem, st, (const float*)gc, (const float*)m, a, r, mu, v, c, L, LP, D, eps);
+    const size_t smem = (size_t)(L * LP + LP + 8 * LP) * sizeof(float);
+    cudaFuncSetAttribute(ba_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    launch_k(ba_small_fwd_kernel, dim3(rgroups, n_bags), dim3(256), smem, st, (const float*)gc, (const float*)m, a, r, mu, L, LP, D,
+             eps);
   }
   {
     LaunchScope scope("bagattn_out", st);
-    launch_k(ba_out_kernel, dim3(ceil_div(D, 256), n_bags), dim3(256), 0, st, x, (const float*)v, (const float*)c, gamma, beta, out,
-             L, D);
+    launch_k(ba_out_kernel, dim3(ceil_div(D, 256), n_bags), dim3(256), 0, st, x, (const float*)a, (const float*)r, (const float*)mu, v,
+             c, gamma, beta, out, L, D);
   }
 }
 
-size_t bagattn_backward_ws_floats(int n_bags, int L) {   // w' [L], z [L], hsum, hbar (padded), K^T [L, L] per bag
-  return (size_t)n_bags * ((size_t)2 * L + 8 + (size_t)L * L);
+size_t bagattn_backward_ws_floats(int n_bags, int L) {   // w', z, a [L], hsum, hbar (padded), K^T, dS [L, L] per bag
+  return (size_t)n_bags * ((size_t)3 * L + 8 + 2 * (size_t)L * L);
 }
 
 void launch_bagattn_backward(const float* x, const float* g, const float* gamma, const float* saved, float* dx, float* dgamma,
@@ -451,18 +506,28 @@ void launch_bagattn_backward(const float* x, const float* g, const float* gamma,
   float* z = wp + (size_t)n_bags * L;
   float* hsum = z + (size_t)n_bags * L;
   float* hbar = hsum + (size_t)n_bags * 4;
-  float* kt = hbar + (size_t)n_bags * 4;
+  float* as = hbar + (size_t)n_bags * 4;
+  float* kt = as + (size_t)n_bags * L;
+  float* ds = kt + (size_t)n_bags * L * L;
   cudaMemsetAsync(ws, 0, ((size_t)n_bags * 2 * L + (size_t)n_bags * 8) * sizeof(float), st);
   {
     LaunchScope scope("bagattn_bwd_vec", st);
     launch_k(ba_bwd_vec_kernel, dim3(ceil_div(D, 256), n_bags), dim3(256), 0, st, x, g, v, c, gamma, wp, hsum, dgamma, L, D);
   }
+  const int rgroups = 8;
   {
-    LaunchScope scope("bagattn_small_bwd", st);
-    const size_t smem = (size_t)(3 * L * LP + 5 * LP) * sizeof(float);
-    cudaFuncSetAttribute(ba_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    launch_k(ba_small_bwd_kernel, dim3(n_bags), dim3(512), smem, st, gc, a, m, r, mu, (const float*)wp, (const float*)hsum, kt, z,
-             hbar, L, LP, D);
+    LaunchScope scope("bagattn_small_bwd_rows", st);
+    const size_t smem = (size_t)(L * LP + 2 * LP + 8 * LP) * sizeof(float);
+    cudaFuncSetAttribute(ba_small_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    launch_k(ba_small_bwd_rows_kernel, dim3(rgroups, n_bags), dim3(256), smem, st, gc, a, m, r, mu, (const float*)wp,
+             (const float*)hsum, ds, as, L, LP, D);
+  }
+  {
+    LaunchScope scope("bagattn_small_bwd_k", st);
+    const size_t smem = (size_t)(L * LP + LP) * sizeof(float);
+    cudaFuncSetAttribute(ba_small_bwd_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    launch_k(ba_small_bwd_k_kernel, dim3(rgroups * 2, n_bags), dim3(256), smem, st, a, (const float*)ds, (const float*)as, mu,
+             (const float*)hsum, kt, z, hbar, L, LP, D);
   }
   {
     LaunchScope scope("bagattn_dx", st);
