@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) ba_rowmean_kernel(const float* __restrict
   __shared__ float red[8];
   const float* row = x + (size_t)blockIdx.x * D;
   float s = 0.f;
+#pragma unroll 8
   for (int d = threadIdx.x; d < D; d += blockDim.x) s += __ldg(row + d);
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -220,8 +221,8 @@ __global__ void __launch_bounds__(256) ba_out_kernel(const float* __restrict__ x
   if (d >= D) return;
   const float* xb = x + (size_t)b * L * D + d;
   float s = 0.f;
-#pragma unroll 4
-  for (int l = 0; l < L; ++l) s = fmaf(vs[l], __ldg(xb + (size_t)l * D), s);
+#pragma unroll 16
+  for (int l = 0; l < L; ++l) s = fmaf(vs[l], __ldg(xb + (size_t)l * D), s);      // (few blocks: keep 16 loads in flight)
   out[(size_t)b * D + d] = fmaf(__ldg(gamma + d) / (float)L, s - cs, __ldg(beta + d));
 }
 
