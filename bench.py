@@ -579,7 +579,7 @@ def run_b200(args, wl, rank, world, local_rank):
                                  ("heads' region overlapped with the encoder backward + encoder region at the end"
                                   if trainer.split_backward else "one flat all-reduce after backward")),
                    "precision_mode": {
-                       "fp32": "fp32: CUDA-core FFMA DFT GEMMs (1e-5 parity mode)",
+                       "fp32": "fp32 (1e-5 parity mode): CUDA-core FFMA DFT GEMMs; the GELU-on-load W-forward of the per-snapshot net on tcgen05 with 3xTF32 operands (1 launch per step)",
                        "tf32": "tf32: all four DFT GEMMs of every 2-D spectral layer on tcgen05 (csrc/tc_layer.cu), fp32 accumulate "
                                "in tensor memory (bound 2e-3 outputs / 1e-2 grads)",
                        "tf32x3": "tf32x3: the same tcgen05 kernels with hi + lo split operands (3 MMAs per K step), meets the 1e-5 bound",

@@ -388,10 +388,11 @@ bool launch_wfwd(const Plan* pl, const float* x, float2* out, int rows, int act,
   // low parts, three MMAs per K step: fp32-level accuracy).  A shape that does not fit the tensor-core kernel's
   // shared-memory budget runs the FFMA kernel below: the return value says which (true = tcgen05), the profile
   // tag names the kernel, and the first such fallback of a shape is reported on stderr.
-  // (experiment, BDN_WFWD_TC_AUTO=1: in fp32 mode the many-row, few-mode W-forward of the per-snapshot net also runs the
-  // tcgen05 kernel with 3xTF32 operands -- fp32-level accuracy, r1: 22.6 vs 23.6 us plain, 26.6 vs 30.8 us with GELU)
-  static const int tc_auto = [] { const char* e = getenv("BDN_WFWD_TC_AUTO"); return e ? atoi(e) : 0; }();
-  if (tc_auto && prec == 0 && rows >= 50000 && pl->m2 < 20 && tc_wfwd_supported(pl, x, true) &&
+  // fp32 mode, many rows, few modes, GELU on load (layers > 0 of the per-snapshot net): the tcgen05 kernel with 3xTF32
+  // operands (fp32-level accuracy) is the faster one -- r2d: 23.8 vs 27.0 us per launch; without the GELU it is not
+  // (21.8 vs 21.0 us) and the FFMA kernel stays.  BDN_WFWD_TC_AUTO=0 switches this off, 2 extends it to the plain case.
+  static const int tc_auto = [] { const char* e = getenv("BDN_WFWD_TC_AUTO"); return e ? atoi(e) : 1; }();
+  if (tc_auto && (act || tc_auto == 2) && prec == 0 && rows >= 50000 && pl->m2 < 20 && tc_wfwd_supported(pl, x, true) &&
       launch_wfwd_tc(pl, x, out, rows, act, true, st))
     return true;
   if (wfwd_uses_tensor_cores(pl, x, rows, prec) && launch_wfwd_tc(pl, x, out, rows, act, prec == 2, st)) return true;
