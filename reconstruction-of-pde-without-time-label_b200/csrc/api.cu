@@ -905,7 +905,7 @@ int bdn_nio_tail_forward(const float* w, const float* basis, const float* b0, co
                          const float* fc0_b, float* out, float* wbar_saved, int32_t n_bags, int32_t n_keep, int32_t p,
                          int32_t npix, int32_t grid_dim, int32_t width, void* stream) {
   if (n_bags < 0 || n_keep < 1 || p < 1 || npix < 1 || grid_dim < 1 || width < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
-  if (p > 64) return set_error(BDN_ERR_UNSUPPORTED, "n_basis=%d > 64 not built", p);
+  if (p > 256) return set_error(BDN_ERR_UNSUPPORTED, "n_basis=%d > 256 not built", p);
   if (n_bags == 0) return BDN_OK;
   if (!w || !basis || !b0 || !grid || !fc0_w || !fc0_b || !out || !wbar_saved) return set_error(BDN_ERR_INVALID, "null pointer argument");
   launch_nio_tail(w, basis, b0, grid, fc0_w, fc0_b, out, wbar_saved, n_bags, n_keep, p, npix, grid_dim, width, (cudaStream_t)stream);
@@ -916,7 +916,7 @@ int bdn_nio_tail_backward(const float* g, const float* basis, const float* wbar_
                           float* g_basis, float* g_b0, float* g_wbar_ws, int32_t n_bags, int32_t n_keep, int32_t p, int32_t npix,
                           int32_t grid_dim, int32_t width, void* stream) {
   if (n_bags < 0 || n_keep < 1 || p < 1 || npix < 1 || grid_dim < 1 || width < 1) return set_error(BDN_ERR_INVALID, "bad sizes");
-  if (p > 64) return set_error(BDN_ERR_UNSUPPORTED, "n_basis=%d > 64 not built", p);
+  if (p > 256) return set_error(BDN_ERR_UNSUPPORTED, "n_basis=%d > 256 not built", p);
   if (!g_basis || !g_b0) return set_error(BDN_ERR_INVALID, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(g_basis, 0, (size_t)npix * p * sizeof(float), st);

@@ -920,7 +920,7 @@ void launch_pool_lift_bwd(const float* g, const float* w0, float* gpool, int n_b
 // the reference is never formed.
 //   out[b, x, j] = fc0_b[j] + sum_d W0[j, d] grid[x, d] + W0[j, gd] * (sum_q wbar[b, q] basis[x, q] + b0) / sqrt(p)
 // ===========================================================================
-constexpr int TAIL_MAXP = 64;
+constexpr int TAIL_MAXP = 256;
 
 __global__ void __launch_bounds__(128) nio_tail_fwd_kernel(const float* __restrict__ w, const float* __restrict__ basis,
                                                            const float* __restrict__ b0, const float* __restrict__ grid,
@@ -931,13 +931,13 @@ __global__ void __launch_bounds__(128) nio_tail_fwd_kernel(const float* __restri
   pdl_wait();
   __shared__ float wbar[TAIL_MAXP];
   const int b = blockIdx.y;
-  if ((int)threadIdx.x < p) {
-    const float* wp = w + (size_t)b * L * p + threadIdx.x;
+  for (int q = threadIdx.x; q < p; q += blockDim.x) {
+    const float* wp = w + (size_t)b * L * p + q;
     float s = 0.f;
     for (int l = 0; l < L; ++l) s += __ldg(wp + (size_t)l * p);
     s /= (float)L;
-    wbar[threadIdx.x] = s;
-    if (blockIdx.x == 0) wbar_out[b * p + threadIdx.x] = s;
+    wbar[q] = s;
+    if (blockIdx.x == 0) wbar_out[b * p + q] = s;
   }
   __syncthreads();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;

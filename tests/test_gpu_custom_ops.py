@@ -166,6 +166,29 @@ def test_pooled_tails_vs_oracle():
         assert rel_err(a.grad, r.grad) < 1e-4      # TF32-free cuBLAS GEMM vs fp64; cancelling sums over n*n points
 
 
+@pytest.mark.parametrize("n_bags,n_keep,p,grid_shape", [(4, 75, 25, (128,)), (2, 9, 130, (11, 7)), (3, 100, 64, (61, 61))])
+def test_nio_tail_other_basis_sizes_and_grids(n_bags, n_keep, p, grid_shape):
+    """deeponet_pool_contract_lift (the one-kernel NIO tail) in 1-D and 2-D, with more basis functions than threads of a
+    block column (p = 130), against DeepOnetNoBiasOrg.forward + bag mean + detached lift in fp64."""
+    g = torch.Generator().manual_seed(p)
+    npix = int(np.prod(grid_shape))
+    gd = len(grid_shape)
+    w, basis, b0 = torch.randn(n_bags, n_keep, p, generator=g), torch.randn(npix, p, generator=g), torch.tensor(-0.4)
+    grid = torch.rand(*grid_shape, gd, generator=g)
+    fc0_w, fc0_b = torch.randn(6, gd + 1, generator=g), torch.randn(6, generator=g)
+    gy = torch.randn(n_bags, *grid_shape, 6, generator=g)
+    dev = [t.to(DEV).requires_grad_(True) for t in (w, basis, b0)]
+    got = NSO.deeponet_pool_contract_lift(*dev, grid.to(DEV), fc0_w.to(DEV), fc0_b.to(DEV))
+    got.backward(gy.to(DEV))
+    ref = [t.double().requires_grad_(True) for t in (w, basis, b0)]
+    s = O.deeponet_forward({"deeponet.b0": ref[2]}, ref[0], ref[1]).reshape(n_bags, n_keep, *grid_shape)
+    want = O.bag_pool_lift(s, grid.double(), fc0_w.double(), fc0_b.double())
+    want.backward(gy.double())
+    assert rel_err(got, want) < TOL
+    for a, r in zip(dev, ref):
+        assert rel_err(a.grad, r.grad) < 2e-5
+
+
 @pytest.mark.parametrize("n_heads,c,shape", [(2, 1, (4, 61, 61)), (1, 1, (4, 128)), (2, 2, (3, 7, 5)), (3, 1, (40, 80, 80))])
 def test_heads_mse_matches_mse_loss_on_the_concatenation(n_heads, c, shape):
     """criterion(model(inputs, grid), outputs) with MSELoss (2d_FPE/train_fno.py:116,146-147) without the torch.cat:
