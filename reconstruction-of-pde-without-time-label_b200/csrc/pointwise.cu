@@ -527,7 +527,8 @@ template <int CP, int NOUT, int JS, int PP>
 static void launch_project_t(const ProjArgs& a, float* out, long total, cudaStream_t st) {
   constexpr int TILE = PROJ_THREADS / JS * PP;
   const long ntiles = (total + TILE - 1) / TILE;
-  const int grid = (int)(ntiles < 148L * 8 ? ntiles : 148L * 8);
+  static const long fcap = [] { const char* e = getenv("BDN_PROJ_FWD_CAP"); return e ? atol(e) : 148L * 8; }();   // (tuning knob)
+  const int grid = (int)(ntiles < fcap ? ntiles : fcap);
   const size_t smem = (size_t)(a.hidden * CP + a.hidden + a.c_out * a.hidden) * sizeof(float);
   cudaFuncSetAttribute(project_kernel<CP, NOUT, JS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);   // hidden = 512, width 32, 4 outputs: 76 KB
   launch_k(project_kernel<CP, NOUT, JS, PP>, dim3(grid), dim3(PROJ_THREADS), smem, st, a, out);
@@ -537,11 +538,14 @@ void launch_project(const ProjArgs& a, float* out, cudaStream_t st) {
   LaunchScope scope("project", st, a.width);
   const long total = (long)a.images * a.out_h * a.out_w;
   const bool many = proj_many_pixels(total);
+  static const int ppf = [] { const char* e = getenv("BDN_PROJ_FWD_PP"); return e ? atoi(e) : 4; }();   // (tuning knob: 2, 4, 8)
   dispatch_cp(a.width, [&](auto cp) {
     constexpr int CP = decltype(cp)::value;
     constexpr int PPM = CP <= 8 ? 4 : 2;
     if (a.c_out == 1) {
-      if (many) launch_project_t<CP, 1, 1, PPM>(a, out, total, st);
+      if (many && CP <= 8 && ppf == 2) launch_project_t<CP, 1, 1, 2>(a, out, total, st);
+      else if (many && CP <= 8 && ppf == 8) launch_project_t<CP, 1, 1, 8>(a, out, total, st);
+      else if (many) launch_project_t<CP, 1, 1, PPM>(a, out, total, st);
       else launch_project_t<CP, 1, 8, 1>(a, out, total, st);
     } else {
       if (many) launch_project_t<CP, PROJ_MAX_OUT, 1, 2>(a, out, total, st);

@@ -4,7 +4,7 @@
 #   gpurun -- 'bash tools/gpu_ab.sh "A=1" "BDN_WFWD_FOLD=0" "BDN_PROJ_BWD_PP8=1"'
 # Knobs (csrc/*.cu, read once per process): BDN_PDL (0/1/2), BDN_CORE_WSTAGE, BDN_CORE_ONETAB, BDN_WFWD_FOLD (0/1/2),
 # BDN_WFWD_TC_AUTO (0/1/2), BDN_GW_TILED, BDN_LIFT_BAGS4, BDN_PROJ_BWD_CAP8, BDN_PROJ_BWD_PP8 (1/2/4),
-# BDN_WINV_TILE ("lines,channels"), BDN_MSE_PIX_PER_BLOCK; build-time: BDN_NVCC_EXTRA="-DBDN_PDL_LATE=1".
+# BDN_WINV_TILE ("lines,channels"), BDN_MSE_PIX_PER_BLOCK, BDN_PROJ_FWD_PP (2/4/8), BDN_PROJ_FWD_CAP (blocks); build-time: BDN_NVCC_EXTRA="-DBDN_PDL_LATE=1".
 O=gpurun_out
 mkdir -p $O
 EXTRA=${BENCH_ARGS:-"--steps 50 --warmup 5 --top 40 --no-cpu-baseline"}
