@@ -506,6 +506,46 @@ def run_b200(args, wl, rank, world, local_rank):
     prof = ops.profile_end()
     np.random.set_state(np_state)
 
+    # The same steps once more under CUDA-graph replay with the CUPTI kernel trace (torch.profiler): warm per-kernel
+    # durations INSIDE the replayed step (event pairs cannot be recorded into a graph; the eager pass above overstates
+    # kernels below ~15 us and misses the overlap of the two heads).  Rank 0 of a single-GPU run only.
+    replay = None
+    if world == 1 and not args.no_graphs:
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            trainer.enable_graphs(True)
+            for i in range(2):
+                step_resident(i)
+            np.random.set_state(np_state)
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as tp:
+                for i in range(prof_steps):
+                    step_resident(i)
+                torch.cuda.synchronize()
+            np.random.set_state(np_state)
+            evs = sorted((e for e in tp.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                         key=lambda e: e.time_range.start)
+            per_kernel, busy, cur_end = {}, 0.0, None
+            for e in evs:
+                s0, s1 = e.time_range.start, e.time_range.end
+                v = per_kernel.setdefault(e.name.split("(")[0][:70], [0, 0.0])
+                v[0] += 1
+                v[1] += s1 - s0
+                if cur_end is None or s0 > cur_end:
+                    busy += s1 - s0
+                    cur_end = s1
+                elif s1 > cur_end:
+                    busy += s1 - cur_end
+                    cur_end = s1
+            span = (max(e.time_range.end for e in evs) - evs[0].time_range.start) if evs else 0.0
+            replay = {"steps": prof_steps, "kernels_per_step": len(evs) / prof_steps, "span_us_per_step": span / prof_steps,
+                      "gpu_busy_us_per_step": busy / prof_steps, "sum_kernel_us_per_step": sum(v[1] for v in per_kernel.values()) / prof_steps,
+                      "per_kernel": per_kernel, "source": "CUPTI kernel trace (torch.profiler) of the same steps under graph replay; kernel durations and GPU-busy "
+                                "time are the tracer's, the span includes its own overhead (the timed region above runs untraced)"}
+        except Exception as ex:          # the trace is explanatory: a profiler problem must not cost the bench line
+            replay = {"error": f"{type(ex).__name__}: {ex}"}
+            np.random.set_state(np_state)
+
     value = world * batch * args.steps / (ms / 1e3)
     e2e = world * batch * args.steps / (ms_e2e / 1e3)
     if rank != 0:
@@ -546,6 +586,16 @@ def run_b200(args, wl, rank, world, local_rank):
     roof_all = [r for r in (roof(k, v) for k, v in kernels) if r]
     if roof_all:
         roofline = dict(roof_all[0])
+        if replay and "per_kernel" in replay:
+            # the dominant kernel's duration inside the replayed step (projection kernels: symbol name = tag + width)
+            stem, _, tag = roofline["kernel"].partition("/")
+            for sym, (n, us) in replay["per_kernel"].items():
+                if f"::{stem}_kernel<{tag}," in sym and n:
+                    us1 = us / n
+                    ach = roofline["algorithmic_bytes_per_launch"] / (us1 * 1e-6) / 1e9
+                    roofline["graph_replay"] = {"us_per_launch": us1, "achieved": ach, "frac": ach / hbm_peak,
+                                                "share_of_kernel_time": us / max(sum(v[1] for v in replay["per_kernel"].values()), 1e-9)}
+                    break
         if roofline["kernel"].startswith("project"):
             roofline["note"] = ("dominant kernel is instruction-issue bound, not HBM-bound: 128 exact-GELU evaluations per "
                                 "pixel, recomputed in backward (ncu --set full, profiles/r1n_ncu_full_eager_step_summary.txt: "
@@ -601,6 +651,7 @@ def run_b200(args, wl, rank, world, local_rank):
                                  for r in roof_all[:10] if not r["kernel"].startswith("project")][:6],
         "cpu_baseline": cpu,
         "tensor_pipe_pct": tensor_pipe,
+        "replay_timeline": ({k: v for k, v in replay.items() if k != "per_kernel"} if replay else None),
         "top_kernels": top,
         "kernel_time_us_per_step": total_ms * 1e3 / prof_steps,
         "final_loss": losses[-1] if losses else None,
