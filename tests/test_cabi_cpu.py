@@ -120,3 +120,20 @@ def test_gelu_formula_accuracy_in_fp32():
     gelu = (np.maximum(x, f(0)) - (np.abs(x) * q).astype(f)).astype(np.float64)
     assert np.abs(gelu[::40] - xd[::40] * ref).max() <= 5e-7
     assert np.abs(e.astype(np.float64) - np.exp(-0.5 * xd * xd) / math.sqrt(2 * math.pi)).max() <= 1e-7
+
+
+def test_concurrent_loads_see_a_whole_library():
+    """One process per GPU imports the package at the same time under torchrun: the check-and-build runs under a file
+    lock and the library is put in place by an atomic rename (a 2-GPU run once loaded a half-written .so).  Four
+    processes load it at once; every one must get a library that answers."""
+    import subprocess
+    import sys
+    code = ("from blindno_b200 import _lib, build; import os; L = _lib.lib(); "
+            "assert os.path.exists(os.path.join(build.LIBDIR, '.build.lock')) or os.path.exists(build.LIBPATH); "
+            "print(L.bdn_abi_version())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = [subprocess.Popen([sys.executable, "-c", code], cwd=root, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for _ in range(4)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-400:] for o in outs]
+    assert len({o[0].strip() for o in outs}) == 1
